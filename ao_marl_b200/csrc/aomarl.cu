@@ -1,0 +1,692 @@
+// libaomarl.so -- C ABI implementation (see include/aomarl.h for the contract and reference citations).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/aomarl.h"
+#include "atmos_kernels.cuh"
+#include "gemm_kernels.cuh"
+#include "rtc_kernels.cuh"
+#include "wfs_kernels.cuh"
+
+static char g_create_error[512] = "";
+
+struct aom_ctx {
+  aom_config cfg;
+  char err[512];
+  int device;
+  int num_sms;
+  uint64_t launches;
+  // tables
+  void* tab[AOM_T_COUNT][AOM_MAX_LAYERS];
+  size_t tab_bytes[AOM_T_COUNT][AOM_MAX_LAYERS];
+  // atmosphere
+  float* screen[AOM_MAX_LAYERS];
+  int* ox[AOM_MAX_LAYERS];
+  int* oy[AOM_MAX_LAYERS];
+  uint32_t* ext_count[AOM_MAX_LAYERS];
+  double accx[AOM_MAX_LAYERS], accy[AOM_MAX_LAYERS];
+  uint32_t *k0, *k1;
+  float *Z, *zref, *newcol;
+  int ldz_max, ldn_max;
+  // sensor / rtc
+  float *slopes_frame, *slopes, *err_v, *com, *com1, *volts, *com_before;
+  float *bincube, *phase;
+  const float* cube_override;
+  int lds, lda, ldm;
+  float gain;
+  int closed;
+  uint32_t frame;
+  // RL
+  float *modes, *modes_before, *modes_res, *state, *hist, *reward, *action, *action_mean, *strehl;
+  int ldst, ldact, hist_head;
+  uint32_t step;
+  float *aX, *aH1, *aH2, *aHO;
+  int ld_ain, ld_ah, ld_aho;
+  bool seeded;
+};
+
+static int fail(aom_ctx* c, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(c ? c->err : g_create_error, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(ctx, AOM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define KCHECK()                                                                                  \
+  do {                                                                                            \
+    ctx->launches++;                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(ctx, AOM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T));
+  return e;
+}
+
+extern "C" size_t aom_config_size(void) { return sizeof(aom_config); }
+
+extern "C" const char* aom_last_error(const aom_ctx* ctx) { return ctx ? ctx->err : g_create_error; }
+
+extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
+  aom_ctx* ctx = nullptr;
+  if (!cfg || !out) return fail(nullptr, AOM_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, AOM_ERR_CUDA, "no CUDA device available: libaomarl has no CPU path");
+  if (cfg->n_env < 1 || cfg->n_env > 65535) return fail(nullptr, AOM_ERR_INVALID, "n_env must be in [1, 65535]");
+  if (cfg->n_layers < 0 || cfg->n_layers > AOM_MAX_LAYERS) return fail(nullptr, AOM_ERR_INVALID, "n_layers out of range");
+  if (cfg->pdiam != 16 || cfg->npix != 16)
+    return fail(nullptr, AOM_ERR_UNSUPPORTED, "only pdiam = npix = 16 Shack-Hartmann subapertures are implemented");
+  if (!((cfg->nfft == 64 && cfg->nrebin == 2) || (cfg->nfft == 128 && cfg->nrebin == 4)))
+    return fail(nullptr, AOM_ERR_UNSUPPORTED, "only (Nfft, nrebin) = (64, 2) or (128, 4) are implemented");
+  if (cfg->stamp_size > 64) return fail(nullptr, AOM_ERR_UNSUPPORTED, "actuator stamp larger than 64 pixels");
+  if (cfg->pzt_pitch > 0 && (cfg->stamp_size + 15 + cfg->pzt_pitch - 1) / cfg->pzt_pitch + 1 > WFS_NG_MAX)
+    return fail(nullptr, AOM_ERR_UNSUPPORTED, "actuator pitch too small for the %d-cell neighbourhood", WFS_NG_MAX);
+  if (cfg->delay != 0 && cfg->delay != 1) return fail(nullptr, AOM_ERR_UNSUPPORTED, "controller delay must be 0 or 1 frame");
+
+  ctx = (aom_ctx*)calloc(1, sizeof(aom_ctx));
+  if (!ctx) return fail(nullptr, AOM_ERR_INVALID, "out of host memory");
+  ctx->cfg = *cfg;
+  ctx->gain = cfg->gain;
+  ctx->closed = 1;
+  *out = ctx;   // returned even on failure so that aom_last_error / aom_destroy work
+  CU(cudaGetDevice(&ctx->device));
+  CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  const size_t E = cfg->n_env;
+  ctx->lds = AOM_LD(cfg->nslopes);
+  ctx->lda = AOM_LD(cfg->nactu);
+  ctx->ldm = AOM_LD(cfg->nmodes > 0 ? cfg->nmodes : 1);
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    size_t N = cfg->screen_dim[l];
+    CU(dalloc(&ctx->screen[l], E * N * N));
+    CU(dalloc(&ctx->ox[l], E));
+    CU(dalloc(&ctx->oy[l], E));
+    CU(dalloc(&ctx->ext_count[l], E));
+    int ldz = AOM_LD(cfg->stencil_size[l] + (int)N);
+    if (ldz > ctx->ldz_max) ctx->ldz_max = ldz;
+    if (AOM_LD((int)N) > ctx->ldn_max) ctx->ldn_max = AOM_LD((int)N);
+  }
+  CU(dalloc(&ctx->k0, E));
+  CU(dalloc(&ctx->k1, E));
+  if (cfg->n_layers > 0) {
+    CU(dalloc(&ctx->Z, E * ctx->ldz_max));
+    CU(dalloc(&ctx->zref, E));
+    CU(dalloc(&ctx->newcol, E * ctx->ldn_max));
+  }
+  CU(dalloc(&ctx->slopes_frame, E * ctx->lds));
+  CU(dalloc(&ctx->slopes, E * ctx->lds));
+  CU(dalloc(&ctx->err_v, E * ctx->lda));
+  CU(dalloc(&ctx->com, E * ctx->lda));
+  CU(dalloc(&ctx->com1, E * ctx->lda));
+  CU(dalloc(&ctx->volts, E * ctx->lda));
+  CU(dalloc(&ctx->com_before, E * ctx->lda));
+  CU(dalloc(&ctx->strehl, E * 4));
+  if (cfg->nmodes > 0) {
+    CU(dalloc(&ctx->modes, E * ctx->ldm));
+    CU(dalloc(&ctx->modes_before, E * ctx->ldm));
+    CU(dalloc(&ctx->modes_res, E * ctx->ldm));
+  }
+  if (cfg->state_dim > 0) {
+    ctx->ldst = AOM_LD(cfg->state_dim);
+    CU(dalloc(&ctx->state, E * ctx->ldst));
+    if (cfg->n_hist > 0) CU(dalloc(&ctx->hist, (size_t)cfg->n_hist * E * cfg->state_modes));
+  }
+  if (cfg->action_dim > 0) {
+    ctx->ldact = AOM_LD(cfg->action_dim);
+    CU(dalloc(&ctx->action, E * ctx->ldact));
+    CU(dalloc(&ctx->action_mean, E * ctx->ldact));
+  }
+  if (cfg->n_agents > 0) {
+    CU(dalloc(&ctx->reward, E * cfg->n_agents));
+    ctx->ld_ain = AOM_LD(cfg->actor_in);
+    ctx->ld_ah = AOM_LD(cfg->actor_hidden);
+    ctx->ld_aho = AOM_LD(2 * cfg->actor_out);
+    size_t A = cfg->n_agents;
+    CU(dalloc(&ctx->aX, A * E * ctx->ld_ain));
+    CU(dalloc(&ctx->aH1, A * E * ctx->ld_ah));
+    CU(dalloc(&ctx->aH2, A * E * ctx->ld_ah));
+    CU(dalloc(&ctx->aHO, A * E * ctx->ld_aho));
+  }
+  CU(cudaFuncSetAttribute(wfs_frame_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfs_smem_bytes<4>()));
+  CU(cudaFuncSetAttribute(wfs_frame_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfs_smem_bytes<8>()));
+  return AOM_OK;
+}
+
+extern "C" void aom_destroy(aom_ctx* ctx) {
+  if (!ctx) return;
+  for (int t = 0; t < AOM_T_COUNT; ++t)
+    for (int l = 0; l < AOM_MAX_LAYERS; ++l) cudaFree(ctx->tab[t][l]);
+  for (int l = 0; l < AOM_MAX_LAYERS; ++l) {
+    cudaFree(ctx->screen[l]); cudaFree(ctx->ox[l]); cudaFree(ctx->oy[l]); cudaFree(ctx->ext_count[l]);
+  }
+  void* bufs[] = {ctx->k0, ctx->k1, ctx->Z, ctx->zref, ctx->newcol, ctx->slopes_frame, ctx->slopes, ctx->err_v,
+                  ctx->com, ctx->com1, ctx->volts, ctx->com_before, ctx->bincube, ctx->phase, ctx->modes,
+                  ctx->modes_before, ctx->modes_res, ctx->state, ctx->hist, ctx->reward, ctx->action,
+                  ctx->action_mean, ctx->strehl, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO};
+  for (void* b : bufs) cudaFree(b);
+  free(ctx);
+}
+
+static size_t table_expected_bytes(const aom_ctx* ctx, int t, int index) {
+  const aom_config& c = ctx->cfg;
+  const size_t A = c.n_agents;
+  switch (t) {
+    case AOM_T_AB: return (size_t)c.screen_dim[index] * AOM_LD(c.stencil_size[index] + c.screen_dim[index]) * 4;
+    case AOM_T_STENCIL: return (size_t)c.stencil_size[index] * 4;
+    case AOM_T_MPUPIL: return (size_t)c.n * c.n * 4;
+    case AOM_T_HALFXY: return 256 * 4;
+    case AOM_T_SUB_X0: case AOM_T_SUB_Y0: case AOM_T_FLUX: return (size_t)c.nvalid * 4;
+    case AOM_T_STAMP1D: return (size_t)c.stamp_size * 4;
+    case AOM_T_ACT_MAP: return (size_t)c.pzt_grid_n * c.pzt_grid_n * 4;
+    case AOM_T_TT_PLANES: return (size_t)2 * c.tt_dim * c.tt_dim * 4;
+    case AOM_T_CMAT: return (size_t)c.nactu * AOM_LD(c.nslopes) * 4;
+    case AOM_T_V2M: return (size_t)c.nmodes * AOM_LD(c.nactu) * 4;
+    case AOM_T_M2V: return (size_t)c.nactu * AOM_LD(c.nmodes) * 4;
+    case AOM_T_FREEDOM: return (size_t)c.nmodes * 4;
+    case AOM_T_ACTION_MAP: return (size_t)c.action_dim * 4;
+    case AOM_T_STATE_MAP: case AOM_T_NORM_DM_MEAN: case AOM_T_NORM_DM_STD: case AOM_T_NORM_RES_MEAN:
+    case AOM_T_NORM_RES_STD: return (size_t)c.state_modes * 4;
+    case AOM_T_AGENT_IDX: return A * c.actor_in * 4;
+    case AOM_T_AGENT_ACT: return A * c.actor_out * 4;
+    case AOM_T_AGENT_REWARD: return A * 2 * 4;
+    case AOM_T_ACTOR_W1: return A * c.actor_hidden * AOM_LD(c.actor_in) * 4;
+    case AOM_T_ACTOR_B1: case AOM_T_ACTOR_B2: return A * c.actor_hidden * 4;
+    case AOM_T_ACTOR_W2: return A * c.actor_hidden * AOM_LD(c.actor_hidden) * 4;
+    case AOM_T_ACTOR_WH: return A * 2 * c.actor_out * AOM_LD(c.actor_hidden) * 4;
+    case AOM_T_ACTOR_BH: return A * 2 * c.actor_out * 4;
+  }
+  return 0;
+}
+
+extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* host, size_t nbytes) {
+  if (!ctx || !host) return fail(ctx, AOM_ERR_INVALID, "null argument");
+  if (table < 0 || table >= AOM_T_COUNT || index < 0 || index >= AOM_MAX_LAYERS)
+    return fail(ctx, AOM_ERR_INVALID, "table id %d / index %d out of range", table, index);
+  size_t want = table_expected_bytes(ctx, table, index);
+  if (want != nbytes)
+    return fail(ctx, AOM_ERR_INVALID, "Dimension mismatch: table %d[%d] expects %zu bytes, got %zu", table, index, want, nbytes);
+  if (ctx->tab[table][index]) { cudaFree(ctx->tab[table][index]); ctx->tab[table][index] = nullptr; }
+  CU(cudaMalloc(&ctx->tab[table][index], nbytes ? nbytes : 4));
+  CU(cudaMemcpy(ctx->tab[table][index], host, nbytes, cudaMemcpyHostToDevice));
+  ctx->tab_bytes[table][index] = nbytes;
+  return AOM_OK;
+}
+
+#define NEED(t, i)                                                                     \
+  do {                                                                                 \
+    if (!ctx->tab[t][i]) return fail(ctx, AOM_ERR_STATE, "table %s[%d] not uploaded", #t, i); \
+  } while (0)
+
+extern "C" int aom_device_count_launches(const aom_ctx* ctx, uint64_t* n) {
+  if (!ctx || !n) return AOM_ERR_INVALID;
+  *n = ctx->launches;
+  return AOM_OK;
+}
+
+extern "C" int aom_get_buffer(aom_ctx* ctx, int buffer, int index, void** dptr, size_t* count) {
+  if (!ctx || !dptr || !count) return fail(ctx, AOM_ERR_INVALID, "null argument");
+  const aom_config& c = ctx->cfg;
+  const size_t E = c.n_env;
+  void* p = nullptr;
+  size_t n = 0;
+  switch (buffer) {
+    case AOM_B_SCREEN:
+      if (index < 0 || index >= c.n_layers) return fail(ctx, AOM_ERR_INVALID, "layer index out of range");
+      p = ctx->screen[index]; n = E * c.screen_dim[index] * c.screen_dim[index]; break;
+    case AOM_B_RING_OX:
+      if (index < 0 || index >= c.n_layers) return fail(ctx, AOM_ERR_INVALID, "layer index out of range");
+      p = ctx->ox[index]; n = E; break;
+    case AOM_B_RING_OY:
+      if (index < 0 || index >= c.n_layers) return fail(ctx, AOM_ERR_INVALID, "layer index out of range");
+      p = ctx->oy[index]; n = E; break;
+    case AOM_B_SLOPES: p = ctx->slopes; n = E * ctx->lds; break;
+    case AOM_B_ERR: p = ctx->err_v; n = E * ctx->lda; break;
+    case AOM_B_COM: p = ctx->com; n = E * ctx->lda; break;
+    case AOM_B_VOLTS: p = ctx->volts; n = E * ctx->lda; break;
+    case AOM_B_BINCUBE:
+      if (!ctx->bincube) CU(dalloc(&ctx->bincube, E * c.nvalid * 256));
+      p = ctx->bincube; n = E * c.nvalid * 256; break;
+    case AOM_B_PHASE:
+      if (!ctx->phase) CU(dalloc(&ctx->phase, E * c.n * c.n));
+      p = ctx->phase; n = E * c.n * c.n; break;
+    case AOM_B_MODES: p = ctx->modes; n = E * ctx->ldm; break;
+    case AOM_B_RES_MODES: p = ctx->modes_res; n = E * ctx->ldm; break;
+    case AOM_B_STATE: p = ctx->state; n = E * ctx->ldst; break;
+    case AOM_B_REWARD: p = ctx->reward; n = E * c.n_agents; break;
+    case AOM_B_ACTION: p = ctx->action; n = E * ctx->ldact; break;
+    case AOM_B_ACTION_MEAN: p = ctx->action_mean; n = E * ctx->ldact; break;
+    case AOM_B_STREHL: p = ctx->strehl; n = E * 4; break;
+    default: return fail(ctx, AOM_ERR_INVALID, "unknown buffer id %d", buffer);
+  }
+  if (!p) return fail(ctx, AOM_ERR_STATE, "buffer %d is not allocated for this configuration", buffer);
+  *dptr = p;
+  *count = n;
+  return AOM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long sA, const float* B, int ldb,
+                       long long sB, float* C, int ldc, long long sC, int M, int N, int K, const float* bias,
+                       long long sBias, int relu, int batch, cudaStream_t st, float* com = nullptr, int ldcom = 0) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int Kp = AOM_LD(K);
+  if (lda < Kp || ldb < Kp || (lda & 3) || (ldb & 3) || (ldc & 3) || ldc < N)
+    return fail(ctx, AOM_ERR_INVALID, "gemm: leading dimensions must cover K rounded to 16 (lda %d ldb %d ldc %d K %d N %d)", lda, ldb, ldc, K, N);
+  p.A = A; p.B = B; p.C = C; p.bias = bias;
+  p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.M = M; p.N = N; p.K = Kp;
+  p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias; p.relu = relu;
+  p.com = com; p.ldcom = ldcom; p.gain = ctx->gain; p.closed = ctx->closed;
+  dim3 grid((ldc + GEMM_BN - 1) / GEMM_BN, (M + GEMM_BM - 1) / GEMM_BM, batch);
+  if (epi == 0) gemm_tn_kernel<0><<<grid, 256, 0, st>>>(p);
+  else gemm_tn_kernel<1><<<grid, 256, 0, st>>>(p);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_gemm_tn(aom_ctx* ctx, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                           int M, int N, int K, const float* bias, int relu, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  return launch_gemm(ctx, 0, A, lda, 0, B, ldb, 0, C, ldc, 0, M, N, K, bias, 0, relu, 1, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+static int extrude_once(aom_ctx* ctx, int l, int axis, int sign, cudaStream_t st) {
+  const aom_config& c = ctx->cfg;
+  NEED(AOM_T_AB, l);
+  NEED(AOM_T_STENCIL, l);
+  ExtrudeParams p;
+  p.screen = ctx->screen[l]; p.ox = ctx->ox[l]; p.oy = ctx->oy[l]; p.count = ctx->ext_count[l];
+  p.k0 = ctx->k0; p.k1 = ctx->k1; p.stencil = (const int*)ctx->tab[AOM_T_STENCIL][l];
+  p.N = c.screen_dim[l]; p.S = c.stencil_size[l]; p.E = c.n_env; p.layer = l; p.axis = axis; p.sign = sign;
+  p.amp = c.amp[l];
+  p.ldz = AOM_LD(p.S + p.N); p.Z = ctx->Z; p.zref = ctx->zref; p.ldn = AOM_LD(p.N); p.newcol = ctx->newcol;
+  dim3 g1((p.ldz + 255) / 256, c.n_env);
+  extrude_gather_kernel<<<g1, 256, 0, st>>>(p);
+  KCHECK();
+  int rc = launch_gemm(ctx, 0, ctx->Z, p.ldz, 0, (const float*)ctx->tab[AOM_T_AB][l], p.ldz, 0, ctx->newcol, p.ldn, 0,
+                       c.n_env, p.N, p.S + p.N, nullptr, 0, 0, 1, st);
+  if (rc) return rc;
+  extrude_scatter_kernel<<<c.n_env, 256, 0, st>>>(p);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_move_atmos(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  if (!ctx->seeded) return fail(ctx, AOM_ERR_STATE, "aom_reset must be called before aom_move_atmos");
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  for (int l = 0; l < c.n_layers; ++l) {
+    ctx->accx[l] += (double)c.deltax[l];
+    ctx->accy[l] += (double)c.deltay[l];
+    int nx = (int)ctx->accx[l], ny = (int)ctx->accy[l];
+    ctx->accx[l] -= nx;
+    ctx->accy[l] -= ny;
+    for (int i = 0; i < abs(nx); ++i) { int rc = extrude_once(ctx, l, 0, nx > 0 ? 1 : -1, st); if (rc) return rc; }
+    for (int i = 0; i < abs(ny); ++i) { int rc = extrude_once(ctx, l, 1, ny > 0 ? 1 : -1, st); if (rc) return rc; }
+  }
+  return AOM_OK;
+}
+
+static int clear_loop_state(aom_ctx* ctx, cudaStream_t st) {
+  const aom_config& c = ctx->cfg;
+  const size_t E = c.n_env;
+  CU(cudaMemsetAsync(ctx->slopes, 0, E * ctx->lds * 4, st));
+  CU(cudaMemsetAsync(ctx->slopes_frame, 0, E * ctx->lds * 4, st));
+  CU(cudaMemsetAsync(ctx->err_v, 0, E * ctx->lda * 4, st));
+  CU(cudaMemsetAsync(ctx->com, 0, E * ctx->lda * 4, st));
+  CU(cudaMemsetAsync(ctx->com1, 0, E * ctx->lda * 4, st));
+  CU(cudaMemsetAsync(ctx->volts, 0, E * ctx->lda * 4, st));
+  CU(cudaMemsetAsync(ctx->com_before, 0, E * ctx->lda * 4, st));
+  if (ctx->modes_res) CU(cudaMemsetAsync(ctx->modes_res, 0, E * ctx->ldm * 4, st));
+  if (ctx->hist) CU(cudaMemsetAsync(ctx->hist, 0, (size_t)c.n_hist * E * c.state_modes * 4, st));
+  if (ctx->state) CU(cudaMemsetAsync(ctx->state, 0, E * ctx->ldst * 4, st));
+  if (ctx->action) CU(cudaMemsetAsync(ctx->action, 0, E * ctx->ldact * 4, st));
+  ctx->hist_head = 0;
+  ctx->cube_override = nullptr;
+  return AOM_OK;
+}
+
+extern "C" int aom_reset(aom_ctx* ctx, const int64_t* seeds, void* stream) {
+  if (!ctx || !seeds) return fail(ctx, AOM_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  const size_t E = c.n_env;
+  uint32_t* h = (uint32_t*)malloc(2 * E * sizeof(uint32_t));
+  for (size_t e = 0; e < E; ++e) {
+    uint64_t s = (uint64_t)seeds[e];
+    h[e] = (uint32_t)(s & 0xffffffffu);
+    h[E + e] = (uint32_t)(s >> 32);
+  }
+  cudaError_t e1 = cudaMemcpyAsync(ctx->k0, h, E * 4, cudaMemcpyHostToDevice, st);
+  cudaError_t e2 = cudaMemcpyAsync(ctx->k1, h + E, E * 4, cudaMemcpyHostToDevice, st);
+  cudaError_t e3 = cudaStreamSynchronize(st);
+  free(h);
+  CU(e1); CU(e2); CU(e3);
+  ctx->seeded = true;
+  ctx->frame = 0;
+  ctx->step = 0;
+  int rc = clear_loop_state(ctx, st);
+  if (rc) return rc;
+  for (int l = 0; l < c.n_layers; ++l) {
+    size_t N = c.screen_dim[l];
+    CU(cudaMemsetAsync(ctx->screen[l], 0, E * N * N * 4, st));
+    CU(cudaMemsetAsync(ctx->ox[l], 0, E * 4, st));
+    CU(cudaMemsetAsync(ctx->oy[l], 0, E * 4, st));
+    CU(cudaMemsetAsync(ctx->ext_count[l], 0, E * 4, st));
+    ctx->accx[l] = ctx->accy[l] = 0.0;
+    int sign = c.deltax[l] < 0 ? -1 : 1;
+    for (size_t i = 0; i < 2 * N; ++i) { rc = extrude_once(ctx, l, 0, sign, st); if (rc) return rc; }
+  }
+  return AOM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int fill_wfs_params(aom_ctx* ctx, WfsParams& p, int flags, float noise) {
+  const aom_config& c = ctx->cfg;
+  memset(&p, 0, sizeof(p));
+  NEED(AOM_T_MPUPIL, 0); NEED(AOM_T_HALFXY, 0); NEED(AOM_T_SUB_X0, 0); NEED(AOM_T_SUB_Y0, 0); NEED(AOM_T_FLUX, 0);
+  p.n_layers = (flags & 1) ? c.n_layers : 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    WfsLayer& L = p.layer[l];
+    L.screen = ctx->screen[l]; L.ox = ctx->ox[l]; L.oy = ctx->oy[l]; L.N = c.screen_dim[l];
+    double px = (double)c.wfs_xoff[l] + ctx->accx[l], py = (double)c.wfs_yoff[l] + ctx->accy[l];
+    L.ix = (int)floor(px); L.iy = (int)floor(py);
+    L.fx = (float)(px - L.ix); L.fy = (float)(py - L.iy);
+    if (L.ix < 0 || L.iy < 0 || L.ix + c.n + 1 > L.N || L.iy + c.n + 1 > L.N)
+      return fail(ctx, AOM_ERR_UNSUPPORTED, "layer %d: pupil footprint leaves the screen", l);
+  }
+  p.use_dm = (flags & 2) ? 1 : 0;
+  if (p.use_dm) {
+    NEED(AOM_T_STAMP1D, 0); NEED(AOM_T_ACT_MAP, 0); NEED(AOM_T_TT_PLANES, 0);
+  }
+  p.E = c.n_env; p.n = c.n; p.nvalid = c.nvalid;
+  p.mpupil = (const float*)ctx->tab[AOM_T_MPUPIL][0];
+  p.halfxy = (const float*)ctx->tab[AOM_T_HALFXY][0];
+  p.sub_x0 = (const int*)ctx->tab[AOM_T_SUB_X0][0];
+  p.sub_y0 = (const int*)ctx->tab[AOM_T_SUB_Y0][0];
+  p.flux = (const float*)ctx->tab[AOM_T_FLUX][0];
+  p.volts = ctx->volts; p.ldv = ctx->lda;
+  p.stamp1d = (const float*)ctx->tab[AOM_T_STAMP1D][0]; p.ss = c.stamp_size;
+  p.act_map = (const int*)ctx->tab[AOM_T_ACT_MAP][0];
+  p.grid_n = c.pzt_grid_n; p.pitch = c.pzt_pitch; p.i1_0 = c.pzt_i1_0; p.j1_0 = c.pzt_j1_0;
+  p.pzt_off = c.pzt_off; p.pzt_nact = c.pzt_nact;
+  p.tt_planes = (const float*)ctx->tab[AOM_T_TT_PLANES][0]; p.tt_dim = c.tt_dim; p.tt_off = c.tt_off;
+  p.k2 = (float)(2.0 * M_PI / (double)c.lambda_um);
+  p.nphotons = c.nphotons; p.noise = noise; p.cog_offset = c.cog_offset; p.pixsize = c.pixsize;
+  p.frame = ctx->frame; p.wfs_index = (uint32_t)c.wfs_index; p.k0 = ctx->k0; p.k1 = ctx->k1;
+  p.slopes = ctx->slopes_frame; p.lds = ctx->lds;
+  return AOM_OK;
+}
+
+extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  if (noise >= 0.f && !ctx->seeded) return fail(ctx, AOM_ERR_STATE, "aom_reset must seed the noise streams first");
+  WfsParams p;
+  int rc = fill_wfs_params(ctx, p, flags, noise);
+  if (rc) return rc;
+  if (flags & 4) {
+    if (!ctx->bincube) CU(dalloc(&ctx->bincube, (size_t)c.n_env * c.nvalid * 256));
+    p.bincube = ctx->bincube;
+  }
+  long long total = (long long)c.n_env * c.nvalid;
+  long long blocks = (total + WFS_WARPS - 1) / WFS_WARPS;
+  long long cap = (long long)ctx->num_sms * 2 * 8;      // 2 resident CTAs per SM, 8 waves of work each
+  int grid = (int)(blocks < cap ? blocks : cap);
+  if (c.nfft == 64) wfs_frame_kernel<4><<<grid, WFS_WARPS * 32, wfs_smem_bytes<4>(), st>>>(p);
+  else wfs_frame_kernel<8><<<grid, WFS_WARPS * 32, wfs_smem_bytes<8>(), st>>>(p);
+  KCHECK();
+  ctx->frame++;
+  ctx->cube_override = nullptr;
+  return AOM_OK;
+}
+
+extern "C" int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  WfsParams p;
+  int rc = fill_wfs_params(ctx, p, flags, -1.f);
+  if (rc) return rc;
+  if (!ctx->phase) CU(dalloc(&ctx->phase, (size_t)c.n_env * c.n * c.n));
+  dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
+  wfs_phase_kernel<<<grid, blk, 0, st>>>(p, ctx->phase);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_set_bincube(aom_ctx* ctx, const float* dcube, void* stream) {
+  if (!ctx || !dcube) return fail(ctx, AOM_ERR_INVALID, "null argument");
+  (void)stream;
+  ctx->cube_override = dcube;
+  return AOM_OK;
+}
+
+extern "C" int aom_do_centroids(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  if (ctx->cube_override) {
+    long long total = (long long)c.n_env * c.nvalid;
+    long long threads = total * 32;
+    cog_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->cube_override, ctx->slopes, ctx->lds, c.nvalid,
+                                                                  total, c.cog_offset, c.pixsize);
+    KCHECK();
+  } else {
+    CU(cudaMemcpyAsync(ctx->slopes, ctx->slopes_frame, (size_t)c.n_env * ctx->lds * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return AOM_OK;
+}
+
+extern "C" int aom_do_control(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  const aom_config& c = ctx->cfg;
+  NEED(AOM_T_CMAT, 0);
+  return launch_gemm(ctx, 1, ctx->slopes, ctx->lds, 0, (const float*)ctx->tab[AOM_T_CMAT][0], ctx->lds, 0, ctx->err_v,
+                     ctx->lda, 0, c.n_env, c.nactu, c.nslopes, nullptr, 0, 0, 1, (cudaStream_t)stream, ctx->com, ctx->lda);
+}
+
+extern "C" int aom_set_command(aom_ctx* ctx, const float* dcom, int ld, void* stream) {
+  if (!ctx || !dcom) return fail(ctx, AOM_ERR_INVALID, "null argument");
+  const aom_config& c = ctx->cfg;
+  if (ld < c.nactu) return fail(ctx, AOM_ERR_INVALID, "Dimension mismatch");
+  dim3 grid((ctx->lda + 255) / 256, c.n_env);
+  copy_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dcom, ld, ctx->com, ctx->lda, c.nactu, c.n_env);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_set_dm_volts(aom_ctx* ctx, const float* dvolts, int ld, void* stream) {
+  if (!ctx || !dvolts) return fail(ctx, AOM_ERR_INVALID, "null argument");
+  const aom_config& c = ctx->cfg;
+  if (ld < c.nactu) return fail(ctx, AOM_ERR_INVALID, "Dimension mismatch");
+  dim3 grid((ctx->lda + 255) / 256, c.n_env);
+  copy_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dvolts, ld, ctx->volts, ctx->lda, c.nactu, c.n_env);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  const aom_config& c = ctx->cfg;
+  size_t total = (size_t)c.n_env * ctx->lda;
+  apply_control_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctx->com, ctx->com1, ctx->volts,
+                                                                                         ctx->lda, total, c.delay, comp_voltage);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_set_gain(aom_ctx* ctx, float gain) {
+  if (!ctx) return AOM_ERR_INVALID;
+  ctx->gain = gain;
+  return AOM_OK;
+}
+
+extern "C" int aom_set_loop(aom_ctx* ctx, int closed) {
+  if (!ctx) return AOM_ERR_INVALID;
+  ctx->closed = closed ? 1 : 0;
+  return AOM_OK;
+}
+
+extern "C" int aom_set_layer(aom_ctx* ctx, int layer, float deltax, float deltay, float amp) {
+  if (!ctx) return AOM_ERR_INVALID;
+  if (layer < 0 || layer >= ctx->cfg.n_layers) return fail(ctx, AOM_ERR_INVALID, "layer index out of range");
+  ctx->cfg.deltax[layer] = deltax;
+  ctx->cfg.deltay[layer] = deltay;
+  ctx->cfg.amp[layer] = amp;
+  return AOM_OK;
+}
+
+extern "C" int aom_reset_dm(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  CU(cudaMemsetAsync(ctx->volts, 0, (size_t)ctx->cfg.n_env * ctx->lda * 4, (cudaStream_t)stream));
+  return AOM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int project_v2m(aom_ctx* ctx, const float* v, float* out, cudaStream_t st) {
+  const aom_config& c = ctx->cfg;
+  NEED(AOM_T_V2M, 0);
+  return launch_gemm(ctx, 0, v, ctx->lda, 0, (const float*)ctx->tab[AOM_T_V2M][0], ctx->lda, 0, out, ctx->ldm, 0, c.n_env,
+                     c.nmodes, c.nactu, nullptr, 0, 0, 1, st);
+}
+
+extern "C" int aom_rl_control(aom_ctx* ctx, const float* daction, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  NEED(AOM_T_M2V, 0); NEED(AOM_T_FREEDOM, 0); NEED(AOM_T_ACTION_MAP, 0);
+  const float* act = daction ? daction : ctx->action;
+  if (!act) return fail(ctx, AOM_ERR_STATE, "no action buffer");
+  int rc = project_v2m(ctx, ctx->com, ctx->modes, st);
+  if (rc) return rc;
+  dim3 grid((c.action_dim + 127) / 128, c.n_env);
+  inject_action_kernel<<<grid, 128, 0, st>>>(ctx->modes, ctx->ldm, act, ctx->ldact, (const int*)ctx->tab[AOM_T_ACTION_MAP][0],
+                                             (const float*)ctx->tab[AOM_T_FREEDOM][0], c.action_dim, c.n_env,
+                                             c.env_act_scale, c.env_act_bias);
+  KCHECK();
+  return launch_gemm(ctx, 0, ctx->modes, ctx->ldm, 0, (const float*)ctx->tab[AOM_T_M2V][0], ctx->ldm, 0, ctx->com, ctx->lda, 0,
+                     c.n_env, c.nactu, c.nmodes, nullptr, 0, 0, 1, st);
+}
+
+extern "C" int aom_state_begin(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  CU(cudaMemcpyAsync(ctx->com_before, ctx->com, (size_t)ctx->cfg.n_env * ctx->lda * 4, cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream));
+  return AOM_OK;
+}
+
+extern "C" int aom_state_end(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  if (!ctx->state) return fail(ctx, AOM_ERR_STATE, "state_dim is 0 in this configuration");
+  NEED(AOM_T_STATE_MAP, 0); NEED(AOM_T_NORM_DM_MEAN, 0); NEED(AOM_T_NORM_DM_STD, 0);
+  NEED(AOM_T_NORM_RES_MEAN, 0); NEED(AOM_T_NORM_RES_STD, 0);
+  int rc = project_v2m(ctx, ctx->com_before, ctx->modes_before, st);
+  if (rc) return rc;
+  rc = project_v2m(ctx, ctx->err_v, ctx->modes_res, st);
+  if (rc) return rc;
+  dim3 grid((c.state_modes + 127) / 128, c.n_env);
+  build_state_kernel<<<grid, 128, 0, st>>>(ctx->state, ctx->ldst, ctx->hist, c.n_hist, ctx->hist_head, ctx->modes_before,
+                                           ctx->modes_res, ctx->ldm, (const int*)ctx->tab[AOM_T_STATE_MAP][0], c.state_modes,
+                                           (const float*)ctx->tab[AOM_T_NORM_DM_MEAN][0], (const float*)ctx->tab[AOM_T_NORM_DM_STD][0],
+                                           (const float*)ctx->tab[AOM_T_NORM_RES_MEAN][0], (const float*)ctx->tab[AOM_T_NORM_RES_STD][0],
+                                           c.n_env);
+  KCHECK();
+  if (c.n_hist > 0) ctx->hist_head = (ctx->hist_head + 1) % c.n_hist;
+  return AOM_OK;
+}
+
+extern "C" int aom_reward(aom_ctx* ctx, float factor, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  const aom_config& c = ctx->cfg;
+  if (!ctx->reward) return fail(ctx, AOM_ERR_STATE, "n_agents is 0 in this configuration");
+  NEED(AOM_T_AGENT_REWARD, 0);
+  long long threads = (long long)c.n_env * c.n_agents * 32;
+  reward_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctx->modes_res, ctx->ldm,
+                                                                                     (const int*)ctx->tab[AOM_T_AGENT_REWARD][0],
+                                                                                     c.n_agents, c.n_env, factor, ctx->reward);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_actor_forward(aom_ctx* ctx, int eval_mode, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  if (c.n_agents <= 0 || !ctx->state) return fail(ctx, AOM_ERR_STATE, "no agents / state configured");
+  NEED(AOM_T_AGENT_IDX, 0); NEED(AOM_T_AGENT_ACT, 0); NEED(AOM_T_ACTOR_W1, 0); NEED(AOM_T_ACTOR_B1, 0);
+  NEED(AOM_T_ACTOR_W2, 0); NEED(AOM_T_ACTOR_B2, 0); NEED(AOM_T_ACTOR_WH, 0); NEED(AOM_T_ACTOR_BH, 0);
+  const int E = c.n_env, A = c.n_agents;
+  dim3 g((ctx->ld_ain + 127) / 128, E, A);
+  actor_gather_kernel<<<g, 128, 0, st>>>(ctx->state, ctx->ldst, (const int*)ctx->tab[AOM_T_AGENT_IDX][0], c.actor_in,
+                                         ctx->ld_ain, E, ctx->aX);
+  KCHECK();
+  int rc = launch_gemm(ctx, 0, ctx->aX, ctx->ld_ain, (long long)E * ctx->ld_ain, (const float*)ctx->tab[AOM_T_ACTOR_W1][0],
+                       ctx->ld_ain, (long long)c.actor_hidden * ctx->ld_ain, ctx->aH1, ctx->ld_ah, (long long)E * ctx->ld_ah, E,
+                       c.actor_hidden, c.actor_in, (const float*)ctx->tab[AOM_T_ACTOR_B1][0], c.actor_hidden, 1, A, st);
+  if (rc) return rc;
+  rc = launch_gemm(ctx, 0, ctx->aH1, ctx->ld_ah, (long long)E * ctx->ld_ah, (const float*)ctx->tab[AOM_T_ACTOR_W2][0], ctx->ld_ah,
+                   (long long)c.actor_hidden * ctx->ld_ah, ctx->aH2, ctx->ld_ah, (long long)E * ctx->ld_ah, E, c.actor_hidden,
+                   c.actor_hidden, (const float*)ctx->tab[AOM_T_ACTOR_B2][0], c.actor_hidden, 1, A, st);
+  if (rc) return rc;
+  rc = launch_gemm(ctx, 0, ctx->aH2, ctx->ld_ah, (long long)E * ctx->ld_ah, (const float*)ctx->tab[AOM_T_ACTOR_WH][0], ctx->ld_ah,
+                   (long long)2 * c.actor_out * ctx->ld_ah, ctx->aHO, ctx->ld_aho, (long long)E * ctx->ld_aho, E, 2 * c.actor_out,
+                   c.actor_hidden, (const float*)ctx->tab[AOM_T_ACTOR_BH][0], 2 * c.actor_out, 0, A, st);
+  if (rc) return rc;
+  dim3 g2((c.actor_out + 63) / 64, E, A);
+  actor_sample_kernel<<<g2, 64, 0, st>>>(ctx->aHO, ctx->ld_aho, c.actor_out, (const int*)ctx->tab[AOM_T_AGENT_ACT][0], E, A,
+                                         c.log_sig_min, c.log_sig_max, c.pol_act_scale, c.pol_act_bias, eval_mode, ctx->step,
+                                         ctx->k0, ctx->k1, ctx->action, ctx->action_mean, ctx->ldact);
+  KCHECK();
+  ctx->step++;      // one decision per call: the exploration-noise counter (oracle/rng.py TAG_ACTOR)
+  return AOM_OK;
+}
+
+extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  int rc;
+  // rl half-step: TrainerRPC.env_step -> AoEnv.rl_step -> RlSupervisor.next_part_two (rlSupervisor.py:900-947)
+  if (mode == 0) { rc = aom_actor_forward(ctx, eval_mode, stream); if (rc) return rc; }
+  if (mode != 2) { rc = aom_rl_control(ctx, nullptr, stream); if (rc) return rc; }
+  rc = aom_apply_control(ctx, 1, stream); if (rc) return rc;
+  if (ctx->reward) { rc = aom_reward(ctx, 1000.f, stream); if (rc) return rc; }
+  // linear half-step: AoEnv.linear_step -> RlSupervisor.next_part_one (rlSupervisor.py:1015-1051)
+  rc = aom_state_begin(ctx, stream); if (rc) return rc;
+  rc = aom_move_atmos(ctx, stream); if (rc) return rc;
+  rc = aom_comp_wfs_image(ctx, 3, ctx->cfg.noise, stream); if (rc) return rc;
+  rc = aom_do_centroids(ctx, stream); if (rc) return rc;
+  rc = aom_do_control(ctx, stream); if (rc) return rc;
+  if (ctx->state) { rc = aom_state_end(ctx, stream); if (rc) return rc; }
+  return AOM_OK;
+}
+
+extern "C" int aom_pixel_noise(aom_ctx* ctx, const float* dlam, float* dout, int64_t n, float noise, int64_t seed,
+                               uint32_t frame, uint32_t wfs, void* stream) {
+  if (!ctx || !dlam || !dout) return fail(ctx, AOM_ERR_INVALID, "null argument");
+  uint64_t s = (uint64_t)seed;
+  pixel_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dlam, dout, n, noise, (uint32_t)(s & 0xffffffffu),
+                                                                                   (uint32_t)(s >> 32), frame, wfs);
+  KCHECK();
+  return AOM_OK;
+}

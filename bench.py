@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the batched closed-loop AO environment step (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA path through the C ABI)
+    python bench.py --impl reference ...                     the reference's CPU path (numpy oracle on host cores)
+    torchrun ... bench.py --gpus N ...                       one rank per GPU, environments sharded, no collective
+
+A "step" is one env-step of every environment of the batch: all agents' actor forward, rl_control,
+apply_control, reward, move_atmos, fused Shack-Hartmann frame, centroids, integrator, state assembly.
+Workload: production_sh_40x40_8m_3layers (3 layers, 1200 subapertures, 1286 actuators, 43 windowed agents),
+4096 environments per GPU, synthetic von-Karman turbulence from seeds.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "40x40": dict(par="production_sh_40x40_8m_3layers.py", world_size=44,
+                  env_rl=dict(n_zernike_start_end=[0, 1260], window_n_zernike=20, include_tip_tilt_windowed=True,
+                              n_reverse_filtered_from_cmat=5, delayed_assignment=2),
+                  name="production_sh_40x40_8m_3layers, 43 agents (42x30 modes + TT, window 20), delay 1"),
+    "10x10": dict(par="production_sh_10x10_2m.py", world_size=3,
+                  env_rl=dict(n_zernike_start_end=[0, 80], n_reverse_filtered_from_cmat=5),
+                  name="production_sh_10x10_2m, 2 agents (80 modes + TT), delay 1"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="40x40", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 4096 / 1024)")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    p = [x.strip() for x in line.split(",")]
+                    if len(p) < 9:
+                        continue
+                    try:
+                        sm.append(float(p[1]))
+                        mx.append(float(p[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                         p[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_env_factory(workload_key, cmat_cache=None):
+    """Builds the numpy oracle environment of a workload (CPU only: tables by the host builders, interaction
+    matrix through the oracle's own Shack-Hartmann pipeline)."""
+    from ao_marl_b200 import tables
+    from ao_marl_b200.config import load_config_from_file
+    from ao_marl_b200.init import rtc as rtc_b
+    from ao_marl_b200.rl.layout import RLLayout
+    from oracle import loop
+    wl = WORKLOADS[workload_key]
+    t = tables.build_static(load_config_from_file(wl["par"]))
+    tables.build_basis(t)
+    tab = t.as_oracle_dict()
+    tab["wfs_index"] = t.wfs_index
+    if cmat_cache is not None and os.path.exists(cmat_cache):
+        cmat = np.load(cmat_cache)
+    else:
+        # the timing does not depend on the values of the command matrix: the geometric interaction matrix
+        # (pre-filter columns dropped) stands in for the measured one to keep the start-up bounded
+        D = rtc_b.imat_geom(t.p_wfs, [t.p_pzt, t.p_tt], t.config.p_geom)
+        cmat = rtc_b.cmat_with_btt(D, t.Btt, 5)
+    env_rl = dict(wl["env_rl"], parameters_telescope=wl["par"])
+    rl = RLLayout(t.Btt.shape[1], env_rl, None, wl["world_size"], seed=0)
+    return lambda seed: loop.OracleEnv(tab, cmat, t.Btt, t.P, rl, seed=seed), t, rl
+
+
+def _cpu_worker(args):
+    workload_key, seed, seconds, min_steps = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    make, t, rl = cpu_env_factory(workload_key)
+    env = make(seed)
+    # no 2N-extrusion reset inside the sample: start from a short warm-up of the screens
+    for l in range(env.atm.nl):
+        for _ in range(8):
+            env.atm._one(l, 0, 1)
+    state = env.linear_step()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        a, _ = env.actors(state)
+        state, _ = env.env_step(a)
+        n += 1
+        el = time.perf_counter() - t0
+        if (el >= seconds and n >= min_steps) or n >= 100000:
+            break
+    return n, el
+
+
+def cpu_baseline(workload_key, seconds, procs=1):
+    """env-steps/s of the oracle on `procs` host processes (one environment each), bounded sample."""
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_cpu_worker((workload_key, 1234, seconds, 2))]
+    else:
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_cpu_worker, [(workload_key, 1234 + i, seconds, 2) for i in range(procs)])
+    rate = sum(n / el for n, el in res)
+    steps = sum(n for n, _ in res)
+    return dict(value=rate, unit="env-steps/s", cores=procs, kind="port",
+                sample="%d env-steps of 1 environment per process on %d process(es), %.1f s of stepping "
+                       "(oracle/loop.py: numpy frame + CPU torch actors), start-up %.0f s excluded"
+                       % (steps, procs, max(el for _, el in res), time.perf_counter() - t0 - max(el for _, el in res)))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    procs = os.cpu_count() or 1
+    per_step = max(2.0, args.cpu_seconds / max(1, args.steps + args.warmup))
+    t0 = time.perf_counter()
+    base = cpu_baseline(args.workload, per_step * (args.steps + args.warmup), procs)
+    line = {
+        "impl": "reference", "metric": "AO env-steps/s (batched closed-loop step + actor forward)",
+        "value": base["value"], "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 / base["value"] if base["value"] else None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "envs_per_process": 1, "processes": procs,
+                   "note": "reference CPU path = numpy restatement of the sutra frame (the compiled simulator is not "
+                           "in the reference repo) + reference-architecture actors on CPU torch"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ao_marl_b200.system import build_system
+    wl = WORKLOADS[args.workload]
+    E = args.envs or (4096 if args.workload == "40x40" else 1024)
+    t_build = time.perf_counter()
+    sim, t, rl = build_system(wl["par"], E, env_rl=dict(wl["env_rl"]), world_size=wl["world_size"], seed=0)
+    seeds = 1234 + rank * E + np.arange(E, dtype=np.int64)
+    sim.reset(seeds)
+    # first frame of the episode (AoEnv.reset ends with one linear step)
+    sim.state_begin(); sim.move_atmos(); sim.comp_wfs_image(); sim.do_centroids(); sim.do_control(); sim.state_end()
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+
+    ev = torch.cuda.Event
+    wfs_events = []
+
+    def one_step(record):
+        # TrainerRPC.episode body (train_rpc.py:503-553) sequenced through the C ABI
+        sim.actor_forward(False)
+        sim.rl_control()
+        sim.apply_control(True)
+        sim.reward(rl.reward_factor)
+        sim.state_begin()
+        sim.move_atmos()
+        if record:
+            a, b = ev(enable_timing=True), ev(enable_timing=True)
+            a.record()
+            sim.comp_wfs_image()
+            b.record()
+            wfs_events.append((a, b))
+        else:
+            sim.comp_wfs_image()
+        sim.do_centroids()
+        sim.do_control()
+        sim.state_end()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = sim.launches()
+    e0, e1 = ev(enable_timing=True), ev(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step(True)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = sim.launches() - l0
+    ms = e0.elapsed_time(e1)
+    wfs_ms = float(np.mean([a.elapsed_time(b) for a, b in wfs_events]))
+
+    # end to end through host buffers: action from pinned host memory in, action / state / reward back out
+    act_h = torch.zeros((E, rl.action_dim), dtype=torch.float32).pin_memory()
+    st_h = torch.zeros((E, rl.state_dim), dtype=torch.float32).pin_memory()
+    rw_h = torch.zeros((E, rl.n_agents), dtype=torch.float32).pin_memory()
+    act_d = sim.rows("ACTION", rl.action_dim)
+    st_d = sim.rows("STATE", rl.state_dim)
+    rw_d = sim.buffer("REWARD").view(E, rl.n_agents)
+    act_h.copy_(act_d)
+    k_e2e = max(2, min(args.steps, 10))
+    barrier()
+    f0, f1 = ev(enable_timing=True), ev(enable_timing=True)
+    f0.record()
+    for _ in range(k_e2e):
+        act_d.copy_(act_h, non_blocking=True)       # H2D: this step's actions
+        sim.step(mode=1)                            # rl half-step + reward + linear half-step
+        sim.actor_forward(False)                    # next actions from the new state
+        act_h.copy_(act_d, non_blocking=True)       # D2H: actions, state, rewards
+        st_h.copy_(st_d, non_blocking=True)
+        rw_h.copy_(rw_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the host owns the results before the next step
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t_all = torch.tensor([ms, ms_e2e, wfs_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, wfs_ms = [float(x) for x in t_all.cpu()]
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        w = t.p_wfs
+        bytes_per_frame = w._nvalid * (w._pdiam ** 2 * 4 + w.npix ** 2 * 4 + 2 * 4)
+        achieved = bytes_per_frame * E / (wfs_ms * 1e-3) / 1e9
+        flops_per_frame = w._nvalid * 8.0 * (32 * 16 * 16 + 32 * 16 * 32)                # pruned DFT-as-GEMM count
+        total_steps = args.steps * E * world
+        line = {
+            "metric": "AO env-steps/s (batched closed-loop step + actor forward)",
+            "value": total_steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "envs_per_gpu": E, "total_envs": E * world,
+                       "parallelism": "env-sharded x%d, no collective on the step path" % world,
+                       "l2": "inputs larger than L2 (%.1f GB of screens per GPU)" % (
+                           sum(int(n) ** 2 for n in t.dim_screens) * 4 * E / 1e9),
+                       "us_per_frame": ms / args.steps / E * 1e3, "build_s": t_build},
+            "roofline": {"kernel": "wfs_frame_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm,
+                         "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "peak_source": "measured" if peaks else "fallback",
+                         "ms_per_launch": wfs_ms, "share_of_step": wfs_ms / (ms / args.steps),
+                         "fp32_tflops_algorithmic": flops_per_frame * E / (wfs_ms * 1e-3) / 1e12,
+                         "note": "issue-bound on the FP32 pipe (SIMT pruned FFT), not on HBM: see DESIGN.md"},
+            "e2e": {"value": k_e2e * E * world / (ms_e2e * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": int(E * rl.action_dim * 4),
+                    "d2h_bytes_per_step": int(E * (rl.action_dim + rl.state_dim + rl.n_agents) * 4), "steps": k_e2e},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_seconds, 1)
+            except Exception as exc:   # the baseline is reported, never allowed to sink the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                                        "sample": "failed: %r" % (exc,)}
+        print(json.dumps(line))
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,215 @@
+/* aomarl.h -- C ABI of libaomarl.so: batched closed-loop adaptive-optics environment step on B200.
+ *
+ * The reference (Tomeu7/AO-MARL) has no C interface for this path: its Python supervisor calls the
+ * un-vendored COMPASS pybind11 objects (shesha/sutra_wrap.py:46-72).  Every entry point below names
+ * the reference call it replaces (paths relative to the reference root).  A maintainer binds these
+ * with ctypes exactly as ao_marl_b200/lib.py does; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - one aom_ctx per GPU / process; it owns all persistent simulator state for E environments
+ *   - every op is asynchronous on the cudaStream_t passed as `void* stream`
+ *   - per-environment vectors are row-major [E][ld], ld = AOM_LD(n) floats, pad columns kept at 0
+ *   - pupil-plane arrays are [y][x], x fastest (flat index x + n*y, as the reference's integer maps)
+ *   - return value: 0 on success, negative aom_status otherwise; aom_last_error() gives the text
+ */
+#ifndef AOMARL_H
+#define AOMARL_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AOM_MAX_LAYERS 8
+#define AOM_LD(n) (((n) + 15) & ~15)
+
+typedef struct aom_ctx aom_ctx;
+
+typedef enum aom_status {
+  AOM_OK = 0,
+  AOM_ERR_INVALID = -1,     /* bad argument / dimension mismatch (reference: ValueError, rtcCompass.py:471-472) */
+  AOM_ERR_CUDA = -2,        /* CUDA runtime error */
+  AOM_ERR_UNSUPPORTED = -3, /* configuration outside the hot-path scope */
+  AOM_ERR_STATE = -4        /* missing table / op called before its prerequisites */
+} aom_status;
+
+/* Scalar description of one configuration (filled from the host builders, ao_marl_b200/tables.py). */
+typedef struct aom_config {
+  int32_t n_env;                        /* E */
+  int32_t n;                            /* mpupil side (p_geom._n, geom_init.py:833) */
+  /* atmosphere (atmos_init.py:76-132) */
+  int32_t n_layers;
+  int32_t screen_dim[AOM_MAX_LAYERS];
+  int32_t stencil_size[AOM_MAX_LAYERS];
+  float deltax[AOM_MAX_LAYERS];         /* wind step, pixels / frame */
+  float deltay[AOM_MAX_LAYERS];
+  float amp[AOM_MAX_LAYERS];            /* innovation amplitude r0_px^(-5/6) * 0.5/(2 pi), microns */
+  float wfs_xoff[AOM_MAX_LAYERS];       /* wfs_init.py:175-185 */
+  float wfs_yoff[AOM_MAX_LAYERS];
+  /* Shack-Hartmann sensor (geom_init.py:168-340, 622-811) */
+  int32_t nxsub, nvalid, pdiam, npix, nfft, nrebin;
+  float lambda_um;
+  float nphotons;
+  float noise;                          /* <0 none, 0 photon, >0 photon + read (e-) */
+  float pixsize;                        /* arcsec / detector pixel (rtc_init.py:217) */
+  float cog_offset;                     /* npix/2 - 0.5 (rtc_init.py:208) */
+  int32_t wfs_index;                    /* RNG sub-stream */
+  /* mirrors (dm_init.py:330-509, 661-694) */
+  int32_t pzt_nact;
+  int32_t stamp_size;                   /* influsize */
+  int32_t pzt_off;                      /* (dim_dm - n)/2, wfs_init.py:196-204 */
+  int32_t pzt_pitch;                    /* actuator pitch in pixels (integer on the production grids) */
+  int32_t pzt_grid_n;                   /* side of the actuator lattice behind act_map */
+  int32_t pzt_i1_0;                     /* i1 of lattice column 0 (DM-support pixels) */
+  int32_t pzt_j1_0;
+  int32_t tt_dim;
+  int32_t tt_off;
+  /* controller (rtc_init.py:451-513) */
+  int32_t nactu, nslopes, nmodes;
+  float gain;
+  int32_t delay;                        /* 0 or 1 frames of command latency (p_controller.delay) */
+  /* RL layer (ao_env.py, train_rpc.py) */
+  int32_t n_hist;                       /* number_of_previous_dm */
+  int32_t state_modes;                  /* modes kept per state block (all modes when windowed, else the action range) */
+  int32_t state_dim;                    /* (n_hist + 2) * state_modes */
+  float env_act_scale, env_act_bias;    /* normalization_{std,mean}_inside_environment (rlSupervisor.py:724-726) */
+  float pol_act_scale, pol_act_bias;    /* gaussian_std / gaussian_mu of the policies (model_rpc.py:115-116) */
+  float log_sig_min, log_sig_max;       /* -20 / LOG_SIG_MAX (model_rpc.py:12, 128) */
+  int32_t n_agents;
+  int32_t actor_in, actor_hidden, actor_out; /* padded common sizes of the batched actors */
+  int32_t action_dim;                   /* length of the global action vector */
+} aom_config;
+
+/* Tables uploaded once after aom_create (host pointers; copied to the device). */
+typedef enum aom_table {
+  AOM_T_AB = 0,        /* float [N][ld(S+N)]   rows of A | B            index = layer   (iterkolmo.py:190-252) */
+  AOM_T_STENCIL,       /* int32 [S]            +x stencil, flat x+N*y   index = layer   (iterkolmo.py:41-73)   */
+  AOM_T_MPUPIL,        /* float [n][n]                                                (geom_init.py:845)     */
+  AOM_T_HALFXY,        /* float [pdiam][pdiam]                                        (geom_init.py:690-701) */
+  AOM_T_SUB_X0,        /* int32 [nvalid]       tile origin column in the mpupil frame (geom_init.py:673-685) */
+  AOM_T_SUB_Y0,        /* int32 [nvalid]       tile origin row                                               */
+  AOM_T_FLUX,          /* float [nvalid]       illuminated fraction, list order       (wfs_init.py:145)      */
+  AOM_T_STAMP1D,       /* float [stamp_size]   separable factor of the actuator stamp (influ_util.py:139-183)*/
+  AOM_T_ACT_MAP,       /* int32 [grid_n^2]     lattice cell -> actuator index or -1   (dm_init.py:414-427)   */
+  AOM_T_TT_PLANES,     /* float [2][tt_dim][tt_dim]                                   (dm_init.py:661-694)   */
+  AOM_T_CMAT,          /* float [nactu][ld(nslopes)]                                  (basis.py:229-256)     */
+  AOM_T_V2M,           /* float [nmodes][ld(nactu)]   volts -> Btt modes (P)          (basis.py:362-443)     */
+  AOM_T_M2V,           /* float [nactu][ld(nmodes)]   Btt modes -> volts (Btt)                               */
+  AOM_T_FREEDOM,       /* float [nmodes]       action bound per mode                  (rlSupervisor.py:255-282)*/
+  AOM_T_ACTION_MAP,    /* int32 [action_dim]   action element -> mode index           (rlSupervisor.py:677-691)*/
+  AOM_T_STATE_MAP,     /* int32 [state_modes]  mode index of each state-block entry    (ao_env.py:482-505)     */
+  AOM_T_NORM_DM_MEAN,  /* float [state_modes]  (ao_env.py:470-480, 279-301)                                  */
+  AOM_T_NORM_DM_STD,
+  AOM_T_NORM_RES_MEAN,
+  AOM_T_NORM_RES_STD,
+  AOM_T_AGENT_IDX,     /* int32 [n_agents][actor_in]  state index per actor input, -1 = pad (helper_states.py:286-317) */
+  AOM_T_AGENT_ACT,     /* int32 [n_agents][actor_out] global action slot per actor output, -1 = pad (train_rpc.py:667-675) */
+  AOM_T_AGENT_REWARD,  /* int32 [n_agents][2]  mode range [a0, a1) of the reward     (train_rpc.py:402-416)  */
+  AOM_T_ACTOR_W1,      /* float [n_agents][hidden][ld(actor_in)]                      (model_rpc.py:78-84)   */
+  AOM_T_ACTOR_B1,      /* float [n_agents][hidden] */
+  AOM_T_ACTOR_W2,      /* float [n_agents][hidden][ld(hidden)] */
+  AOM_T_ACTOR_B2,
+  AOM_T_ACTOR_WH,      /* float [n_agents][2*actor_out][ld(hidden)]  mean rows then log-std rows */
+  AOM_T_ACTOR_BH,      /* float [n_agents][2*actor_out] */
+  AOM_T_COUNT
+} aom_table;
+
+/* Device buffers owned by the context (aom_get_buffer returns the device pointer and its element count). */
+typedef enum aom_buffer {
+  AOM_B_SCREEN = 0,    /* float [E][N][N] ring-buffered screen, index = layer           */
+  AOM_B_RING_OX,       /* int32 [E]  physical column of logical column 0, index = layer */
+  AOM_B_RING_OY,       /* int32 [E]                                                      */
+  AOM_B_SLOPES,        /* float [E][ld(nslopes)]   rtc.get_slopes  (rtcCompass.py:104-114) */
+  AOM_B_ERR,           /* float [E][ld(nactu)]     rtc.get_err                            */
+  AOM_B_COM,           /* float [E][ld(nactu)]     rtc.get_command                        */
+  AOM_B_VOLTS,         /* float [E][ld(nactu)]     rtc.get_voltages                       */
+  AOM_B_BINCUBE,       /* float [E][nvalid][npix*npix]  (allocated on first use)          */
+  AOM_B_PHASE,         /* float [E][n][n]               (allocated on first use)          */
+  AOM_B_MODES,         /* float [E][ld(nmodes)]    scratch: last volts->modes product     */
+  AOM_B_RES_MODES,     /* float [E][ld(nmodes)]    v2m . err of the last frame            */
+  AOM_B_STATE,         /* float [E][ld(state_dim)]                                        */
+  AOM_B_REWARD,        /* float [E][n_agents]                                             */
+  AOM_B_ACTION,        /* float [E][ld(action_dim)]                                       */
+  AOM_B_ACTION_MEAN,   /* float [E][ld(action_dim)]                                       */
+  AOM_B_STREHL,        /* float [E][4]  SE, LE, phase variance, running mean variance     */
+  AOM_B_COUNT
+} aom_buffer;
+
+/* lifetime */
+size_t aom_config_size(void);                       /* sizeof(aom_config) the library was built with (binding check) */
+int aom_create(const aom_config* cfg, aom_ctx** out);
+void aom_destroy(aom_ctx* ctx);
+const char* aom_last_error(const aom_ctx* ctx);     /* ctx may be NULL for create-time errors */
+int aom_set_table(aom_ctx* ctx, int table, int index, const void* host, size_t nbytes);
+int aom_get_buffer(aom_ctx* ctx, int buffer, int index, void** dptr, size_t* count);
+int aom_device_count_launches(const aom_ctx* ctx, uint64_t* n_launches);  /* kernels launched so far */
+
+/* RlSupervisor.reset (rlSupervisor.py:236-246): reseed + regenerate turbulence (2N extrusions per layer),
+ * clear mirrors / integrator / delay line / histories.  seeds: host int64 [E]. */
+int aom_reset(aom_ctx* ctx, const int64_t* seeds, void* stream);
+
+/* AtmosCompass.move_atmos (atmosCompass.py:158-161) */
+int aom_move_atmos(aom_ctx* ctx, void* stream);
+
+/* AtmosCompass.set_wind / set_r0 (atmosCompass.py:79-135): new wind step (pixels / frame) and innovation
+ * amplitude of one layer; a sign change of the wind needs no stencil upload (mirroring is index arithmetic). */
+int aom_set_layer(aom_ctx* ctx, int layer, float deltax, float deltay, float amp);
+
+/* WfsCompass.raytrace + compute_wfs_image fused (wfsCompass.py:334-343, sourceCompass.py:54-85).
+ * flags: bit0 atmosphere, bit1 mirrors, bit2 keep image (writes AOM_B_BINCUBE). noise: sensor noise for
+ * this frame (pass cfg.noise for the configured value).  Also leaves the centre-of-gravity slopes of the
+ * frame for aom_do_centroids. */
+int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* stream);
+
+/* Materialise the pupil-plane phase seen by the sensor (wfs.get_wfs_phase) into AOM_B_PHASE. */
+int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream);
+
+/* Replace the detector image (RlSupervisor.autoencoder_denoising -> set_binimg, rlSupervisor.py:876-891):
+ * device pointer to float [E][nvalid][npix*npix]; the next aom_do_centroids reads it. */
+int aom_set_bincube(aom_ctx* ctx, const float* dcube, void* stream);
+
+/* RtcCompass.do_centroids / do_control / set_command / apply_control (rtcCompass.py:557-563, 527-547, 463-473, 573-582) */
+int aom_do_centroids(aom_ctx* ctx, void* stream);
+int aom_do_control(aom_ctx* ctx, void* stream);
+int aom_set_command(aom_ctx* ctx, const float* dcom, int ld, void* stream);
+int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream);
+int aom_set_gain(aom_ctx* ctx, float gain);
+int aom_set_loop(aom_ctx* ctx, int closed);       /* rtc.open_loop / close_loop (rtcCompass.py:116-142) */
+int aom_reset_dm(aom_ctx* ctx, void* stream);     /* DmCompass.reset_dm */
+int aom_set_dm_volts(aom_ctx* ctx, const float* dvolts, int ld, void* stream); /* DmCompass.set_command */
+
+/* RlSupervisor.rl_control (rlSupervisor.py:713-733, 784-818): com <- m2v.(v2m.com + scatter(a * f)).
+ * daction: device float [E][ld(action_dim)] (NULL: use AOM_B_ACTION). */
+int aom_rl_control(aom_ctx* ctx, const float* daction, void* stream);
+
+/* AoEnv.linear_step state assembly (ao_env.py:871-909): call aom_state_begin BEFORE the frame (captures the
+ * command "before linear"), aom_state_end after do_control (projects, standardises, pushes history). */
+int aom_state_begin(aom_ctx* ctx, void* stream);
+int aom_state_end(aom_ctx* ctx, void* stream);
+
+/* TrainerRPC.divide_rewards_for_agents (train_rpc.py:402-416): r[e][w] = -factor * mean((v2m.err)[a0:a1]^2) */
+int aom_reward(aom_ctx* ctx, float factor, void* stream);
+
+/* TrainerRPC.choose_action -> GaussianPolicy.sample(only_choosing_action=True) for every agent
+ * (train_rpc.py:706-732, model_rpc.py:121-158).  eval_mode != 0: action = tanh(mean). */
+int aom_actor_forward(aom_ctx* ctx, int eval_mode, void* stream);
+
+/* One whole env-step: rl half-step (rl_control + apply_control + reward) and linear half-step
+ * (move_atmos + WFS frame + centroids + control + state) -- TrainerRPC.env_step (train_rpc.py:633-648).
+ * mode 0: actions from aom_actor_forward on the current state; 1: actions from AOM_B_ACTION; 2: integrator only. */
+int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream);
+
+/* Generic device GEMM used by the path, exposed for the parity tests:
+ * C[M][ldc] = A[M][lda] . B[N][ldb]^T (+ bias[N]) ; relu optional. */
+int aom_gemm_tn(aom_ctx* ctx, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                int M, int N, int K, const float* bias, int relu, void* stream);
+
+/* Sensor-noise sampler exposed for the parity tests: out[i] = noise(lam[i]) with pixel index i. */
+int aom_pixel_noise(aom_ctx* ctx, const float* dlam, float* dout, int64_t n, float noise, int64_t seed,
+                    uint32_t frame, uint32_t wfs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AOMARL_H */

@@ -1,0 +1,228 @@
+"""Parity of the CUDA path (through the C ABI) against the numpy oracle on identical seeds.
+
+Tolerances: integers (photon counts, ring offsets) bit-exact; float32 slopes / commands / rewards
+rel 1e-4 of the oracle's scale (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def sim10(static10, torch):
+    from ao_marl_b200.lib import Simulator
+    sim = Simulator(static10, 4, rl=None)
+    yield sim
+    sim.close()
+
+
+def test_gemm_tn(sim10, torch):
+    from ao_marl_b200.lib import LD
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (M, N, K) in ((1, 5, 7), (4, 648, 1957), (300, 90, 128), (257, 129, 100)):
+        A = torch.zeros((M, LD(K)), device="cuda")
+        Bm = torch.zeros((N, LD(K)), device="cuda")
+        A[:, :K] = torch.randn((M, K), device="cuda", generator=g)
+        Bm[:, :K] = torch.randn((N, K), device="cuda", generator=g)
+        bias = torch.randn(N, device="cuda", generator=g)
+        C = sim10.gemm_tn(A, Bm, bias=bias, relu=True)
+        ref = torch.relu(A.double() @ Bm.double().T + bias.double())
+        assert relerr(C[:, :N].cpu().numpy(), ref.cpu().numpy()) < 1e-5
+        assert float(C[:, N:].abs().max()) == 0.0 if C.shape[1] > N else True
+
+
+def test_pixel_noise_bit_exact(sim10, torch):
+    from oracle import rng
+    r = np.random.default_rng(3)
+    lam = (r.random(200000) ** 3 * 400).astype(np.float32)
+    lam[:100] = 0
+    for noise in (0.0, 3.0):
+        out = sim10.pixel_noise(torch.as_tensor(lam, device="cuda"), noise, 2 ** 40 + 17, 9, 1).cpu().numpy()
+        ref = rng.wfs_pixel_noise(2 ** 40 + 17, 1, 9, lam, noise)
+        assert np.array_equal(out, ref)
+
+
+def _oracle_atmos(tab, seed):
+    from oracle import aoframe
+    a = aoframe.OracleAtmos(tab, seed)
+    a.reset(seed)
+    return a
+
+
+def _logical_screen(sim, layer, env):
+    n = int(sim.cfg.screen_dim[layer])
+    scr = sim.buffer("SCREEN", layer).view(sim.n_env, n, n)[env]
+    ox = int(sim.buffer("RING_OX", layer)[env])
+    oy = int(sim.buffer("RING_OY", layer)[env])
+    return np.roll(scr.cpu().numpy(), (-oy, -ox), axis=(0, 1)), ox, oy
+
+
+def test_turbulence_extrusion(sim10, oracle_tab10, torch):
+    seeds = np.array([1234, 1235, 77, 2 ** 33 + 5], dtype=np.int64)
+    sim10.reset(seeds)
+    torch.cuda.synchronize()
+    oracles = [_oracle_atmos(oracle_tab10, s) for s in seeds[:2]]
+    for e, o in enumerate(oracles):
+        got, ox, oy = _logical_screen(sim10, 0, e)
+        assert relerr(got, o.screens[0]) < RTOL
+    for _ in range(7):
+        sim10.move_atmos()
+        for o in oracles:
+            o.move()
+    torch.cuda.synchronize()
+    for e, o in enumerate(oracles):
+        got, ox, oy = _logical_screen(sim10, 0, e)
+        assert relerr(got, o.screens[0]) < RTOL
+    # environments with different seeds differ
+    a, _, _ = _logical_screen(sim10, 0, 0)
+    b, _, _ = _logical_screen(sim10, 0, 2)
+    assert np.abs(a - b).max() > 0.1 * np.abs(a).max()
+
+
+def test_phase_and_frame(sim10, oracle_tab10, oracle_imat10, static10, torch):
+    """raytrace + mirrors + SH image + COG against the oracle on a turbulent screen with non-zero volts."""
+    from oracle import loop
+    seeds = np.array([1234, 1235, 77, 99], dtype=np.int64)
+    sim10.reset(seeds)
+    r = np.random.default_rng(5)
+    volts = (r.standard_normal((4, static10.nactu)) * 20).astype(np.float32)
+    volts[:, -2:] *= 5
+    sim10.set_dm_volts(torch.as_tensor(volts, device="cuda"))
+    for _ in range(3):
+        sim10.move_atmos()
+    envs = []
+    for e in range(2):
+        o = loop.OracleEnv(oracle_tab10, np.zeros((static10.nactu, static10.nslopes), np.float32), seed=int(seeds[e]))
+        o.reset(int(seeds[e]))
+        o.volts = volts[e].copy()
+        for _ in range(3):
+            o.atm.move()
+        envs.append(o)
+    ph = sim10.raytrace_wfs().cpu().numpy()
+    for e, o in enumerate(envs):
+        ref = o.wfs_phase()
+        assert relerr(ph[e], ref) < 2e-5
+        assert relerr(sim10.raytrace_wfs(atmos=False)[e].cpu().numpy(), o.wfs_phase(atmos=False)) < 2e-5
+    sim10.comp_wfs_image(keep_image=True, noise=-1.0)
+    sim10.do_centroids()
+    s = sim10.rows("SLOPES", static10.nslopes).cpu().numpy()
+    cube = sim10.buffer("BINCUBE").view(4, static10.p_wfs._nvalid, 16, 16).cpu().numpy()
+    for e, o in enumerate(envs):
+        sref, cref = o.comp_wfs_image(noise=-1.0, keep=True)
+        assert relerr(cube[e], cref) < 1e-4
+        assert relerr(s[e], sref) < RTOL
+
+
+def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
+    """Photon noise: the oracle's sampler applied to the GPU's noise-free image reproduces the GPU's
+    noisy image exactly (same Philox stream, same integer Poisson draws)."""
+    from oracle import aoframe
+    seeds = np.array([11, 12, 13, 14], dtype=np.int64)
+    sim10.reset(seeds)
+    sim10.comp_wfs_image(keep_image=True, noise=-1.0)       # frame 0
+    clean = sim10.buffer("BINCUBE").clone().view(4, -1).cpu().numpy()
+    sim10.reset(seeds)
+    sim10.comp_wfs_image(keep_image=True, noise=3.0)        # frame 0 again, same screens
+    noisy = sim10.buffer("BINCUBE").view(4, -1).cpu().numpy()
+    for e in range(4):
+        ref = aoframe.sh_noise(clean[e], 3.0, int(seeds[e]), static10.wfs_index, 0)
+        assert np.array_equal(noisy[e], ref)
+
+
+def test_imat_matches_oracle(static10, oracle_imat10, torch):
+    from ao_marl_b200 import calibration
+    D = calibration.measure_imat(static10)
+    assert D.shape == oracle_imat10.shape
+    assert relerr(D, oracle_imat10) < RTOL
+
+
+@pytest.fixture(scope="module")
+def system10(static10, oracle_imat10, torch):
+    """Full 10x10 system (2 agents: 80 modes + tip-tilt) built on the GPU-measured imat."""
+    import copy
+    from ao_marl_b200 import calibration
+    from ao_marl_b200.init import rtc as rtc_b
+    from ao_marl_b200.lib import Simulator
+    from ao_marl_b200.rl.layout import RLLayout
+    t = copy.copy(static10)
+    t.imat = calibration.measure_imat(static10)
+    t.cmat = rtc_b.cmat_with_btt(t.imat, t.Btt, 5)
+    rl = RLLayout(t.Btt.shape[1], dict(parameters_telescope="production_sh_10x10_2m.py", n_zernike_start_end=[0, 80],
+                                       n_reverse_filtered_from_cmat=5), None, world_size=3, seed=3)
+    import torch as th
+    with th.no_grad():           # non-trivial heads so that actions are not all zero-mean/unit-std
+        for p in rl.policies:
+            p.mean_linear.weight.normal_(0, 0.05)
+            p.log_std_linear.weight.normal_(0, 0.05)
+            p.log_std_linear.bias.fill_(-1.0)
+    sim = Simulator(t, 3, rl)
+    yield sim, t, rl
+    sim.close()
+
+
+def test_closed_loop_against_oracle(system10, oracle_tab10, torch):
+    from oracle import loop
+    sim, t, rl = system10
+    seeds = np.array([1234, 4321, 999], dtype=np.int64)
+    sim.reset(seeds)
+    envs = [loop.OracleEnv(oracle_tab10, t.cmat, t.Btt, t.P, rl, seed=int(s)) for s in seeds[:2]]
+    for o, s in zip(envs, seeds):
+        o.reset(int(s))
+    # initial linear step (AoEnv.reset ends with one, ao_env.py:354)
+    sim.state_begin(); sim.move_atmos(); sim.comp_wfs_image(); sim.do_centroids(); sim.do_control(); sim.state_end()
+    states = [o.linear_step() for o in envs]
+    st = sim.rows("STATE", rl.state_dim).cpu().numpy()
+    for e in range(2):
+        assert relerr(st[e], states[e]) < RTOL
+    for it in range(12):
+        sim.step(mode=0)
+        act = sim.rows("ACTION", rl.action_dim).cpu().numpy()
+        rew = sim.buffer("REWARD").view(3, rl.n_agents).cpu().numpy()
+        st = sim.rows("STATE", rl.state_dim).cpu().numpy()
+        com = sim.rows("COM", t.nactu).cpu().numpy()
+        sl = sim.rows("SLOPES", t.nslopes).cpu().numpy()
+        for e, o in enumerate(envs):
+            a, _ = o.actors(states[e])
+            assert relerr(act[e], a) < 5e-4, "actions, step %d" % it
+            states[e], r = o.env_step(act[e])     # feed the GPU's action so that errors do not compound through tanh
+            assert relerr(sl[e], o.slopes) < 5 * RTOL, "slopes, step %d" % it
+            assert relerr(com[e], o.com) < 5 * RTOL, "commands, step %d" % it
+            assert relerr(rew[e], r) < 1e-3, "rewards, step %d" % it
+            assert relerr(st[e], states[e]) < 1e-3, "state, step %d" % it
+
+
+def test_delay_impulse(system10, torch):
+    """An action impulse at step t shows in d_err at frame t+2 for delay 1 (train_rpc.py:620-630)."""
+    sim, t, rl = system10
+    sim.reset(np.array([5, 5, 5], dtype=np.int64))
+    assert int(round(t.delay)) == 1
+    sim.set_loop(False)                      # integrator frozen: only the injected action moves the mirror
+    try:
+        errs = []
+        for it in range(5):
+            a = torch.zeros((3, rl.action_dim), device="cuda")
+            if it == 1:
+                a[1, 0] = 5.0                # env 1 only
+            sim.rows("ACTION", rl.action_dim).copy_(a)
+            sim.step(mode=1)
+            e = sim.rows("ERR", t.nactu)
+            errs.append(float((e[1] - e[0]).abs().max()))
+        assert errs[0] == 0.0 and errs[1] == 0.0
+        assert errs[2] > 0.0                 # frame t+1 in 0-based counting of frames after the action step
+    finally:
+        sim.set_loop(True)
