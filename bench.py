@@ -261,12 +261,14 @@ def run_ours(args):
     barrier()
     sampler.start()
     l0 = sim.launches()
+    torch.cuda.profiler.start()      # ncu --profile-from-start off captures the timed region only
     e0, e1 = ev(enable_timing=True), ev(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         one_step(True)
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = sim.launches() - l0
     ms = e0.elapsed_time(e1)
