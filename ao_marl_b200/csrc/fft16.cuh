@@ -10,6 +10,7 @@
 // the second radix-4 stage.  Forward sign exp(-2 pi i k n / N), as numpy.fft / cuFFT forward.
 #pragma once
 #include "rng.cuh"
+#include "twiddles.cuh"
 
 #define AOM_C_PI 3.14159265358979323846
 
@@ -24,19 +25,10 @@ AOM_HD void aom_cmul_conj(float ar, float ai, float c, float s, float& orr, floa
   oi = ai * c - ar * s;
 }
 
-// in: xr/xi[16]; twr/twi[16] = cos/sin parts of W_N^{b n} as (cos, -sin) i.e. the complex value itself
-// out[o], o = q      -> a = q       (k = R q + b,        non-negative frequencies)
-//         o = 4 + q  -> a = 12 + q  (k = R (12 + q) + b, negative frequencies)
-AOM_HD void aom_fft16_pruned(const float* xr, const float* xi, const float* twr, const float* twi,
-                             float* outr, float* outi) {
-  float ur[16], ui[16];
-  ur[0] = xr[0];
-  ui[0] = xi[0];
-#pragma unroll
-  for (int n = 1; n < 16; ++n) {
-    ur[n] = xr[n] * twr[n] - xi[n] * twi[n];
-    ui[n] = xr[n] * twi[n] + xi[n] * twr[n];
-  }
+// Radix-4 x radix-4 16-point DFT of u, pruned to the outputs a in {0,1,2,3,12,13,14,15}:
+// out[o], o = q      -> a = q       (non-negative frequencies)
+//         o = 4 + q  -> a = 12 + q  (negative frequencies)
+AOM_HD void aom_fft16_core(const float* ur, const float* ui, float* outr, float* outi) {
   float yr[4][4], yi[4][4];  // [q][m]
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
@@ -71,4 +63,39 @@ AOM_HD void aom_fft16_pruned(const float* xr, const float* xi, const float* twr,
     outr[4 + q] = (yr[q][0] - yr[q][2]) - (yi[q][1] - yi[q][3]);
     outi[4 + q] = (yi[q][0] - yi[q][2]) + (yr[q][1] - yr[q][3]);
   }
+}
+
+// x . W_N^{b n} with the twiddles read from memory (row pass: b differs between lanes), then the core.
+// twr/twi[16] hold the complex value W_N^{b n} = (cos, -sin).
+AOM_HD void aom_fft16_pruned(const float* xr, const float* xi, const float* twr, const float* twi,
+                             float* outr, float* outi) {
+  float ur[16], ui[16];
+  ur[0] = xr[0];
+  ui[0] = xi[0];
+#pragma unroll
+  for (int n = 1; n < 16; ++n) {
+    ur[n] = xr[n] * twr[n] - xi[n] * twi[n];
+    ui[n] = xr[n] * twi[n] + xi[n] * twr[n];
+  }
+  aom_fft16_core(ur, ui, outr, outi);
+}
+
+// Same with a compile-time phase class B of an N = 16 R point transform: the twiddles fold into immediates
+// (column pass: every lane of the warp works on the same b).
+template <int R, int B>
+AOM_HD void aom_fft16_pruned_const(const float* xr, const float* xi, float* outr, float* outi) {
+  if (B == 0) {
+    aom_fft16_core(xr, xi, outr, outi);
+    return;
+  }
+  float ur[16], ui[16];
+  ur[0] = xr[0];
+  ui[0] = xi[0];
+#pragma unroll
+  for (int n = 1; n < 16; ++n) {
+    const float c = aom_tw_c((128 / (16 * R)) * B * n), s = aom_tw_s((128 / (16 * R)) * B * n);
+    ur[n] = xr[n] * c + xi[n] * s;       // (xr + i xi)(c - i s)
+    ui[n] = xi[n] * c - xr[n] * s;
+  }
+  aom_fft16_core(ur, ui, outr, outi);
 }

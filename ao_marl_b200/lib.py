@@ -297,6 +297,16 @@ class Simulator:
         self.set_table("CMAT", pad_rows(cmat))
         self.cmat = cmat
 
+    def env_seeds(self, seed):
+        """int64 [E] seeds from a scalar (environment e gets seed + e, so E == 1 keeps the reference's
+        single stream) or from an explicit array."""
+        seed = np.asarray(seed, dtype=np.int64)
+        if seed.ndim == 0:
+            return seed + np.arange(self.n_env, dtype=np.int64)
+        if seed.shape != (self.n_env,):
+            raise ValueError("Dimension mismatch")
+        return seed
+
     # -- ops (thin, asynchronous on the current stream) -----------------------------------------
     def reset(self, seeds):
         seeds = np.ascontiguousarray(np.broadcast_to(np.asarray(seeds, dtype=np.int64), (self.n_env,)))

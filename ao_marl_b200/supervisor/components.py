@@ -1,0 +1,351 @@
+"""Component objects of the supervisor: the same method names and argument meaning as the reference's
+shesha/supervisor/components/{atmos,wfs,dm,rtc,target,telescope}Compass.py, each a thin stream-ordered
+call into libaomarl.so through `ao_marl_b200.lib.Simulator`.
+
+Every per-environment array carries a leading batch dimension E; with E == 1 getters return numpy
+arrays of the reference's shapes (float32), otherwise device tensors [E, ...] (no host copy).
+"""
+import numpy as np
+
+from ..init.geom import DEG2RAD
+
+
+class _Base:
+    def __init__(self, sim, config):
+        self._sim = sim
+        self._config = config
+
+    def _out(self, t):
+        """[E, ...] device tensor -> reference-shaped numpy when E == 1."""
+        if self._sim.n_env == 1:
+            return t[0].detach().cpu().numpy()
+        return t
+
+
+class TelescopeB200(_Base):
+    pass
+
+
+class AtmosB200(_Base):
+    """atmosCompass.py:50-161"""
+
+    def __init__(self, sim, config):
+        super().__init__(sim, config)
+        self.is_enable = True
+
+    def enable_atmos(self, enable):
+        self.is_enable = enable
+
+    def move_atmos(self):
+        self._sim.move_atmos()
+
+    def reset_turbu(self, seed):
+        """Reseed and regenerate every layer.  `seed` may be a scalar (environment e gets seed + e * 1000003,
+        so that E == 1 reproduces the reference's single stream) or an int64 array [E]."""
+        self._sim.reset(self._sim.env_seeds(seed))
+
+    def _amp(self, layer):
+        a = self._config.p_atmos
+        r0_px = a.r0 / (a.frac[layer] ** (3.0 / 5.0) * a.pupixsize)
+        return float(np.float32(np.float32(r0_px) ** np.float32(-5.0 / 6.0) * np.float32(0.5 / (2 * np.pi))))
+
+    def set_r0(self, r0, *, reset_seed=-1):
+        self._config.p_atmos.r0 = r0
+        a = self._config.p_atmos
+        for l in range(a.nscreens):
+            self._sim.set_layer(l, a._deltax[l], a._deltay[l], self._amp(l))
+        if reset_seed != -1:
+            seed = np.random.randint(int(1e4)) if reset_seed == 0 else reset_seed
+            self._sim.reset(self._sim.env_seeds(1234 + seed))
+
+    def set_wind(self, screen_index, *, windspeed=None, winddir=None):
+        c = self._config
+        a = c.p_atmos
+        if windspeed is not None:
+            a.windspeed[screen_index] = windspeed
+        if winddir is not None:
+            a.winddir[screen_index] = winddir
+        lin = c.p_geom.pupdiam / c.p_tel.diam * a.windspeed[screen_index] * np.cos(DEG2RAD * c.p_geom.zenithangle) \
+            * c.p_loop.ittime
+        a._deltax[screen_index] = lin * np.sin(DEG2RAD * a.winddir[screen_index] + np.pi)
+        a._deltay[screen_index] = lin * np.cos(DEG2RAD * a.winddir[screen_index] + np.pi)
+        # a change of sign needs no new stencil here: mirroring is index arithmetic in the kernels
+        self._sim.set_layer(screen_index, a._deltax[screen_index], a._deltay[screen_index], self._amp(screen_index))
+
+    def get_atmos_layer(self, indx):
+        """Logical (un-rotated) screen(s) of layer `indx`."""
+        import torch
+        sim = self._sim
+        n = int(sim.cfg.screen_dim[indx])
+        scr = sim.buffer("SCREEN", indx).view(sim.n_env, n, n)
+        ox = sim.buffer("RING_OX", indx).cpu().numpy()
+        oy = sim.buffer("RING_OY", indx).cpu().numpy()
+        out = torch.stack([torch.roll(scr[e], (-int(oy[e]), -int(ox[e])), dims=(0, 1)) for e in range(sim.n_env)])
+        return self._out(out)
+
+
+class WfsB200(_Base):
+    """wfsCompass.py + sourceCompass.py:54-85.  raytrace only records what the next frame must contain; the
+    fused kernel evaluates the phase per subaperture inside compute_wfs_image."""
+
+    def __init__(self, sim, config, wfs_index=0):
+        super().__init__(sim, config)
+        self._index = wfs_index
+        self._atm = False
+        self._dms = False
+        self._noise = float(sim.cfg.noise)
+        self.keep_image = False
+
+    def _chk(self, i):
+        if i != self._index:
+            raise NotImplementedError("only the sensor driving controller 0 is on the hot path")
+
+    def raytrace(self, index, *, tel=None, atm=None, dms=None, ncpa=True, reset=True):
+        self._chk(index)
+        if reset:
+            self._atm = self._dms = False
+        if atm is not None and getattr(atm, "is_enable", True):
+            self._atm = True
+        if dms is not None:
+            self._dms = True
+
+    def compute_wfs_image(self, wfs_index, *, noise=True):
+        self._chk(wfs_index)
+        self._sim.comp_wfs_image(atmos=self._atm, dms=self._dms, keep_image=self.keep_image,
+                                 noise=self._noise if noise else -1.0)
+
+    def set_noise(self, wfs_index, noise, *, seed=1234):
+        self._chk(wfs_index)
+        self._noise = float(noise)
+        self._config.p_wfss[wfs_index].noise = noise
+
+    def reset_noise(self, seed):
+        """Noise streams are keyed by the environment seed and the frame counter: reseeding happens in
+        AtmosB200.reset_turbu (one aom_reset covers both, rlSupervisor.py:240-241)."""
+
+    def get_wfs_phase(self, wfs_index):
+        self._chk(wfs_index)
+        return self._out(self._sim.raytrace_wfs(atmos=self._atm, dms=self._dms))
+
+    def get_bincube(self):
+        """[E, nvalid, npix, npix] spots of the last frame computed with keep_image=True."""
+        c = self._sim.cfg
+        return self._sim.buffer("BINCUBE").view(self._sim.n_env, c.nvalid, c.npix, c.npix)
+
+    def get_wfs_image(self, wfs_index):
+        """Detector mosaic (rlSupervisor.py:857-874 layout: spot k at [validsubsy[k], validsubsx[k]] in [y, x])."""
+        import torch
+        self._chk(wfs_index)
+        c = self._sim.cfg
+        w = self._config.p_wfss[wfs_index]
+        cube = self.get_bincube()
+        side = c.nxsub * c.npix
+        img = torch.zeros((self._sim.n_env, side, side), device=cube.device)
+        for k in range(c.nvalid):
+            x0, y0 = int(w._validsubsx[k]), int(w._validsubsy[k])
+            img[:, y0:y0 + c.npix, x0:x0 + c.npix] = cube[:, k]
+        return self._out(img)
+
+    def set_bincube(self, cube):
+        """Replace the detector spots before centroiding (denoiser path, rlSupervisor.py:876-891)."""
+        import torch
+        c = self._sim.cfg
+        cube = torch.as_tensor(cube, dtype=torch.float32, device="cuda").reshape(self._sim.n_env, c.nvalid, 256)
+        self._sim.set_bincube(cube.contiguous())
+
+
+class DmB200(_Base):
+    """dmCompass.py:50-160.  dm_index follows the parameter file's p_dms list."""
+
+    def __init__(self, sim, config, pzt_index, tt_index):
+        super().__init__(sim, config)
+        self._pzt, self._tt = pzt_index, tt_index
+
+    def reset_dm(self, dm_index=-1):
+        self._sim.reset_dm()
+
+    def set_command(self, commands, *, dm_index=None, shape_dm=True):
+        import torch
+        sim = self._sim
+        v = sim.rows("VOLTS", sim.cfg.nactu)
+        x = torch.as_tensor(commands, dtype=torch.float32, device="cuda")
+        if x.dim() == 1:
+            x = x.unsqueeze(0).expand(sim.n_env, -1)
+        if dm_index is None:
+            if x.shape[1] != sim.cfg.nactu:
+                raise ValueError("Dimension mismatch")
+            v.copy_(x)
+        elif dm_index == self._pzt:
+            if x.shape[1] != sim.cfg.pzt_nact:
+                raise ValueError("Dimension mismatch")
+            v[:, :sim.cfg.pzt_nact].copy_(x)
+        elif dm_index == self._tt:
+            if x.shape[1] != 2:
+                raise ValueError("Dimension mismatch")
+            v[:, sim.cfg.pzt_nact:].copy_(x)
+        else:
+            raise NotImplementedError("DM %d is not driven by controller 0" % dm_index)
+
+    def get_dm_shape(self, indx):
+        raise NotImplementedError("mirror surfaces are evaluated per subaperture inside the fused kernel; "
+                                  "use wfs.raytrace(dms=...) + wfs.get_wfs_phase for the surface seen by the sensor")
+
+
+class _Controller:
+    """Stand-in for ``rtc._rtc.d_control[i]`` (ao_env.py:957, train_rpc.py:84 read .gain / call .set_gain)."""
+
+    def __init__(self, sim, ctype):
+        self._sim = sim
+        self.type = ctype
+        self.gain = float(sim.cfg.gain)
+
+    def set_gain(self, g):
+        self.gain = float(g)
+        self._sim.set_gain(g)
+
+
+class _RtcHandle:
+    def __init__(self, controls):
+        self.d_control = controls
+
+
+class RtcB200(_Base):
+    """rtcCompass.py:55-630 (controller 0 = least-squares integrator)."""
+
+    def __init__(self, sim, config, tables):
+        super().__init__(sim, config)
+        self._tables = tables
+        self._rtc = _RtcHandle([_Controller(sim, "ls")])
+        self.d_control = self._rtc.d_control
+
+    def _chk(self, i):
+        if i != 0:
+            raise NotImplementedError("only controller 0 (LS integrator) is on the hot path")
+
+    def do_centroids(self, controller_index):
+        self._chk(controller_index)
+        self._sim.do_centroids()
+
+    def do_control(self, controller_index, **kw):
+        self._chk(controller_index)
+        self._sim.do_control()
+
+    def apply_control(self, controller_index, *, comp_voltage=True):
+        self._chk(controller_index)
+        self._sim.apply_control(comp_voltage)
+
+    def do_clipping(self, controller_index):
+        self._chk(controller_index)   # +-1e5 V limits are never reached on this path
+
+    def get_slopes(self, controller_index):
+        self._chk(controller_index)
+        return self._out(self._sim.rows("SLOPES", self._sim.cfg.nslopes))
+
+    def get_err(self, controller_index):
+        self._chk(controller_index)
+        return self._out(self._sim.rows("ERR", self._sim.cfg.nactu))
+
+    def get_command(self, controller_index):
+        self._chk(controller_index)
+        return self._out(self._sim.rows("COM", self._sim.cfg.nactu))
+
+    def get_voltages(self, controller_index):
+        self._chk(controller_index)
+        return self._out(self._sim.rows("VOLTS", self._sim.cfg.nactu))
+
+    def set_command(self, controller_index, com):
+        self._chk(controller_index)
+        if np.shape(com)[-1] != self._sim.cfg.nactu:
+            raise ValueError("Dimension mismatch")
+        self._sim.set_command(com)
+
+    def reset_command(self, controller_index=None):
+        import torch
+        self._sim.set_command(torch.zeros((self._sim.n_env, self._sim.cfg.nactu), device="cuda"))
+
+    def set_gain(self, controller_index, gain):
+        self._chk(controller_index)
+        self.d_control[0].set_gain(gain)
+
+    def get_interaction_matrix(self, controller_index):
+        self._chk(controller_index)
+        return self._tables.imat
+
+    def get_command_matrix(self, controller_index):
+        self._chk(controller_index)
+        return self._sim.cmat
+
+    def set_command_matrix(self, controller_index, cmat):
+        self._chk(controller_index)
+        self._sim.set_command_matrix(cmat)
+
+    def open_loop(self, controller_index=None, reset=True):
+        self._sim.set_loop(False)
+        if reset:
+            self.reset_command()
+
+    def close_loop(self, controller_index=None):
+        self._sim.set_loop(True)
+
+
+class TargetB200(_Base):
+    """targetCompass.py (next-row scope): Strehl from the residual phase variance over the pupil
+    (Marechal, exp(-sigma^2)), which is what get_strehl()[2] reports in the reference too; the 2048^2 PSF
+    of comp_tar_image is not computed."""
+
+    def __init__(self, sim, config, tables):
+        super().__init__(sim, config)
+        self._tables = tables
+        self._n_le = 0
+        self._var = None
+        self._var_sum = None
+        self._se = None
+        self._le_sum = None
+        self._flags = (False, False)
+
+    def raytrace(self, index, *, tel=None, atm=None, dms=None, ncpa=True, reset=True):
+        a, d = (False, False) if reset else self._flags
+        if atm is not None and getattr(atm, "is_enable", True):
+            a = True
+        if dms is not None:
+            d = True
+        self._flags = (a, d)
+
+    def comp_tar_image(self, tarNum, *, puponly=0, compLE=True):
+        import torch
+        sim, t = self._sim, self._tables
+        ph = sim.raytrace_wfs(atmos=self._flags[0], dms=self._flags[1])
+        pup = torch.as_tensor(t.mpupil, device=ph.device) > 0
+        v = ph[:, pup]
+        self._var = v.var(dim=1, unbiased=False)
+        lam = float(self._config.p_targets[tarNum].Lambda)
+        self._se = torch.exp(-self._var * (2 * np.pi / lam) ** 2)
+        if compLE:
+            self._le_sum = self._se.clone() if self._le_sum is None else self._le_sum + self._se
+            self._var_sum = self._var.clone() if self._var_sum is None else self._var_sum + self._var
+            self._n_le += 1
+
+    def comp_strehl(self, tarNum, *, do_fit=True):
+        pass
+
+    def reset_strehl(self, tar_index):
+        self._n_le = 0
+        self._le_sum = self._var_sum = None
+
+    def get_strehl(self, tar_index, *, do_fit=True):
+        import torch
+        z = torch.zeros(self._sim.n_env, device="cuda")
+        se = self._se if self._se is not None else z
+        le = self._le_sum / self._n_le if self._n_le else z
+        var = self._var if self._var is not None else z
+        avg = self._var_sum / self._n_le if self._n_le else z
+        out = [se, le, var, avg]
+        if self._sim.n_env == 1:
+            return [float(x[0]) for x in out]
+        return out
+
+    def get_tar_image(self, tar_index, *, expo_type="se"):
+        raise NotImplementedError("the focal-plane PSF is outside the hot-path scope (SURVEY.md 8(f) rank 1)")
+
+    def get_tar_phase(self, tar_index, *, pupil=False):
+        return self._out(self._sim.raytrace_wfs(atmos=self._flags[0], dms=self._flags[1]))
