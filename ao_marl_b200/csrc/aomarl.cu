@@ -9,8 +9,10 @@
 #include "../../include/aomarl.h"
 #include "atmos_kernels.cuh"
 #include "gemm_kernels.cuh"
+#include "gemm_tc.cuh"
 #include "rtc_kernels.cuh"
 #include "wfs_kernels.cuh"
+#include "wfs_mma.cuh"
 
 static char g_create_error[512] = "";
 
@@ -40,6 +42,8 @@ struct aom_ctx {
   float gain;
   int closed;
   uint32_t frame;
+  int opt[AOM_OPT_COUNT];
+  int* d_err;                 // device error word raised by bounded waits (gemm_tc.cuh)
   // RL
   float *modes, *modes_before, *modes_res, *state, *hist, *reward, *action, *action_mean, *strehl;
   int ldst, ldact, hist_head;
@@ -105,6 +109,14 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
   ctx->cfg = *cfg;
   ctx->gain = cfg->gain;
   ctx->closed = 1;
+  {
+    // development overrides of the default kernel paths (see aom_set_option)
+    const char* g = getenv("AOM_GEMM_PATH");
+    if (g && !strcmp(g, "simt")) ctx->opt[AOM_OPT_GEMM_PATH] = AOM_GEMM_SIMT;
+    const char* w = getenv("AOM_WFS_PATH");
+    if (w && !strcmp(w, "simt")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_SIMT;
+    if (w && !strcmp(w, "tensor_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_FAST;
+  }
   *out = ctx;   // returned even on failure so that aom_last_error / aom_destroy work
   CU(cudaGetDevice(&ctx->device));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -163,6 +175,9 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     CU(dalloc(&ctx->aH2, A * E * ctx->ld_ah));
     CU(dalloc(&ctx->aHO, A * E * ctx->ld_aho));
   }
+  CU(dalloc(&ctx->d_err, 1));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES));
   CU(cudaFuncSetAttribute(wfs_frame_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfs_smem_bytes<4>()));
   CU(cudaFuncSetAttribute(wfs_frame_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfs_smem_bytes<8>()));
   return AOM_OK;
@@ -178,7 +193,7 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
   void* bufs[] = {ctx->k0, ctx->k1, ctx->Z, ctx->zref, ctx->newcol, ctx->slopes_frame, ctx->slopes, ctx->err_v,
                   ctx->com, ctx->com1, ctx->volts, ctx->com_before, ctx->bincube, ctx->phase, ctx->modes,
                   ctx->modes_before, ctx->modes_res, ctx->state, ctx->hist, ctx->reward, ctx->action,
-                  ctx->action_mean, ctx->strehl, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO};
+                  ctx->action_mean, ctx->strehl, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO, ctx->d_err};
   for (void* b : bufs) cudaFree(b);
   free(ctx);
 }
@@ -283,7 +298,8 @@ extern "C" int aom_get_buffer(aom_ctx* ctx, int buffer, int index, void** dptr, 
 // ---------------------------------------------------------------------------------------------
 static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long sA, const float* B, int ldb,
                        long long sB, float* C, int ldc, long long sC, int M, int N, int K, const float* bias,
-                       long long sBias, int relu, int batch, cudaStream_t st, float* com = nullptr, int ldcom = 0) {
+                       long long sBias, int relu, int batch, cudaStream_t st, float* com = nullptr, int ldcom = 0,
+                       bool exact = false) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int Kp = AOM_LD(K);
@@ -293,9 +309,17 @@ static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.M = M; p.N = N; p.K = Kp;
   p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias; p.relu = relu;
   p.com = com; p.ldcom = ldcom; p.gain = ctx->gain; p.closed = ctx->closed;
-  dim3 grid((ldc + GEMM_BN - 1) / GEMM_BN, (M + GEMM_BM - 1) / GEMM_BM, batch);
-  if (epi == 0) gemm_tn_kernel<0><<<grid, 256, 0, st>>>(p);
-  else gemm_tn_kernel<1><<<grid, 256, 0, st>>>(p);
+  // `exact`: float32 FFMA accumulation with round-to-nearest (the recursive screen extrusion needs it: the
+  // tensor core truncates its float32 accumulator, a ~1e-5 systematic shrink that an autoregression integrates)
+  if (!exact && ctx->opt[AOM_OPT_GEMM_PATH] == AOM_GEMM_TCGEN05) {
+    dim3 grid((ldc + GTC_BN - 1) / GTC_BN, (M + GTC_BM - 1) / GTC_BM, batch);
+    if (epi == 0) gemm_tc_kernel<0><<<grid, GTC_THREADS, GTC_SMEM_BYTES, st>>>(p, ctx->d_err);
+    else gemm_tc_kernel<1><<<grid, GTC_THREADS, GTC_SMEM_BYTES, st>>>(p, ctx->d_err);
+  } else {
+    dim3 grid((ldc + GEMM_BN - 1) / GEMM_BN, (M + GEMM_BM - 1) / GEMM_BM, batch);
+    if (epi == 0) gemm_tn_kernel<0><<<grid, 256, 0, st>>>(p);
+    else gemm_tn_kernel<1><<<grid, 256, 0, st>>>(p);
+  }
   KCHECK();
   return AOM_OK;
 }
@@ -321,7 +345,7 @@ static int extrude_once(aom_ctx* ctx, int l, int axis, int sign, cudaStream_t st
   extrude_gather_kernel<<<g1, 256, 0, st>>>(p);
   KCHECK();
   int rc = launch_gemm(ctx, 0, ctx->Z, p.ldz, 0, (const float*)ctx->tab[AOM_T_AB][l], p.ldz, 0, ctx->newcol, p.ldn, 0,
-                       c.n_env, p.N, p.S + p.N, nullptr, 0, 0, 1, st);
+                       c.n_env, p.N, p.S + p.N, nullptr, 0, 0, 1, st, nullptr, 0, true);
   if (rc) return rc;
   extrude_scatter_kernel<<<c.n_env, 256, 0, st>>>(p);
   KCHECK();
@@ -452,7 +476,19 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
   long long blocks = (total + WFS_WARPS - 1) / WFS_WARPS;
   long long cap = (long long)ctx->num_sms * 2 * 8;      // 2 resident CTAs per SM, 8 waves of work each
   int grid = (int)(blocks < cap ? blocks : cap);
-  if (c.nfft == 64) wfs_frame_kernel<4><<<grid, WFS_WARPS * 32, wfs_smem_bytes<4>(), st>>>(p);
+  const int path = ctx->opt[AOM_OPT_WFS_PATH];
+  if (c.nfft == 64 && path != AOM_WFS_SIMT) {
+    const int full = (path == AOM_WFS_TENSOR);
+#define WFM_LAUNCH(F, NL) wfs_frame_mma_kernel<F, NL><<<grid, WFM_WARPS * 32, 0, st>>>(p)
+    switch (p.n_layers) {
+      case 0: if (full) WFM_LAUNCH(1, 0); else WFM_LAUNCH(0, 0); break;
+      case 1: if (full) WFM_LAUNCH(1, 1); else WFM_LAUNCH(0, 1); break;
+      case 3: if (full) WFM_LAUNCH(1, 3); else WFM_LAUNCH(0, 3); break;
+      default: if (full) WFM_LAUNCH(1, -1); else WFM_LAUNCH(0, -1); break;
+    }
+#undef WFM_LAUNCH
+  }
+  else if (c.nfft == 64) wfs_frame_kernel<4><<<grid, WFS_WARPS * 32, wfs_smem_bytes<4>(), st>>>(p);
   else wfs_frame_kernel<8><<<grid, WFS_WARPS * 32, wfs_smem_bytes<8>(), st>>>(p);
   KCHECK();
   ctx->frame++;
@@ -532,6 +568,29 @@ extern "C" int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream) {
   apply_control_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctx->com, ctx->com1, ctx->volts,
                                                                                          ctx->lda, total, c.delay, comp_voltage);
   KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_set_option(aom_ctx* ctx, int option, int value) {
+  if (!ctx) return AOM_ERR_INVALID;
+  if (option < 0 || option >= AOM_OPT_COUNT) return fail(ctx, AOM_ERR_INVALID, "unknown option %d", option);
+  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_SIMT))
+    return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_WFS_PATH: value %d out of range", value);
+  if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_SIMT))
+    return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_GEMM_PATH: value %d out of range", value);
+  ctx->opt[option] = value;
+  return AOM_OK;
+}
+
+extern "C" int aom_check_device(aom_ctx* ctx) {
+  if (!ctx) return AOM_ERR_INVALID;
+  int h = 0;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(&h, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h) {
+    CU(cudaMemset(ctx->d_err, 0, sizeof(int)));
+    return fail(ctx, AOM_ERR_CUDA, "device error word %d: a bounded mbarrier wait expired in gemm_tc_kernel", h);
+  }
   return AOM_OK;
 }
 

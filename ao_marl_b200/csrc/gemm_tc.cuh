@@ -1,0 +1,253 @@
+// Env-batched contractions on the 5th-generation tensor cores (tcgen05 + TMEM), float32 in / float32 out.
+//
+//        C[b][m][n] = sum_k A[b][m][k] * B[b][n][k]  (+ bias[b][n]) (relu)   |   integrator epilogue
+//
+// Same contract as gemm_tn_kernel (gemm_kernels.cuh): A = per-environment vectors [E][ld], B = shared
+// operator [rows][ld], both K-major with zero-padded leading dimensions.  Serves the screen extrusion
+// (A.z + B.noise, iterkolmo.py:255-288), the command-matrix reconstruction (rtcCompass.py:527-547), the
+// Btt projections (rlSupervisor.py:784-818, ao_env.py:482-505) and the actors (model_rpc.py:121-158).
+//
+// Precision: every float32 operand is split on the fly into two TF32 numbers, hi = the leading 11
+// significant bits, lo = x - hi (exact), and each product is three kind::tf32 MMAs
+// (hi.hi + hi.lo + lo.hi) accumulated in float32 in TMEM: ~2^-21 relative per product, so commands,
+// screens and rewards stay well inside the rel 1e-4 parity bar where a single TF32/BF16 pass does not.
+//
+// Structure (one 128 x 128 output tile per CTA, 160 threads, two CTAs per SM):
+//   warps 0-3  loaders: coalesced 128-bit global loads of the A and B slabs (16 k-values per stage),
+//              hi/lo split in registers, st.shared into the canonical K-major no-swizzle UMMA layout
+//              (8-row x 16-byte core matrices), fence.proxy.async, mbarrier arrive.   Then the epilogue:
+//              tcgen05.ld of their 32 TMEM lanes, bias / relu / integrator, 128-bit stores.
+//   warp 4     TMEM allocation; one lane waits on the full barriers and issues the six tcgen05.mma of the
+//              stage, tcgen05.commit releases the stage to the loaders and finally the accumulator.
+// Every mbarrier wait is bounded: on expiry the kernel raises an error word and runs to completion
+// instead of hanging the device.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gemm_kernels.cuh"
+
+#define GTC_BM 128
+#define GTC_BN 128
+#define GTC_BK 16
+#define GTC_STAGES 3
+#define GTC_TILE_BYTES (GTC_BM * GTC_BK * 4)                 // 8 KB: one hi or lo slab of one operand
+#define GTC_STAGE_BYTES (4 * GTC_TILE_BYTES)                 // A hi, A lo, B hi, B lo
+#define GTC_SMEM_BYTES (GTC_STAGES * GTC_STAGE_BYTES + 128)
+#define GTC_THREADS 160
+#define GTC_WAIT_SPINS (1u << 20)
+
+__device__ __forceinline__ uint32_t gtc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void gtc_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gtc_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool gtc_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: false (and *err raised) if the phase never completes
+__device__ __forceinline__ bool gtc_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+  for (uint32_t it = 0; it < GTC_WAIT_SPINS; ++it)
+    if (gtc_mbar_try(bar, parity)) return true;
+  if (err) atomicExch(err, 1);
+  return false;
+}
+
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = 128 B between the K chunks of a row group,
+// SBO = 512 B between 8-row groups (GTC_BK = 16 floats = 4 chunks per row)
+__device__ __forceinline__ uint64_t gtc_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128u >> 4) << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= 1ull << 46;                                           // descriptor version of sm_100
+  return d;
+}
+
+__device__ __forceinline__ void gtc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void gtc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void gtc_split4(const float4& v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, int* err) {
+  extern __shared__ __align__(1024) uint8_t gtc_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bz = blockIdx.z;
+  const float* __restrict__ A = p.A + (long long)bz * p.sA;
+  const float* __restrict__ B = p.B + (long long)bz * p.sB;
+  float* __restrict__ C = p.C + (long long)bz * p.sC;
+  const int m0 = blockIdx.y * GTC_BM;
+  const int n0 = blockIdx.x * GTC_BN;
+  const int nkb = (p.K + GTC_BK - 1) / GTC_BK;
+
+  uint8_t* tiles = gtc_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gtc_smem + GTC_STAGES * GTC_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GTC_STAGES + 1);
+  const uint32_t full0 = gtc_smem_u32(bars), empty0 = gtc_smem_u32(bars + GTC_STAGES);
+  const uint32_t accum_bar = gtc_smem_u32(bars + 2 * GTC_STAGES);
+
+  if (tid == 0) {
+    for (int s = 0; s < GTC_STAGES; ++s) {
+      gtc_mbar_init(full0 + 8 * s, 4);        // one arrive per loader warp
+      gtc_mbar_init(empty0 + 8 * s, 1);       // tcgen05.commit
+    }
+    gtc_mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gtc_smem_u32(tmem_slot)), "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===== loaders =====
+    const int c = tid & 3;                       // 16-byte chunk (4 k-values) of the 16-wide slab
+    const int r0 = tid >> 2;                     // rows r0, r0 + 32, r0 + 64, r0 + 96
+    float4 va[4], vb[4];
+    auto load_regs = [&](int kb) {
+      const int k = kb * GTC_BK + c * 4;
+      const bool kin = k < p.K;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ra = m0 + r0 + 32 * i, rb = n0 + r0 + 32 * i;
+        va[i] = (kin && ra < p.M) ? __ldg(reinterpret_cast<const float4*>(A + (long long)ra * p.lda + k))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = (kin && rb < p.N) ? __ldg(reinterpret_cast<const float4*>(B + (long long)rb * p.ldb + k))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (nkb > 0) load_regs(0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % GTC_STAGES;
+      const uint32_t round = (uint32_t)(kb / GTC_STAGES);
+      gtc_mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u, err);
+      uint8_t* st = tiles + (size_t)s * GTC_STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        const uint32_t off = (uint32_t)((r >> 3) * 512 + c * 128 + (r & 7) * 16);
+        float4 hi, lo;
+        gtc_split4(va[i], hi, lo);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + GTC_TILE_BYTES + off) = lo;
+        gtc_split4(vb[i], hi, lo);
+        *reinterpret_cast<float4*>(st + 2 * GTC_TILE_BYTES + off) = hi;
+        *reinterpret_cast<float4*>(st + 3 * GTC_TILE_BYTES + off) = lo;
+      }
+      if (kb + 1 < nkb) load_regs(kb + 1);       // next slab in flight while the tensor core works
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) gtc_mbar_arrive(full0 + 8 * s);
+    }
+
+    // ===== epilogue: TMEM lanes 32 warp .. 32 warp + 31 are rows m0 + 32 warp + lane =====
+    gtc_mbar_wait(accum_bar, 0u, err);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + warp * 32 + lane;
+    const float* bias = p.bias ? p.bias + (long long)bz * p.sBias : nullptr;
+#pragma unroll 1
+    for (int cb = 0; cb < GTC_BN / 32; ++cb) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < p.M) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int col = n0 + cb * 32 + j4 * 4;
+          if (col >= p.ldc) continue;
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cc = col + j;
+            float x = (nkb > 0) ? __uint_as_float(v[j4 * 4 + j]) : 0.f;
+            if (EPI == 0) {
+              if (bias && cc < p.N) x += bias[cc];
+              if (p.relu) x = fmaxf(x, 0.f);
+            } else {
+              x = -x;
+            }
+            o[j] = (cc < p.N) ? x : 0.f;         // pad columns stay zero
+          }
+          *reinterpret_cast<float4*>(C + (long long)row * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
+          if (EPI == 1 && p.closed) {
+            float4* cp = reinterpret_cast<float4*>(p.com + (long long)row * p.ldcom + col);
+            float4 c4 = *cp;
+            c4.x = fmaf(p.gain, o[0], c4.x); c4.y = fmaf(p.gain, o[1], c4.y);
+            c4.z = fmaf(p.gain, o[2], c4.z); c4.w = fmaf(p.gain, o[3], c4.w);
+            *cp = c4;
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (lane == 0) {
+    // ===== MMA issuer (one thread) =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GTC_BN >> 3) << 17) |
+                           ((uint32_t)(GTC_BM >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % GTC_STAGES;
+      const uint32_t round = (uint32_t)(kb / GTC_STAGES);
+      gtc_mbar_wait(full0 + 8 * s, round & 1u, err);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t base = gtc_smem_u32(tiles + (size_t)s * GTC_STAGE_BYTES);
+#pragma unroll
+      for (int k8 = 0; k8 < GTC_BK / 8; ++k8) {
+        const uint32_t ko = (uint32_t)k8 * 256u;                 // two 16-byte chunks = 8 tf32 values
+        const uint64_t a_hi = gtc_desc(base + ko), a_lo = gtc_desc(base + GTC_TILE_BYTES + ko);
+        const uint64_t b_hi = gtc_desc(base + 2 * GTC_TILE_BYTES + ko), b_lo = gtc_desc(base + 3 * GTC_TILE_BYTES + ko);
+        gtc_mma_tf32(tmem_base, a_hi, b_hi, idesc, (kb | k8) ? 1u : 0u);
+        gtc_mma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+        gtc_mma_tf32(tmem_base, a_lo, b_hi, idesc, 1u);
+      }
+      gtc_commit(empty0 + 8 * s);                                // stage reusable once these MMAs have read it
+    }
+    gtc_commit(accum_bar);                                       // accumulator complete
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}

@@ -48,7 +48,7 @@ B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
-           "aom_device_count_launches", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_raytrace_wfs",
+           "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_raytrace_wfs",
            "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
            "aom_set_gain", "aom_set_loop", "aom_reset_dm", "aom_set_dm_volts", "aom_rl_control",
            "aom_state_begin", "aom_state_end", "aom_reward", "aom_actor_forward", "aom_step", "aom_gemm_tn",
@@ -81,6 +81,8 @@ def load_library():
     lib.aom_set_table.argtypes = [vp, i32, i32, vp, sz]
     lib.aom_get_buffer.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(sz)]
     lib.aom_device_count_launches.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+    lib.aom_set_option.argtypes = [vp, i32, i32]
+    lib.aom_check_device.argtypes = [vp]
     lib.aom_reset.argtypes = [vp, vp, vp]
     lib.aom_move_atmos.argtypes = [vp, vp]
     lib.aom_set_layer.argtypes = [vp, i32, f32, f32, f32]
@@ -257,6 +259,22 @@ class Simulator:
         n = ctypes.c_uint64()
         self.lib.aom_device_count_launches(self._ctx, ctypes.byref(n))
         return n.value
+
+    WFS_PATHS = {"tensor": 0, "tensor_fast": 1, "simt": 2}
+
+    def set_wfs_path(self, name):
+        """Select the Shack-Hartmann frame kernel: 'tensor' (default), 'tensor_fast' or 'simt'."""
+        self._check(self.lib.aom_set_option(self._ctx, 0, self.WFS_PATHS[name]), "aom_set_option")
+
+    GEMM_PATHS = {"tcgen05": 0, "simt": 1}
+
+    def set_gemm_path(self, name):
+        """Select the GEMM kernel of the env-batched contractions: 'tcgen05' (default) or 'simt'."""
+        self._check(self.lib.aom_set_option(self._ctx, 1, self.GEMM_PATHS[name]), "aom_set_option")
+
+    def check_device(self):
+        """Synchronise and raise if a kernel reported an asynchronous error."""
+        self._check(self.lib.aom_check_device(self._ctx), "aom_check_device")
 
     def close(self):
         if self._ctx:

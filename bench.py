@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 4096 / 1024)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt"],
+                    help="Shack-Hartmann frame kernel (tensor = default product path)")
     return ap.parse_args()
 
 
@@ -219,6 +221,7 @@ def run_ours(args):
     E = args.envs or (4096 if args.workload == "40x40" else 1024)
     t_build = time.perf_counter()
     sim, t, rl = build_system(wl["par"], E, env_rl=dict(wl["env_rl"]), world_size=wl["world_size"], seed=0)
+    sim.set_wfs_path(args.wfs_path)
     seeds = 1234 + rank * E + np.arange(E, dtype=np.int64)
     sim.reset(seeds)
     # first frame of the episode (AoEnv.reset ends with one linear step)
@@ -321,16 +324,18 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "envs_per_gpu": E, "total_envs": E * world,
-                       "parallelism": "env-sharded x%d, no collective on the step path" % world,
+                       "parallelism": "env-sharded x%d, no collective on the step path" % world, "wfs_path": args.wfs_path,
                        "l2": "inputs larger than L2 (%.1f GB of screens per GPU)" % (
                            sum(int(n) ** 2 for n in t.dim_screens) * 4 * E / 1e9),
                        "us_per_frame": ms / args.steps / E * 1e3, "build_s": t_build},
-            "roofline": {"kernel": "wfs_frame_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm,
+            "roofline": {"kernel": "wfs_frame_kernel" if args.wfs_path == "simt" else "wfs_frame_mma_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                          "peak_source": "measured" if peaks else "fallback",
                          "ms_per_launch": wfs_ms, "share_of_step": wfs_ms / (ms / args.steps),
                          "fp32_tflops_algorithmic": flops_per_frame * E / (wfs_ms * 1e-3) / 1e12,
-                         "note": "issue-bound on the FP32 pipe (SIMT pruned FFT), not on HBM: see DESIGN.md"},
+                         "note": "instruction-issue / tensor-pipe bound (3 x fp16 split MMA DFT in registers), not HBM bound: "
+                                 "see DESIGN.md" if args.wfs_path != "simt" else
+                                 "issue-bound on the FP32 pipe (SIMT pruned FFT), not on HBM: see DESIGN.md"},
             "e2e": {"value": k_e2e * E * world / (ms_e2e * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": int(E * rl.action_dim * 4),
                     "d2h_bytes_per_step": int(E * (rl.action_dim + rl.state_dim + rl.n_agents) * 4), "steps": k_e2e},

@@ -136,6 +136,23 @@ typedef enum aom_buffer {
   AOM_B_COUNT
 } aom_buffer;
 
+/* Run-time switches (aom_set_option). */
+typedef enum aom_option {
+  AOM_OPT_WFS_PATH = 0, /* which Shack-Hartmann frame kernel serves the Nfft = 64 geometry */
+  AOM_OPT_GEMM_PATH,    /* which GEMM kernel serves the env-batched contractions */
+  AOM_OPT_COUNT
+} aom_option;
+enum {
+  AOM_WFS_TENSOR = 0,      /* tensor-pipe DFT, three fp16 MMAs per product in both stages (fp32-grade; default) */
+  AOM_WFS_TENSOR_FAST = 1, /* tensor-pipe DFT, twiddle low parts dropped in stage 2 (slopes ~1e-5 relative) */
+  AOM_WFS_SIMT = 2         /* float32 shared-memory FFT on the FP32 pipe (cross-check path) */
+};
+
+enum {
+  AOM_GEMM_TCGEN05 = 0,    /* tcgen05 / TMEM, three TF32 MMAs per product (fp32-grade; default) */
+  AOM_GEMM_SIMT = 1        /* float32 FFMA tiles (cross-check path) */
+};
+
 /* lifetime */
 size_t aom_config_size(void);                       /* sizeof(aom_config) the library was built with (binding check) */
 int aom_create(const aom_config* cfg, aom_ctx** out);
@@ -144,6 +161,9 @@ const char* aom_last_error(const aom_ctx* ctx);     /* ctx may be NULL for creat
 int aom_set_table(aom_ctx* ctx, int table, int index, const void* host, size_t nbytes);
 int aom_get_buffer(aom_ctx* ctx, int buffer, int index, void** dptr, size_t* count);
 int aom_device_count_launches(const aom_ctx* ctx, uint64_t* n_launches);  /* kernels launched so far */
+int aom_set_option(aom_ctx* ctx, int option, int value);
+/* Synchronise the device and report asynchronous kernel-side errors (bounded waits that expired). */
+int aom_check_device(aom_ctx* ctx);
 
 /* RlSupervisor.reset (rlSupervisor.py:236-246): reseed + regenerate turbulence (2N extrusions per layer),
  * clear mirrors / integrator / delay line / histories.  seeds: host int64 [E]. */

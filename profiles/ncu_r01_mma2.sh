@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+export AOM_GEMM_PATH=simt
+CMD="python bench.py --steps 2 --warmup 3 --envs 1024 --no-cpu-baseline"
+$CMD > gpurun_out/plain_mma2.log 2>&1 && \
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:wfs_frame_mma -c 1 -o gpurun_out/prof_wfs_mma2_r01 $CMD > gpurun_out/ncu_mma2.log 2>&1
+tail -c 300 gpurun_out/plain_mma2.log

@@ -31,19 +31,50 @@ def sim10(static10, torch):
     sim.close()
 
 
+GEMM_TOL = {"simt": 1e-5, "tcgen05": 5e-5}     # the tensor core truncates its float32 accumulator
+
+
 def test_gemm_tn(sim10, torch):
     from ao_marl_b200.lib import LD
     g = torch.Generator(device="cuda").manual_seed(0)
-    for (M, N, K) in ((1, 5, 7), (4, 648, 1957), (300, 90, 128), (257, 129, 100)):
-        A = torch.zeros((M, LD(K)), device="cuda")
-        Bm = torch.zeros((N, LD(K)), device="cuda")
-        A[:, :K] = torch.randn((M, K), device="cuda", generator=g)
-        Bm[:, :K] = torch.randn((N, K), device="cuda", generator=g)
-        bias = torch.randn(N, device="cuda", generator=g)
-        C = sim10.gemm_tn(A, Bm, bias=bias, relu=True)
-        ref = torch.relu(A.double() @ Bm.double().T + bias.double())
-        assert relerr(C[:, :N].cpu().numpy(), ref.cpu().numpy()) < 1e-5
-        assert float(C[:, N:].abs().max()) == 0.0 if C.shape[1] > N else True
+    try:
+        for path in ("simt", "tcgen05"):
+            sim10.set_gemm_path(path)
+            for (M, N, K) in ((1, 5, 7), (4, 648, 1957), (300, 90, 128), (257, 129, 100)):
+                A = torch.zeros((M, LD(K)), device="cuda")
+                Bm = torch.zeros((N, LD(K)), device="cuda")
+                A[:, :K] = torch.randn((M, K), device="cuda", generator=g)
+                Bm[:, :K] = torch.randn((N, K), device="cuda", generator=g)
+                bias = torch.randn(N, device="cuda", generator=g)
+                C = sim10.gemm_tn(A, Bm, bias=bias, relu=True)
+                sim10.check_device()
+                ref = torch.relu(A.double() @ Bm.double().T + bias.double())
+                assert relerr(C[:, :N].cpu().numpy(), ref.cpu().numpy()) < GEMM_TOL[path], (path, M, N, K)
+                assert float(C[:, N:].abs().max()) == 0.0 if C.shape[1] > N else True
+    finally:
+        sim10.set_gemm_path("tcgen05")
+
+
+def test_gemm_paths(sim10, torch):
+    """tcgen05 (3 x TF32 split) GEMM against float64 and against the FFMA kernel, shapes of the 40x40 step."""
+    from ao_marl_b200.lib import LD
+    g = torch.Generator(device="cuda").manual_seed(1)
+    try:
+        for (M, N, K) in ((256, 648, 1957), (130, 1286, 2400), (512, 1283, 1286), (3, 60, 256), (128, 128, 16)):
+            A = torch.zeros((M, LD(K)), device="cuda")
+            Bm = torch.zeros((N, LD(K)), device="cuda")
+            A[:, :K] = torch.randn((M, K), device="cuda", generator=g) * 3
+            Bm[:, :K] = torch.randn((N, K), device="cuda", generator=g)
+            ref = (A.double() @ Bm.double().T).cpu().numpy()
+            out = {}
+            for path in ("tcgen05", "simt"):
+                sim10.set_gemm_path(path)
+                out[path] = sim10.gemm_tn(A, Bm)[:, :N].cpu().numpy()
+                sim10.check_device()
+            assert relerr(out["simt"], ref) < GEMM_TOL["simt"]
+            assert relerr(out["tcgen05"], ref) < GEMM_TOL["tcgen05"], (M, N, K)
+    finally:
+        sim10.set_gemm_path("tcgen05")
 
 
 def test_pixel_noise_bit_exact(sim10, torch):
@@ -126,6 +157,28 @@ def test_phase_and_frame(sim10, oracle_tab10, oracle_imat10, static10, torch):
         sref, cref = o.comp_wfs_image(noise=-1.0, keep=True)
         assert relerr(cube[e], cref) < 1e-4
         assert relerr(s[e], sref) < RTOL
+
+
+def test_wfs_paths_agree(sim10, static10, torch):
+    """Tensor-pipe DFT (fp16 split, 3 MMAs per product) against the float32 shared-memory FFT on the same frame."""
+    seeds = np.array([21, 22, 23, 24], dtype=np.int64)
+    sim10.reset(seeds)
+    r = np.random.default_rng(9)
+    volts = (r.standard_normal((4, static10.nactu)) * 10).astype(np.float32)
+    sim10.set_dm_volts(torch.as_tensor(volts, device="cuda"))
+    out = {}
+    try:
+        for path in ("simt", "tensor", "tensor_fast"):
+            sim10.set_wfs_path(path)
+            sim10.comp_wfs_image(keep_image=True, noise=-1.0)
+            sim10.do_centroids()
+            out[path] = (sim10.rows("SLOPES", static10.nslopes).cpu().numpy().copy(),
+                         sim10.buffer("BINCUBE").cpu().numpy().copy())
+    finally:
+        sim10.set_wfs_path("tensor")
+    assert relerr(out["tensor"][1], out["simt"][1]) < 2e-5
+    assert relerr(out["tensor"][0], out["simt"][0]) < 2e-5
+    assert relerr(out["tensor_fast"][0], out["simt"][0]) < 5e-4
 
 
 def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
