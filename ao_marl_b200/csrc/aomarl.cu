@@ -13,6 +13,7 @@
 #include "rtc_kernels.cuh"
 #include "wfs_kernels.cuh"
 #include "wfs_mma.cuh"
+#include "wfs_tma.cuh"
 
 static char g_create_error[512] = "";
 
@@ -51,6 +52,15 @@ struct aom_ctx {
   float *aX, *aH1, *aH2, *aHO;
   int ld_ain, ld_ah, ld_aho;
   bool seeded;
+  // TMA-staged Shack-Hartmann kernel (wfs_tma.cuh): host copies of the tables it derives from, derived tables
+  void* htab[AOM_T_COUNT];
+  size_t htab_bytes[AOM_T_COUNT];
+  int fast_state;            // 0 = not prepared, 1 = eligible, -1 = not eligible (fast_why says why)
+  char fast_why[160];
+  WfsFast fast;
+  void* fast_dev[6];
+  CUtensorMap fast_maps[WFT_MAX_LAYERS];
+  size_t fast_smem;
 };
 
 static int fail(aom_ctx* c, int code, const char* fmt, ...) {
@@ -116,6 +126,7 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     const char* w = getenv("AOM_WFS_PATH");
     if (w && !strcmp(w, "simt")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_SIMT;
     if (w && !strcmp(w, "tensor_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_FAST;
+    if (w && !strcmp(w, "tensor_reg")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_REG;
   }
   *out = ctx;   // returned even on failure so that aom_last_error / aom_destroy work
   CU(cudaGetDevice(&ctx->device));
@@ -195,6 +206,8 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
                   ctx->modes_before, ctx->modes_res, ctx->state, ctx->hist, ctx->reward, ctx->action,
                   ctx->action_mean, ctx->strehl, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO, ctx->d_err};
   for (void* b : bufs) cudaFree(b);
+  for (void* b : ctx->fast_dev) cudaFree(b);
+  for (int t = 0; t < AOM_T_COUNT; ++t) free(ctx->htab[t]);
   free(ctx);
 }
 
@@ -240,6 +253,15 @@ extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* hos
   CU(cudaMalloc(&ctx->tab[table][index], nbytes ? nbytes : 4));
   CU(cudaMemcpy(ctx->tab[table][index], host, nbytes, cudaMemcpyHostToDevice));
   ctx->tab_bytes[table][index] = nbytes;
+  if (table == AOM_T_MPUPIL || table == AOM_T_SUB_X0 || table == AOM_T_SUB_Y0 || table == AOM_T_STAMP1D ||
+      table == AOM_T_ACT_MAP) {
+    free(ctx->htab[table]);
+    ctx->htab[table] = malloc(nbytes ? nbytes : 4);
+    if (!ctx->htab[table]) return fail(ctx, AOM_ERR_INVALID, "out of host memory");
+    memcpy(ctx->htab[table], host, nbytes);
+    ctx->htab_bytes[table] = nbytes;
+    ctx->fast_state = 0;     // derived tables of the TMA-staged sensor kernel are rebuilt on the next frame
+  }
   return AOM_OK;
 }
 
@@ -423,6 +445,245 @@ extern "C" int aom_reset(aom_ctx* ctx, const int64_t* seeds, void* stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Host side of wfs_frame_tma_kernel (wfs_tma.cuh): eligibility, derived tables, TMA descriptors.
+static uint32_t half2_bits(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  uint32_t u;
+  memcpy(&u, &h, 4);
+  return u;
+}
+
+static void split_pair(double a, double b, int lo_part, uint32_t& out) {
+  const float ah = __half2float(__float2half_rn((float)a)), bh = __half2float(__float2half_rn((float)b));
+  out = lo_part ? half2_bits((float)(a - (double)ah), (float)(b - (double)bh)) : half2_bits(ah, bh);
+}
+
+// W[n][i] = exp(-2 pi i n F(i) / 64), F = the 32 kept frequencies (0..15, 48..63); part 0 = real, 1 = imaginary
+static double wft_w(int n, int i, int part) {
+  const int F = (i < 16) ? i : i + 32;
+  const int ang = (n * F) & 63;
+  const double th = -2.0 * M_PI * (double)ang / 64.0;
+  return part ? sin(th) : cos(th);
+}
+
+typedef CUresult (*aom_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+#define FAST_NO(...)                                             \
+  do {                                                           \
+    snprintf(ctx->fast_why, sizeof(ctx->fast_why), __VA_ARGS__); \
+    ctx->fast_state = -1;                                        \
+    return AOM_OK;                                               \
+  } while (0)
+
+static int wfs_fast_prepare(aom_ctx* ctx) {
+  const aom_config& c = ctx->cfg;
+  if (ctx->fast_state != 0) return AOM_OK;
+  for (void*& b : ctx->fast_dev) { cudaFree(b); b = nullptr; }
+  if (c.nfft != 64 || c.nrebin != 2) FAST_NO("Nfft != 64");
+  if (c.n_layers > WFT_MAX_LAYERS) FAST_NO("more than %d layers", WFT_MAX_LAYERS);
+  if (c.pzt_pitch != 16) FAST_NO("actuator pitch is not 16 pixels");
+  if (c.nvalid > 65535 / 256 * 256 || c.n > 65535) FAST_NO("geometry too large for the packed tables");
+  if ((c.tt_dim & 3) || c.tt_dim <= 0) FAST_NO("tip-tilt support not a multiple of 4");
+  const float* pup = (const float*)ctx->htab[AOM_T_MPUPIL];
+  const int* sx = (const int*)ctx->htab[AOM_T_SUB_X0];
+  const int* sy = (const int*)ctx->htab[AOM_T_SUB_Y0];
+  const float* stamp = (const float*)ctx->htab[AOM_T_STAMP1D];
+  const int* amap = (const int*)ctx->htab[AOM_T_ACT_MAP];
+  if (!pup || !sx || !sy) FAST_NO("sensor tables not uploaded");
+  const bool dm = stamp && amap;
+  for (int l = 0; l < c.n_layers; ++l)
+    if (c.screen_dim[l] & 3) FAST_NO("screen side not a multiple of 4");
+  for (size_t i = 0; i < (size_t)c.n * c.n; ++i)
+    if (pup[i] != 0.f && pup[i] != 1.f) FAST_NO("pupil transmission is not binary");
+  const int ss = c.stamp_size, nv = c.nvalid;
+  int cx = 0, cy = 0;
+  for (int k = 0; k < nv; ++k) {
+    if (sx[k] < 0 || sy[k] < 0 || sx[k] + 16 > c.n || sy[k] + 16 > c.n) FAST_NO("subaperture outside the pupil frame");
+    if ((sx[k] + c.tt_off) & 3) FAST_NO("tip-tilt rows not 16-byte aligned");
+    const int mx = (((sx[k] + c.pzt_off - c.pzt_i1_0) % 16) + 16) % 16, my = (((sy[k] + c.pzt_off - c.pzt_j1_0) % 16) + 16) % 16;
+    if (k == 0) { cx = mx; cy = my; }
+    if (mx != cx || my != cy) FAST_NO("subapertures not aligned with the actuator lattice");
+  }
+  // lattice cells j = 0 .. NG-1 from gx_lo = m - joff, m = (X0 - cx) / 16; stamp index a = c0 + x - 16 j
+  auto axis = [&](int cm, int& joff, int& c0, int& ng) {
+    const int num = cm - (ss - 1);                       // ceil(num / 16) = -joff
+    joff = -((num >= 0) ? (num + 15) / 16 : -((-num) / 16));
+    c0 = cm + 16 * joff;
+    ng = (c0 + 15) / 16 + 1;
+  };
+  int joffx = 0, joffy = 0, c0x = 0, c0y = 0, ngx = 0, ngy = 0;
+  if (dm) {
+    axis(cx, joffx, c0x, ngx);
+    axis(cy, joffy, c0y, ngy);
+    if (ngx > WFT_NG || ngy > WFT_NG) FAST_NO("stamp spans more than %d lattice cells", WFT_NG);
+  }
+  const int GW = c.pzt_grid_n + 2 * WFT_PAD;
+  if ((size_t)GW * GW * 2 > 16384) FAST_NO("actuator lattice too large");
+
+  // ---- derived tables ----
+  uint2* h_sub = (uint2*)malloc((size_t)nv * sizeof(uint2));
+  unsigned char* h_pm = (unsigned char*)malloc((size_t)nv * 32);
+  short* h_amap = (short*)malloc((size_t)GW * GW * sizeof(short));
+  float h_fxy[2 * WFT_NG * 16];
+  uint4* h_c1 = (uint4*)malloc(8 * 32 * sizeof(uint4));
+  uint4* h_c2 = (uint4*)malloc(12 * 32 * sizeof(uint4));
+  bool ok = h_sub && h_pm && h_amap && h_c1 && h_c2;
+  if (ok) {
+    for (int i = 0; i < GW * GW; ++i) h_amap[i] = -1;
+    if (dm)
+      for (int gy = 0; gy < c.pzt_grid_n; ++gy)
+        for (int gx = 0; gx < c.pzt_grid_n; ++gx) {
+          const int a = amap[gy * c.pzt_grid_n + gx];
+          if (a > 32767) ok = false;
+          h_amap[(gy + WFT_PAD) * GW + gx + WFT_PAD] = (short)a;
+        }
+    for (int k = 0; k < nv && ok; ++k) {
+      int gb = 0;
+      if (dm) {
+        const int gxl = (sx[k] + c.pzt_off - c.pzt_i1_0 - cx) / 16 - joffx + WFT_PAD;   // exact multiples of 16
+        const int gyl = (sy[k] + c.pzt_off - c.pzt_j1_0 - cy) / 16 - joffy + WFT_PAD;
+        if (gxl < 0 || gyl < 0 || gxl + WFT_NG > GW || gyl + WFT_NG > GW) { ok = false; break; }
+        gb = gyl * GW + gxl;
+      }
+      h_sub[k] = make_uint2(((uint32_t)sy[k] << 16) | (uint32_t)sx[k], (uint32_t)gb);
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, q = lane & 3;
+        unsigned m = 0;
+        for (int r = 0; r < 2; ++r)
+          for (int cc = 0; cc < 4; ++cc)
+            if (pup[(size_t)(sy[k] + 2 * g + r) * c.n + sx[k] + 4 * q + cc] != 0.f) m |= 1u << (r * 4 + cc);
+        h_pm[(size_t)k * 32 + lane] = (unsigned char)m;
+      }
+    }
+    for (int ax = 0; ax < 2; ++ax)
+      for (int j = 0; j < WFT_NG; ++j)
+        for (int x = 0; x < 16; ++x) {
+          const int a = (ax ? c0y : c0x) + x - 16 * j;
+          h_fxy[(ax * WFT_NG + j) * 16 + x] = (dm && a >= 0 && a < ss) ? stamp[a] : 0.f;
+        }
+    // stage-1 A fragments: row r of m-tile mt <-> kept frequency 16 mt + 2 (r & 7) + (r >> 3); k <-> x = sigma(k)
+    auto sigma = [](int kk) { return kk < 8 ? 4 * (kk >> 1) + (kk & 1) : 4 * ((kk - 8) >> 1) + 2 + (kk & 1); };
+    auto yk = [](int kk) { return kk < 8 ? 2 * kk : 2 * (kk - 8) + 1; };
+    for (int mt = 0; mt < 2; ++mt)
+      for (int part = 0; part < 2; ++part)
+        for (int hl = 0; hl < 2; ++hl)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, q = lane & 3;
+            const int rows[2] = {g, g + 8};
+            const int ks[4] = {2 * q, 2 * q + 1, 2 * q + 8, 2 * q + 9};
+            uint32_t w[4];
+            for (int reg = 0; reg < 4; ++reg) {      // a0 (g; 2q..) a1 (g+8; 2q..) a2 (g; 2q+8..) a3 (g+8; 2q+8..)
+              const int r = rows[reg & 1], fi = 16 * mt + 2 * (r & 7) + (r >> 3);
+              const int k0 = ks[(reg >> 1) * 2], k1 = ks[(reg >> 1) * 2 + 1];
+              split_pair(wft_w(sigma(k0), fi, part), wft_w(sigma(k1), fi, part), hl, w[reg]);
+            }
+            h_c1[((mt * 2 + part) * 2 + hl) * 32 + lane] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+    // stage-2 B fragments: k <-> y = yk(k), n = g <-> kept frequency 8 b + g
+    for (int b = 0; b < 4; ++b)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, q = lane & 3;
+        const int ks[4] = {2 * q, 2 * q + 1, 2 * q + 8, 2 * q + 9};
+        uint32_t hi[4], lo[4], nh[2], nl[2];
+        for (int reg = 0; reg < 4; ++reg) {        // {Wr b0, Wr b1, Wi b0, Wi b1}
+          const int part = reg >> 1, k0 = ks[(reg & 1) * 2], k1 = ks[(reg & 1) * 2 + 1];
+          split_pair(wft_w(yk(k0), 8 * b + g, part), wft_w(yk(k1), 8 * b + g, part), 0, hi[reg]);
+          split_pair(wft_w(yk(k0), 8 * b + g, part), wft_w(yk(k1), 8 * b + g, part), 1, lo[reg]);
+        }
+        for (int h = 0; h < 2; ++h) { nh[h] = hi[2 + h] ^ 0x80008000u; nl[h] = lo[2 + h] ^ 0x80008000u; }
+        h_c2[(b * 3 + 0) * 32 + lane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        h_c2[(b * 3 + 1) * 32 + lane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        h_c2[(b * 3 + 2) * 32 + lane] = make_uint4(nh[0], nh[1], nl[0], nl[1]);
+      }
+  }
+  cudaError_t ce = cudaSuccess;
+  const void* srcs[6] = {h_sub, h_amap, h_pm, h_c1, h_c2, h_fxy};
+  const size_t sizes[6] = {(size_t)nv * sizeof(uint2), (size_t)GW * GW * sizeof(short), (size_t)nv * 32,
+                           8 * 32 * sizeof(uint4), 12 * 32 * sizeof(uint4), sizeof(h_fxy)};
+  for (int i = 0; i < 6 && ok && ce == cudaSuccess; ++i) {
+    ce = cudaMalloc(&ctx->fast_dev[i], sizes[i]);
+    if (ce == cudaSuccess) ce = cudaMemcpy(ctx->fast_dev[i], srcs[i], sizes[i], cudaMemcpyHostToDevice);
+  }
+  free(h_sub); free(h_pm); free(h_amap); free(h_c1); free(h_c2);
+  if (ce != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "wfs_fast_prepare: %s", cudaGetErrorString(ce));
+  if (!ok) FAST_NO("derived tables out of range");
+
+  // ---- TMA descriptors: one 3-D map [E][N][N] per layer, box 24 x 17 x 1, zero fill outside ----
+  if (c.n_layers > 0) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess)
+      FAST_NO("cuTensorMapEncodeTiled not available");
+    for (int l = 0; l < c.n_layers; ++l) {
+      const cuuint64_t N = (cuuint64_t)c.screen_dim[l];
+      const cuuint64_t dims[3] = {N, N, (cuuint64_t)c.n_env};
+      const cuuint64_t strides[2] = {N * 4, N * N * 4};
+      const cuuint32_t box[3] = {WFT_TILE_W, WFT_TILE_H, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = ((aom_encode_tiled_fn)fn)(&ctx->fast_maps[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ctx->screen[l], dims,
+                                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) FAST_NO("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+  }
+  WfsFast& f = ctx->fast;
+  f.sub = (const uint2*)ctx->fast_dev[0];
+  f.amap = (const short*)ctx->fast_dev[1];
+  f.pmask = (const unsigned char*)ctx->fast_dev[2];
+  f.c1 = (const uint4*)ctx->fast_dev[3];
+  f.c2 = (const uint4*)ctx->fast_dev[4];
+  f.fxy = (const float*)ctx->fast_dev[5];
+  f.GW = GW;
+  f.sub_in_smem = (nv <= 1280) ? 1 : 0;
+  f.err = ctx->d_err;
+  ctx->fast_state = 1;
+  ctx->fast_why[0] = 0;
+  return AOM_OK;
+}
+
+template <int FULL, int NL>
+static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, int grid, long long ipc, cudaStream_t st) {
+  WfsTmaParams P;
+  memset(&P, 0, sizeof(P));
+  P.p = p;
+  P.f = ctx->fast;
+  P.f.items_per_cta = ipc;
+  for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
+  const size_t smem = wft_smem_bytes<NL>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(wfs_frame_tma_kernel<FULL, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_tma_kernel): %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  wfs_frame_tma_kernel<FULL, NL><<<grid, WFT_WARPS * 32, smem, st>>>(P);
+  return AOM_OK;
+}
+
+static int wfs_fast_launch(aom_ctx* ctx, const WfsParams& p, int full, cudaStream_t st) {
+  const long long total = (long long)p.E * p.nvalid;
+  // contiguous ranges of work items per CTA: about 8 waves of 2 CTAs per SM, at least 16 items per warp
+  long long grid = (long long)ctx->num_sms * 2 * 8;
+  long long ipc = (total + grid - 1) / grid;
+  if (ipc < 16 * WFT_WARPS) ipc = 16 * WFT_WARPS;
+  ipc = (ipc + WFT_WARPS - 1) / WFT_WARPS * WFT_WARPS;
+  grid = (total + ipc - 1) / ipc;
+#define WFT_GO(NL) return full ? wfs_fast_launch_t<1, NL>(ctx, p, (int)grid, ipc, st) : wfs_fast_launch_t<0, NL>(ctx, p, (int)grid, ipc, st)
+  switch (p.n_layers) {
+    case 0: WFT_GO(0);
+    case 1: WFT_GO(1);
+    case 2: WFT_GO(2);
+    case 3: WFT_GO(3);
+    case 4: WFT_GO(4);
+  }
+#undef WFT_GO
+  return fail(ctx, AOM_ERR_UNSUPPORTED, "wfs_fast_launch: %d layers", p.n_layers);
+}
+
+// ---------------------------------------------------------------------------------------------
 static int fill_wfs_params(aom_ctx* ctx, WfsParams& p, int flags, float noise) {
   const aom_config& c = ctx->cfg;
   memset(&p, 0, sizeof(p));
@@ -477,8 +738,16 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
   long long cap = (long long)ctx->num_sms * 2 * 8;      // 2 resident CTAs per SM, 8 waves of work each
   int grid = (int)(blocks < cap ? blocks : cap);
   const int path = ctx->opt[AOM_OPT_WFS_PATH];
-  if (c.nfft == 64 && path != AOM_WFS_SIMT) {
-    const int full = (path == AOM_WFS_TENSOR);
+  if (c.nfft == 64 && (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST)) {
+    rc = wfs_fast_prepare(ctx);
+    if (rc) return rc;
+  }
+  if (c.nfft == 64 && (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST) && ctx->fast_state == 1) {
+    rc = wfs_fast_launch(ctx, p, path == AOM_WFS_TENSOR, st);
+    if (rc) return rc;
+  }
+  else if (c.nfft == 64 && path != AOM_WFS_SIMT) {
+    const int full = (path != AOM_WFS_TENSOR_FAST);
 #define WFM_LAUNCH(F, NL) wfs_frame_mma_kernel<F, NL><<<grid, WFM_WARPS * 32, 0, st>>>(p)
     switch (p.n_layers) {
       case 0: if (full) WFM_LAUNCH(1, 0); else WFM_LAUNCH(0, 0); break;
@@ -494,6 +763,17 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
   ctx->frame++;
   ctx->cube_override = nullptr;
   return AOM_OK;
+}
+
+extern "C" const char* aom_wfs_kernel(aom_ctx* ctx) {
+  if (!ctx) return "";
+  const int path = ctx->opt[AOM_OPT_WFS_PATH];
+  if (ctx->cfg.nfft != 64 || path == AOM_WFS_SIMT) return "wfs_frame_kernel";
+  if (path == AOM_WFS_TENSOR_REG) return "wfs_frame_mma_kernel";
+  if (wfs_fast_prepare(ctx) != AOM_OK) return "";
+  if (ctx->fast_state == 1) return "wfs_frame_tma_kernel";
+  snprintf(ctx->err, sizeof(ctx->err), "staged sensor kernel not eligible: %s", ctx->fast_why);
+  return "wfs_frame_mma_kernel";
 }
 
 extern "C" int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream) {
@@ -574,7 +854,7 @@ extern "C" int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream) {
 extern "C" int aom_set_option(aom_ctx* ctx, int option, int value) {
   if (!ctx) return AOM_ERR_INVALID;
   if (option < 0 || option >= AOM_OPT_COUNT) return fail(ctx, AOM_ERR_INVALID, "unknown option %d", option);
-  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_SIMT))
+  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_TENSOR_REG))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_WFS_PATH: value %d out of range", value);
   if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_SIMT))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_GEMM_PATH: value %d out of range", value);

@@ -48,7 +48,7 @@ B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
-           "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_raytrace_wfs",
+           "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_raytrace_wfs",
            "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
            "aom_set_gain", "aom_set_loop", "aom_reset_dm", "aom_set_dm_volts", "aom_rl_control",
            "aom_state_begin", "aom_state_end", "aom_reward", "aom_actor_forward", "aom_step", "aom_gemm_tn",
@@ -88,6 +88,8 @@ def load_library():
     lib.aom_set_layer.argtypes = [vp, i32, f32, f32, f32]
     lib.aom_comp_wfs_image.argtypes = [vp, i32, f32, vp]
     lib.aom_raytrace_wfs.argtypes = [vp, i32, vp]
+    lib.aom_wfs_kernel.argtypes = [vp]
+    lib.aom_wfs_kernel.restype = ctypes.c_char_p
     lib.aom_set_bincube.argtypes = [vp, vp, vp]
     lib.aom_do_centroids.argtypes = [vp, vp]
     lib.aom_do_control.argtypes = [vp, vp]
@@ -260,11 +262,15 @@ class Simulator:
         self.lib.aom_device_count_launches(self._ctx, ctypes.byref(n))
         return n.value
 
-    WFS_PATHS = {"tensor": 0, "tensor_fast": 1, "simt": 2}
+    WFS_PATHS = {"tensor": 0, "tensor_fast": 1, "simt": 2, "tensor_reg": 3}
 
     def set_wfs_path(self, name):
-        """Select the Shack-Hartmann frame kernel: 'tensor' (default), 'tensor_fast' or 'simt'."""
+        """Select the Shack-Hartmann frame kernel: 'tensor' (default), 'tensor_fast', 'tensor_reg' or 'simt'."""
         self._check(self.lib.aom_set_option(self._ctx, 0, self.WFS_PATHS[name]), "aom_set_option")
+
+    def wfs_kernel(self):
+        """Name of the kernel the next frame launches (and, via last_error, why the staged one is not used)."""
+        return self.lib.aom_wfs_kernel(self._ctx).decode()
 
     GEMM_PATHS = {"tcgen05": 0, "simt": 1}
 

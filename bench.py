@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 4096 / 1024)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt"],
+    ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt", "tensor_reg"],
                     help="Shack-Hartmann frame kernel (tensor = default product path)")
     return ap.parse_args()
 
@@ -222,6 +222,7 @@ def run_ours(args):
     t_build = time.perf_counter()
     sim, t, rl = build_system(wl["par"], E, env_rl=dict(wl["env_rl"]), world_size=wl["world_size"], seed=0)
     sim.set_wfs_path(args.wfs_path)
+    wfs_kernel_name = sim.wfs_kernel()
     seeds = 1234 + rank * E + np.arange(E, dtype=np.int64)
     sim.reset(seeds)
     # first frame of the episode (AoEnv.reset ends with one linear step)
@@ -328,7 +329,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (%.1f GB of screens per GPU)" % (
                            sum(int(n) ** 2 for n in t.dim_screens) * 4 * E / 1e9),
                        "us_per_frame": ms / args.steps / E * 1e3, "build_s": t_build},
-            "roofline": {"kernel": "wfs_frame_kernel" if args.wfs_path == "simt" else "wfs_frame_mma_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm,
+            "roofline": {"kernel": wfs_kernel_name, "bound": "hbm", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                          "peak_source": "measured" if peaks else "fallback",
                          "ms_per_launch": wfs_ms, "share_of_step": wfs_ms / (ms / args.steps),

@@ -143,9 +143,11 @@ typedef enum aom_option {
   AOM_OPT_COUNT
 } aom_option;
 enum {
-  AOM_WFS_TENSOR = 0,      /* tensor-pipe DFT, three fp16 MMAs per product in both stages (fp32-grade; default) */
-  AOM_WFS_TENSOR_FAST = 1, /* tensor-pipe DFT, twiddle low parts dropped in stage 2 (slopes ~1e-5 relative) */
-  AOM_WFS_SIMT = 2         /* float32 shared-memory FFT on the FP32 pipe (cross-check path) */
+  AOM_WFS_TENSOR = 0,      /* TMA-staged tiles + tensor-pipe DFT, three fp16 MMAs per product in both stages (fp32-grade;
+                              default; geometries the staged kernel does not cover fall back to AOM_WFS_TENSOR_REG) */
+  AOM_WFS_TENSOR_FAST = 1, /* same, twiddle low parts dropped in stage 2 (slopes ~1e-5 relative) */
+  AOM_WFS_SIMT = 2,        /* float32 shared-memory FFT on the FP32 pipe (cross-check path) */
+  AOM_WFS_TENSOR_REG = 3   /* tensor-pipe DFT fed by plain global loads (previous generation; cross-check path) */
 };
 
 enum {
@@ -181,6 +183,11 @@ int aom_set_layer(aom_ctx* ctx, int layer, float deltax, float deltay, float amp
  * this frame (pass cfg.noise for the configured value).  Also leaves the centre-of-gravity slopes of the
  * frame for aom_do_centroids. */
 int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* stream);
+
+/* Name of the kernel the next aom_comp_wfs_image will launch under the current AOM_OPT_WFS_PATH
+ * ("wfs_frame_tma_kernel", "wfs_frame_mma_kernel" or "wfs_frame_kernel"); when the staged kernel is not
+ * eligible for the geometry, aom_last_error() says why. */
+const char* aom_wfs_kernel(aom_ctx* ctx);
 
 /* Materialise the pupil-plane phase seen by the sensor (wfs.get_wfs_phase) into AOM_B_PHASE. */
 int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream);

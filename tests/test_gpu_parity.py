@@ -168,8 +168,10 @@ def test_wfs_paths_agree(sim10, static10, torch):
     sim10.set_dm_volts(torch.as_tensor(volts, device="cuda"))
     out = {}
     try:
-        for path in ("simt", "tensor", "tensor_fast"):
+        for path in ("simt", "tensor", "tensor_fast", "tensor_reg"):
             sim10.set_wfs_path(path)
+            if path in ("tensor", "tensor_fast"):
+                assert sim10.wfs_kernel() == "wfs_frame_tma_kernel", sim10.lib.aom_last_error(sim10._ctx)
             sim10.comp_wfs_image(keep_image=True, noise=-1.0)
             sim10.do_centroids()
             out[path] = (sim10.rows("SLOPES", static10.nslopes).cpu().numpy().copy(),
@@ -179,6 +181,33 @@ def test_wfs_paths_agree(sim10, static10, torch):
     assert relerr(out["tensor"][1], out["simt"][1]) < 2e-5
     assert relerr(out["tensor"][0], out["simt"][0]) < 2e-5
     assert relerr(out["tensor_fast"][0], out["simt"][0]) < 5e-4
+    assert relerr(out["tensor_reg"][1], out["simt"][1]) < 2e-5
+    assert relerr(out["tensor_reg"][0], out["simt"][0]) < 2e-5
+
+
+def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
+    """The TMA-staged kernel against the float32 FFT kernel while the torus seam sweeps through the pupil
+    (tiles that straddle it take the plain-load fill), with and without the image / normalisation path."""
+    seeds = np.array([31, 32, 33, 34], dtype=np.int64)
+    sim10.reset(seeds)
+    r = np.random.default_rng(10)
+    volts = (r.standard_normal((4, static10.nactu)) * 10).astype(np.float32)
+    sim10.set_dm_volts(torch.as_tensor(volts, device="cuda"))
+    n = static10.nslopes
+    try:
+        for it in range(24):
+            for _ in range(3):
+                sim10.move_atmos()
+            res = {}
+            for path in ("simt", "tensor"):
+                sim10.set_wfs_path(path)
+                sim10.comp_wfs_image(keep_image=(it % 2 == 0), noise=-1.0)
+                sim10.do_centroids()
+                res[path] = sim10.rows("SLOPES", n).cpu().numpy().copy()
+            sim10.check_device()
+            assert relerr(res["tensor"], res["simt"]) < 2e-5, it
+    finally:
+        sim10.set_wfs_path("tensor")
 
 
 def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
