@@ -51,6 +51,7 @@ struct WfsFast {
   int GW;                    // side of the padded actuator map
   int sub_in_smem;           // stage the subaperture table in shared memory
   int* err;                  // device error word (bounded waits)
+  int dbg;                   // development switches (AOM_WFS_DBG): 1 = skip the MMAs, 2 = skip the field arithmetic
   long long items_per_cta;
 };
 
@@ -221,6 +222,12 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
   prefetch(e, k, 0);
   s_v[lane] = n_v;
   __syncwarp();
+  // De-phase the warps that share a scheduler: identical work per iteration would otherwise keep them in
+  // lock step, all in the field arithmetic or all queueing on the tensor pipe at the same time.
+  {
+    const unsigned stagger_ns = (unsigned)(f.dbg >> 4);
+    if (stagger_ns && (warp & 4)) __nanosleep(stagger_ns);
+  }
 
   for (int it = 0; w < end; ++it, w += WFT_WARPS) {
     const int s = it & 1;
@@ -255,6 +262,7 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
       for (int c = 0; c < 4; ++c) ph[r][c] = 0.f;
 
     // ---- atmosphere: bilinear sample of the staged tiles ----
+    const bool dbg_nofield = f.dbg & 2, dbg_nomma = f.dbg & 1;
     if (NL > 0) {
       if (!c_seam) {
         wft_mbar_wait(my_bar_u32 + s * 8, (phase_bits >> s) & 1u, f.err);
@@ -279,6 +287,7 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
       }
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
+        if (dbg_nofield) break;
         const float* t = reinterpret_cast<const float*>(my_tiles + (s * NL + l) * WFT_TILE_STRIDE) + lane_off;
         const float fx = p.layer[l].fx, fy = p.layer[l].fy;
         switch ((c_d >> (2 * l)) & 3u) {
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
     }
 
     // ---- mirrors: separable stamps of the 4 x 4 lattice neighbourhood + two tip-tilt planes ----
-    if (p.use_dm) {
+    if (p.use_dm && !dbg_nofield) {
       const float* V = s_v + s * 32;
       float u[2][WFT_NG];
 #pragma unroll
@@ -333,6 +342,12 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
 
     // ---- complex field -> fp16 hi / lo B fragments of stage 1 (row 2g + j feeds n-tile j) ----
     uint32_t xr_h[2][2], xr_l[2][2], xi_h[2][2], xi_l[2][2];
+    if (dbg_nofield) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) { xr_h[r][c] = 0x3c003c00u ^ c_pm; xr_l[r][c] = c_xy; xi_h[r][c] = c_pm; xi_l[r][c] = c_xy >> 3; }
+    } else
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const float4 hf = *reinterpret_cast<const float4*>(s_half + (2 * g + r) * 16 + 4 * q);
@@ -353,33 +368,47 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
     }
 
     // ---- stage 1: T[part][mt][j] (16 x 8 tiles: rows = kept fx (pair-interleaved), cols = y) ----
+    // Issue order = source order (asm volatile): the eight accumulator tiles advance in lock step, so eight
+    // independent MMAs are in flight and the ~30-cycle MMA latency of a dependent chain is covered.
     float T[2][2][2][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const uint4 wr_h = s_c1[(mt * 4 + 0) * 32 + lane], wr_l = s_c1[(mt * 4 + 1) * 32 + lane];
-      const uint4 wi_h = s_c1[(mt * 4 + 2) * 32 + lane], wi_l = s_c1[(mt * 4 + 3) * 32 + lane];
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float (&tr)[4] = T[0][mt][j];
-        float (&ti)[4] = T[1][mt][j];
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { tr[c] = 0.f; ti[c] = 0.f; }
-        const uint32_t nh0 = xi_h[j][0] ^ 0x80008000u, nh1 = xi_h[j][1] ^ 0x80008000u;
-        const uint32_t nl0 = xi_l[j][0] ^ 0x80008000u, nl1 = xi_l[j][1] ^ 0x80008000u;
-        // Tr = Wr.Xr - Wi.Xi
-        wfm_mma(tr, wr_h, xr_h[j][0], xr_h[j][1]);
-        wfm_mma(ti, wi_h, xr_h[j][0], xr_h[j][1]);
-        wfm_mma(tr, wi_h, nh0, nh1);
-        wfm_mma(ti, wr_h, xi_h[j][0], xi_h[j][1]);
-        wfm_mma(tr, wr_h, xr_l[j][0], xr_l[j][1]);
-        wfm_mma(ti, wi_h, xr_l[j][0], xr_l[j][1]);
-        wfm_mma(tr, wi_h, nl0, nl1);
-        wfm_mma(ti, wr_h, xi_l[j][0], xi_l[j][1]);
-        wfm_mma(tr, wr_l, xr_h[j][0], xr_h[j][1]);
-        wfm_mma(ti, wi_l, xr_h[j][0], xr_h[j][1]);
-        wfm_mma(tr, wi_l, nh0, nh1);
-        wfm_mma(ti, wr_l, xi_h[j][0], xi_h[j][1]);
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) T[a][mt][j][c] = 0.f;
+    if (!dbg_nomma) {
+      uint32_t nxi_h[2][2], nxi_l[2][2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) { nxi_h[j][c] = xi_h[j][c] ^ 0x80008000u; nxi_l[j][c] = xi_l[j][c] ^ 0x80008000u; }
+      uint4 wr_h[2], wr_l[2], wi_h[2], wi_l[2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        wr_h[mt] = s_c1[(mt * 4 + 0) * 32 + lane]; wr_l[mt] = s_c1[(mt * 4 + 1) * 32 + lane];
+        wi_h[mt] = s_c1[(mt * 4 + 2) * 32 + lane]; wi_l[mt] = s_c1[(mt * 4 + 3) * 32 + lane];
       }
+#define WFT_S1(WR, WI, XR, XI, NXI)                                            \
+  _Pragma("unroll") for (int mt = 0; mt < 2; ++mt)                             \
+  _Pragma("unroll") for (int j = 0; j < 2; ++j) {                              \
+    wfm_mma(T[0][mt][j], WR[mt], XR[j][0], XR[j][1]);                          \
+    wfm_mma(T[1][mt][j], WI[mt], XR[j][0], XR[j][1]);                          \
+  }                                                                            \
+  _Pragma("unroll") for (int mt = 0; mt < 2; ++mt)                             \
+  _Pragma("unroll") for (int j = 0; j < 2; ++j) {                              \
+    wfm_mma(T[0][mt][j], WI[mt], NXI[j][0], NXI[j][1]);                        \
+    wfm_mma(T[1][mt][j], WR[mt], XI[j][0], XI[j][1]);                          \
+  }
+      // Tr = Wr.Xr - Wi.Xi     Ti = Wi.Xr + Wr.Xi     (hi.hi, hi.lo, lo.hi)
+      WFT_S1(wr_h, wi_h, xr_h, xi_h, nxi_h)
+      WFT_S1(wr_h, wi_h, xr_l, xi_l, nxi_l)
+      WFT_S1(wr_l, wi_l, xr_h, xi_h, nxi_h)
+#undef WFT_S1
+    } else {
+      T[0][0][0][0] = __uint_as_float(xr_h[0][0]); T[1][1][1][1] = __uint_as_float(xi_l[1][1]);
     }
 
     // ---- stage-2 A fragments: a0 = tile(j=0) c0,c1  a1 = tile(j=0) c2,c3  a2 = tile(j=1) c0,c1  a3 = tile(j=1) c2,c3 ----
@@ -397,6 +426,7 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
     }
 
     // ---- stage 2 + |.|^2 + 2 x 2 binning, all in-thread: pix[u][b] = detector pixel (px(u, g), py(b, q)) ----
+    // Four accumulator tiles (Yr / Yi of both fx tiles) advance in lock step per fy tile b.
     float pix[2][4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -404,32 +434,40 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
       const uint4 cn = s_c2[(b * 3 + 2) * 32 + lane];     // {-Wi_hi b0, -Wi_hi b1, -Wi_lo b0, -Wi_lo b1}
       uint4 cl = make_uint4(0u, 0u, 0u, 0u);
       if (FULL) cl = s_c2[(b * 3 + 1) * 32 + lane];       // lo
+      float yr[2][4], yi[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { yr[u][c] = 0.f; yi[u][c] = 0.f; }
+      if (!dbg_nomma) {
+        // Yr = Tr.Wr - Ti.Wi     Yi = Tr.Wi + Ti.Wr
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { wfm_mma(yr[u], tr_h[u], ch.x, ch.y); wfm_mma(yi[u], tr_h[u], ch.z, ch.w); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { wfm_mma(yr[u], ti_h[u], cn.x, cn.y); wfm_mma(yi[u], ti_h[u], ch.x, ch.y); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { wfm_mma(yr[u], tr_l[u], ch.x, ch.y); wfm_mma(yi[u], tr_l[u], ch.z, ch.w); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { wfm_mma(yr[u], ti_l[u], cn.x, cn.y); wfm_mma(yi[u], ti_l[u], ch.x, ch.y); }
+        if (FULL) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) { wfm_mma(yr[u], tr_h[u], cl.x, cl.y); wfm_mma(yi[u], tr_h[u], cl.z, cl.w); }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) { wfm_mma(yr[u], ti_h[u], cn.z, cn.w); wfm_mma(yi[u], ti_h[u], cl.x, cl.y); }
+        }
+      } else {
+        yr[0][0] = __uint_as_float(tr_h[0].x ^ ch.x); yi[1][3] = __uint_as_float(ti_l[1].w ^ cn.y);
+      }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        float yr[4] = {0.f, 0.f, 0.f, 0.f}, yi[4] = {0.f, 0.f, 0.f, 0.f};
-        // Yr = Tr.Wr - Ti.Wi     Yi = Tr.Wi + Ti.Wr
-        wfm_mma(yr, tr_h[u], ch.x, ch.y);
-        wfm_mma(yi, tr_h[u], ch.z, ch.w);
-        wfm_mma(yr, ti_h[u], cn.x, cn.y);
-        wfm_mma(yi, ti_h[u], ch.x, ch.y);
-        wfm_mma(yr, tr_l[u], ch.x, ch.y);
-        wfm_mma(yi, tr_l[u], ch.z, ch.w);
-        wfm_mma(yr, ti_l[u], cn.x, cn.y);
-        wfm_mma(yi, ti_l[u], ch.x, ch.y);
-        if (FULL) {
-          wfm_mma(yr, tr_h[u], cl.x, cl.y);
-          wfm_mma(yi, tr_h[u], cl.z, cl.w);
-          wfm_mma(yr, ti_h[u], cn.z, cn.w);
-          wfm_mma(yi, ti_h[u], cl.x, cl.y);
-        }
-        float a = yr[0] * yr[0];
-        a = fmaf(yi[0], yi[0], a);
-        a = fmaf(yr[1], yr[1], a);
-        a = fmaf(yi[1], yi[1], a);
-        float c = yr[2] * yr[2];
-        c = fmaf(yi[2], yi[2], c);
-        c = fmaf(yr[3], yr[3], c);
-        c = fmaf(yi[3], yi[3], c);
+        float a = yr[u][0] * yr[u][0];
+        a = fmaf(yi[u][0], yi[u][0], a);
+        a = fmaf(yr[u][1], yr[u][1], a);
+        a = fmaf(yi[u][1], yi[u][1], a);
+        float c = yr[u][2] * yr[u][2];
+        c = fmaf(yi[u][2], yi[u][2], c);
+        c = fmaf(yr[u][3], yr[u][3], c);
+        c = fmaf(yi[u][3], yi[u][3], c);
         pix[u][b] = a + c;
       }
     }
