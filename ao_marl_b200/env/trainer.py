@@ -46,3 +46,49 @@ class BatchedRollout:
             self.total_step += 1
         self.num_episode += 1
         return r_total
+
+
+class BatchedTrainer(BatchedRollout):
+    """Episode loop with learning: TrainerRPC.episode + manage_memory + update_all_agents
+    (train_rpc.py:503-553, 734-757, 556-560) for all agents and all environments at once.
+
+    Every env-step contributes E transitions per agent to the learner's device replay (credit assignment through
+    `DelayedMDP` exactly as the reference: oldest state/action of the window, newest next state, current reward,
+    mask = 1 because episodes are time-limited, train_rpc.py:755); after the episode the learner runs
+    `updates_per_episode` batched SAC updates (gradients all-reduced over the process group when there is one)
+    and the new actors are uploaded into the simulator's tables."""
+
+    def __init__(self, env, learner, seed=1234, updates_per_episode=1000):
+        super().__init__(env, seed=seed)
+        import torch
+        self.learner = learner
+        self.updates_per_episode = int(updates_per_episode)
+        dev = learner.device
+        idx = torch.as_tensor(self.rl.agent_idx.astype(np.int64), device=dev)        # [A, IN], -1 = pad
+        act = torch.as_tensor(self.rl.agent_act.astype(np.int64), device=dev)        # [A, ACT], -1 = pad
+        self._idx, self._idx_ok = idx.clamp(min=0), (idx >= 0).float()
+        self._act, self._act_ok = act.clamp(min=0), (act >= 0).float()
+
+    def states_per_agent(self, state):
+        """[E, state_dim] -> [A, E, IN] (zero padded; TrainerRPC.divide_states_for_agents, train_rpc.py:418-427)."""
+        return state[:, self._idx].permute(1, 0, 2) * self._idx_ok[:, None, :]
+
+    def actions_per_agent(self, action):
+        """[E, action_dim] -> [A, E, ACT] (select_correct_modes_for_array, train_rpc.py:650-665)."""
+        return action[:, self._act].permute(1, 0, 2) * self._act_ok[:, None, :]
+
+    def _push(self, s0, a0, s2, r):
+        import torch
+        mem = self.learner.memory
+        mem.push(self.states_per_agent(s0), self.actions_per_agent(a0), r.t().contiguous(),
+                 self.states_per_agent(s2), torch.ones_like(r.t()))
+
+    def train_episode(self, steps=None, updates=None):
+        r_total = self.episode(steps=steps, on_transition=self._push)
+        n = self.updates_per_episode if updates is None else int(updates)
+        stats = None
+        if len(self.learner.memory) > self.learner.batch_size:
+            for _ in range(n):
+                stats = self.learner.update()
+            self.learner.upload_actors(self.sim)
+        return r_total, stats

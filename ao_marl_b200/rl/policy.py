@@ -15,7 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 LOG_SIG_MIN = -20.0
-EPS = 1e-6
+EPS = 1e-5          # model_rpc.py:13 (epsilon)
 
 
 class GaussianPolicy(nn.Module):

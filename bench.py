@@ -25,6 +25,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# DRAM bytes per environment per launch of the sensor kernel from `ncu --set full` (dram__bytes_read.sum +
+# dram__bytes_write.sum of one launch at E = 1024, divided by 1024): profiles/r01_wfs_tma_E1024_metrics.csv,
+# profiles/r01_wfs_mma_E1024_metrics.csv.  Used for roofline.traffic (scaled to the E of this run).
+NCU_DRAM_BYTES_PER_ENV = {("40x40", "wfs_frame_tma_kernel"): (4.108122e9 + 13.919744e6) / 1024,
+                          ("40x40", "wfs_frame_mma_kernel"): (4.062998e9 + 18.132992e6) / 1024}
+
 WORKLOADS = {
     "40x40": dict(par="production_sh_40x40_8m_3layers.py", world_size=44,
                   env_rl=dict(n_zernike_start_end=[0, 1260], window_n_zernike=20, include_tip_tilt_windowed=True,
@@ -136,15 +142,18 @@ def cpu_env_factory(workload_key, cmat_cache=None):
 
 
 def _cpu_worker(args):
-    workload_key, seed, seconds, min_steps = args
+    blob_path, seed, seconds, min_steps = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import pickle
     try:
         import torch
         torch.set_num_threads(1)
     except Exception:
         pass
-    make, t, rl = cpu_env_factory(workload_key)
-    env = make(seed)
+    from oracle import loop
+    with open(blob_path, "rb") as f:
+        d = pickle.load(f)
+    env = loop.OracleEnv(d["tab"], d["cmat"], d["Btt"], d["P"], d["rl"], seed=seed)
     # no 2N-extrusion reset inside the sample: start from a short warm-up of the screens
     for l in range(env.atm.nl):
         for _ in range(8):
@@ -163,15 +172,26 @@ def _cpu_worker(args):
 
 
 def cpu_baseline(workload_key, seconds, procs=1):
-    """env-steps/s of the oracle on `procs` host processes (one environment each), bounded sample."""
+    """env-steps/s of the oracle on `procs` host processes (one environment each), bounded sample.  The static
+    tables are built once in this process and handed to the workers through a pickle."""
     import multiprocessing as mp
+    import pickle
     t0 = time.perf_counter()
-    if procs == 1:
-        res = [_cpu_worker((workload_key, 1234, seconds, 2))]
-    else:
-        ctx = mp.get_context("spawn")
-        with ctx.Pool(procs) as pool:
-            res = pool.map(_cpu_worker, [(workload_key, 1234 + i, seconds, 2) for i in range(procs)])
+    make, t, rl = cpu_env_factory(workload_key)
+    cells = dict(zip(make.__code__.co_freevars, (c.cell_contents for c in make.__closure__)))
+    blob = dict(tab=cells["tab"], cmat=cells["cmat"], Btt=cells["t"].Btt, P=cells["t"].P, rl=cells["rl"])
+    with tempfile.NamedTemporaryFile("wb", suffix=".pkl", delete=False) as f:
+        pickle.dump(blob, f, protocol=pickle.HIGHEST_PROTOCOL)
+        path = f.name
+    try:
+        if procs == 1:
+            res = [_cpu_worker((path, 1234, seconds, 2))]
+        else:
+            ctx = mp.get_context("spawn")
+            with ctx.Pool(procs) as pool:
+                res = pool.map(_cpu_worker, [(path, 1234 + i, seconds, 2) for i in range(procs)])
+    finally:
+        os.unlink(path)
     rate = sum(n / el for n, el in res)
     steps = sum(n for n, _ in res)
     return dict(value=rate, unit="env-steps/s", cores=procs, kind="port",
@@ -333,11 +353,16 @@ def run_ours(args):
                            sum(int(n) ** 2 for n in t.dim_screens) * 4 * E / 1e9),
                        "us_per_frame": ms / args.steps / E * 1e3, "build_s": t_build},
             "roofline": {"kernel": wfs_kernel_name, "bound": "hbm", "achieved": achieved, "peak": hbm,
-                         "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": (NCU_DRAM_BYTES_PER_ENV[(args.workload, wfs_kernel_name)] * E
+                                     if (args.workload, wfs_kernel_name) in NCU_DRAM_BYTES_PER_ENV else None),
+                         "traffic_source": "ncu dram bytes per env at E=1024 (profiles/) x E",
+                         "algorithmic_bytes": bytes_per_frame * E,
                          "peak_source": "measured" if peaks else "fallback",
                          "ms_per_launch": wfs_ms, "share_of_step": wfs_ms / (ms / args.steps),
                          "fp32_tflops_algorithmic": flops_per_frame * E / (wfs_ms * 1e-3) / 1e12,
-                         "note": "instruction-issue / tensor-pipe bound (3 x fp16 split MMA DFT in registers), not HBM bound: "
+                         "note": "issue-slot bound: 144 legacy HMMA (3 x fp16 split DFT in registers) cost ~6 issue cycles "
+                                 "each next to ~1030 other warp instructions per subaperture; not HBM bound: "
                                  "see DESIGN.md" if args.wfs_path != "simt" else
                                  "issue-bound on the FP32 pipe (SIMT pruned FFT), not on HBM: see DESIGN.md"},
             "e2e": {"value": k_e2e * E * world / (ms_e2e * 1e-3), "unit": "env-steps/s",

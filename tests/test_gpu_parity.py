@@ -308,3 +308,142 @@ def test_delay_impulse(system10, torch):
         assert errs[2] > 0.0                 # frame t+1 in 0-based counting of frames after the action step
     finally:
         sim.set_loop(True)
+
+
+# ------------------------------------------------------------------------------------------------
+# Full-size configuration (production_sh_40x40_8m_3layers, 1200 subapertures, 1286 actuators, 3 layers,
+# 43 windowed agents): the oracle needs minutes per frame here, so the checks are size-independent properties.
+@pytest.fixture(scope="module")
+def system40(torch):
+    from ao_marl_b200.system import build_system
+    sim, t, rl = build_system("production_sh_40x40_8m_3layers.py", 6,
+                              env_rl=dict(n_zernike_start_end=[0, 1260], window_n_zernike=20,
+                                          include_tip_tilt_windowed=True, n_reverse_filtered_from_cmat=5,
+                                          delayed_assignment=2), world_size=44, seed=0)
+    yield sim, t, rl
+    sim.close()
+
+
+def test_40x40_flat_and_tilt(system40, torch):
+    """Flat wavefront -> zero slopes; a tip-tilt command -> the same slope on every subaperture, linear in the
+    command; all on the staged kernel."""
+    sim, t, rl = system40
+    assert sim.wfs_kernel() == "wfs_frame_tma_kernel", sim.lib.aom_last_error(sim._ctx)
+    nv = t.p_wfs._nvalid
+    sim.reset(np.arange(6, dtype=np.int64) + 500)
+    sim.reset_dm()
+    sim.comp_wfs_image(atmos=False, dms=True, noise=-1.0)
+    sim.do_centroids()
+    s = sim.rows("SLOPES", t.nslopes).cpu().numpy()
+    assert np.abs(s).max() < 2e-6
+    volts = np.zeros((6, t.nactu), np.float32)
+    volts[:, -2] = [50.0, 100.0, 200.0, 0.0, 0.0, 50.0]       # ~0.025 .. 0.1 arcsec on a 0.258 arcsec pixel
+    volts[:, -1] = [0.0, 0.0, 0.0, 50.0, 100.0, 50.0]
+    sim.set_dm_volts(torch.as_tensor(volts, device="cuda"))
+    sim.comp_wfs_image(atmos=False, dms=True, noise=-1.0)
+    sim.do_centroids()
+    s = sim.rows("SLOPES", t.nslopes).cpu().numpy()
+    sx, sy = s[:, :nv], s[:, nv:]
+    full = np.asarray(t.p_wfs._fluxPerSub_list) > 0.999          # fully illuminated subapertures
+    for e in range(6):
+        for comp in (sx[e][full], sy[e][full]):
+            assert np.abs(comp - comp.mean()).max() < 2e-3 * max(np.abs(s[e]).max(), 1e-9) + 1e-6
+    m = np.hypot(sx[:, full].mean(axis=1), sy[:, full].mean(axis=1))
+    assert m[0] > 5e-3                                                            # a real signal
+    assert abs(m[1] / m[0] - 2.0) < 1e-2 and abs(m[2] / m[0] - 4.0) < 4e-2      # linear in the command
+    assert abs(m[4] / m[3] - 2.0) < 1e-2
+    # the two mirror axes are orthogonal on the sensor
+    d0 = np.array([sx[0, full].mean(), sy[0, full].mean()])
+    d3 = np.array([sx[3, full].mean(), sy[3, full].mean()])
+    assert abs(d0 @ d3) < 1e-3 * np.linalg.norm(d0) * np.linalg.norm(d3)
+
+
+def test_40x40_kernel_generations_agree(system40, torch):
+    """Three layers + random mirror shape: staged tensor kernel == register tensor kernel == float32 FFT kernel,
+    also after the torus seam has moved into the pupil."""
+    sim, t, rl = system40
+    sim.reset(np.arange(6, dtype=np.int64) + 900)
+    r = np.random.default_rng(3)
+    volts = (r.standard_normal((6, t.nactu)) * 0.3).astype(np.float32)
+    sim.set_dm_volts(torch.as_tensor(volts, device="cuda"))
+    try:
+        for it in range(3):
+            for _ in range(1 + 40 * it):
+                sim.move_atmos()
+            res = {}
+            for path in ("simt", "tensor", "tensor_reg"):
+                sim.set_wfs_path(path)
+                sim.comp_wfs_image(noise=-1.0)
+                sim.do_centroids()
+                res[path] = sim.rows("SLOPES", t.nslopes).cpu().numpy().copy()
+            sim.check_device()
+            assert np.abs(res["simt"]).max() > 1e-3
+            assert relerr(res["tensor"], res["simt"]) < 2e-5, it
+            assert relerr(res["tensor_reg"], res["simt"]) < 2e-5, it
+    finally:
+        sim.set_wfs_path("tensor")
+
+
+def test_40x40_closed_loop_properties(system40, torch):
+    """Integrator-only loop converges (residual slopes far below open loop); the modal projector applied by
+    rl_control with a zero action is idempotent; rewards are negative and finite for every agent."""
+    sim, t, rl = system40
+    sim.reset(np.arange(6, dtype=np.int64) + 1234)
+    sim.comp_wfs_image(noise=-1.0)
+    sim.do_centroids()
+    open_rms = float(sim.rows("SLOPES", t.nslopes).square().mean().sqrt())
+    for _ in range(40):
+        sim.step(mode=2)
+    closed_rms = float(sim.rows("SLOPES", t.nslopes).square().mean().sqrt())
+    assert closed_rms < 0.5 * open_rms, (open_rms, closed_rms)
+    zero = torch.zeros((6, rl.action_dim), device="cuda")
+    sim.rl_control(zero)
+    c1 = sim.rows("COM", t.nactu).clone()
+    sim.rl_control(zero)
+    c2 = sim.rows("COM", t.nactu)
+    assert float((c1 - c2).abs().max()) < 1e-4 * float(c1.abs().max())
+    sim.step(mode=0)
+    rw = sim.buffer("REWARD").view(6, rl.n_agents)
+    assert torch.isfinite(rw).all() and float(rw.max()) <= 0.0
+    st = sim.rows("STATE", rl.state_dim)
+    assert torch.isfinite(st).all()
+    sim.check_device()
+
+
+def test_batched_trainer_learns_on_device(torch):
+    """AoEnv + BatchedTrainer + BatchedSAC on the 10x10 system: pooled replay fills with E transitions per step
+    after the credit-assignment window, updates run, and the actors uploaded into the simulator reproduce the
+    learner's own forward pass (aom_actor_forward == torch policy, eval mode)."""
+    from ao_marl_b200.env.ao_env import AoEnv
+    from ao_marl_b200.env.config_rl import Config
+    from ao_marl_b200.env.trainer import BatchedTrainer
+    from ao_marl_b200.rl.sac import BatchedSAC
+    cfg = Config(parameters_telescope="production_sh_10x10_2m.py", n_zernike_start_end=[0, 80],
+                 n_reverse_filtered_from_cmat=5, delayed_assignment=2)
+    cfg.sac.update(batch_size=64, hidden_size_critic=64, num_layers_critic=2)
+    E = 8
+    env = AoEnv(cfg, n_env=E, world_size=3, initial_seed=1234)
+    rl = env.supervisor.rl
+    learner = BatchedSAC.from_layout(rl, device="cuda", seed=3, memory_size=4096)
+    tr = BatchedTrainer(env, learner, seed=1234, updates_per_episode=6)
+    steps = 24
+    r_total, stats = tr.train_episode(steps=steps)
+    depth = cfg.env_rl["delayed_assignment"] + 1
+    assert len(learner.memory) == E * (steps - depth)
+    assert stats is not None and all(torch.isfinite(v).all() for v in stats.values())
+    assert np.isfinite(r_total) and r_total < 0
+    # stored transitions are consistent: next state of a slot differs from its state, rewards negative
+    assert float(learner.memory.r[:, :len(learner.memory)].max()) <= 0
+    # uploaded actors == learner forward
+    env.sim.actor_forward(True)
+    a_sim = env.sim.rows("ACTION_MEAN", rl.action_dim).clone()
+    s = env.sim.rows("STATE", rl.state_dim)
+    with torch.no_grad():
+        _, _, mean = learner.policy_sample(tr.states_per_agent(s))
+    a_ref = torch.zeros_like(a_sim)
+    for a in range(rl.n_agents):
+        n = learner.act_dims[a]
+        a_ref[:, tr._act[a, :n]] = mean[a, :, :n]
+    assert float((a_sim - a_ref).abs().max()) < 2e-4
+    env.sim.check_device()
+    env.sim.close()
