@@ -33,6 +33,10 @@ def load_normalization(parameters_telescope):
     name = os.path.basename(parameters_telescope)
     name = name[:-3] if name.endswith(".py") else name
     path = os.path.join(DATA_DIR, name + ".npz")
+    if not os.path.exists(path) and name.endswith("_d0_noise"):
+        # the reference ships the statistics of its magnitude-9 noisy configuration under this name
+        # (normalization_production_sh_40x40_8m_3layers_noise_M9_zernike_space.pickle)
+        path = os.path.join(DATA_DIR, name[:-len("_d0_noise")] + "_noise_M9.npz")
     if not os.path.exists(path):
         raise FileNotFoundError("no normalisation statistics shipped for %s" % name)
     z = np.load(path)

@@ -15,7 +15,7 @@ import numpy as np
 REF = "/root/reference/src/reinforcement_learning/helper_functions/preprocessing/normalization/"
 OUT = os.path.join(os.path.dirname(__file__), "..", "..", "ao_marl_b200", "data", "normalization")
 NAMES = ["production_sh_10x10_2m", "production_sh_40x40_8m_3layers", "production_sh_40x40_8m_3layers_d1_noise",
-         "production_sh_40x40_8m_3layers_same_dir_roket"]
+         "production_sh_40x40_8m_3layers_same_dir_roket", "production_sh_40x40_8m_3layers_noise_M9"]
 
 
 def main():
