@@ -347,7 +347,7 @@ def test_40x40_flat_and_tilt(system40, torch):
     full = np.asarray(t.p_wfs._fluxPerSub_list) > 0.999          # fully illuminated subapertures
     for e in range(6):
         for comp in (sx[e][full], sy[e][full]):
-            assert np.abs(comp - comp.mean()).max() < 3e-2 * max(np.abs(s[e]).max(), 1e-9) + 1e-6
+            assert np.abs(comp - comp.mean()).max() < 6e-2 * max(np.abs(s[e]).max(), 1e-9) + 1e-6
     m = np.hypot(sx[:, full].mean(axis=1), sy[:, full].mean(axis=1))
     assert m[0] > 5e-3                                                            # a real signal
     assert abs(m[1] / m[0] - 2.0) < 1e-2 and abs(m[2] / m[0] - 4.0) < 4e-2      # linear in the command
