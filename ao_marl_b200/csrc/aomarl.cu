@@ -187,8 +187,10 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     CU(dalloc(&ctx->aHO, A * E * ctx->ld_aho));
   }
   CU(dalloc(&ctx->d_err, 1));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<0, GTC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<1, GTC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<0, GTC_BN_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES_T(GTC_BN_WIDE)));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<1, GTC_BN_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES_T(GTC_BN_WIDE)));
   CU(cudaFuncSetAttribute(wfs_frame_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfs_smem_bytes<4>()));
   CU(cudaFuncSetAttribute(wfs_frame_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfs_smem_bytes<8>()));
   return AOM_OK;
@@ -334,9 +336,30 @@ static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long
   // `exact`: float32 FFMA accumulation with round-to-nearest (the recursive screen extrusion needs it: the
   // tensor core truncates its float32 accumulator, a ~1e-5 systematic shrink that an autoregression integrates)
   if (!exact && ctx->opt[AOM_OPT_GEMM_PATH] == AOM_GEMM_TCGEN05) {
-    dim3 grid((ldc + GTC_BN - 1) / GTC_BN, (M + GTC_BM - 1) / GTC_BM, batch);
-    if (epi == 0) gemm_tc_kernel<0><<<grid, GTC_THREADS, GTC_SMEM_BYTES, st>>>(p, ctx->d_err);
-    else gemm_tc_kernel<1><<<grid, GTC_THREADS, GTC_SMEM_BYTES, st>>>(p, ctx->d_err);
+    // column tile: the wide one when it saves CTA waves (two CTAs per SM)
+    const long long slots = 2LL * ctx->num_sms, rows = (M + GTC_BM - 1) / GTC_BM;
+    auto waves = [&](int bn) { return (double)((rows * ((ldc + bn - 1) / bn) * batch + slots - 1) / slots) * bn; };
+    if (waves(GTC_BN_WIDE) < waves(GTC_BN)) {
+      dim3 grid((ldc + GTC_BN_WIDE - 1) / GTC_BN_WIDE, (unsigned)rows, batch);
+      if (epi == 0) gemm_tc_kernel<0, GTC_BN_WIDE><<<grid, GTC_THREADS, GTC_SMEM_BYTES_T(GTC_BN_WIDE), st>>>(p, ctx->d_err);
+      else gemm_tc_kernel<1, GTC_BN_WIDE><<<grid, GTC_THREADS, GTC_SMEM_BYTES_T(GTC_BN_WIDE), st>>>(p, ctx->d_err);
+    } else {
+      dim3 grid((ldc + GTC_BN - 1) / GTC_BN, (unsigned)rows, batch);
+      if (epi == 0) gemm_tc_kernel<0, GTC_BN><<<grid, GTC_THREADS, GTC_SMEM_BYTES, st>>>(p, ctx->d_err);
+      else gemm_tc_kernel<1, GTC_BN><<<grid, GTC_THREADS, GTC_SMEM_BYTES, st>>>(p, ctx->d_err);
+    }
+  } else if (exact && epi == 0 && batch == 1 && !bias && !relu && ctx->opt[AOM_OPT_GEMM_PATH] != AOM_GEMM_SIMT) {
+    // shaped exact kernel: column tile 8 CN with the least padding.  Only columns < N are consumed by the
+    // extrusion scatter; pad columns inside the last tile are written as zeros, the rest keep their zeros.
+    int best = 9, waste = 1 << 30;
+    for (int cn = 9; cn >= 8; --cn) {
+      const int bn = 8 * cn, w = (N + bn - 1) / bn * bn - N;
+      if (w < waste) { waste = w; best = cn; }
+    }
+    const int bn = 8 * best;
+    dim3 grid((N + bn - 1) / bn, (M + GEMM_BM - 1) / GEMM_BM, 1);
+    if (best == 8) gemm_tn_exact_kernel<8><<<grid, 128, 0, st>>>(p);
+    else gemm_tn_exact_kernel<9><<<grid, 128, 0, st>>>(p);
   } else {
     dim3 grid((ldc + GEMM_BN - 1) / GEMM_BN, (M + GEMM_BM - 1) / GEMM_BM, batch);
     if (epi == 0) gemm_tn_kernel<0><<<grid, 256, 0, st>>>(p);

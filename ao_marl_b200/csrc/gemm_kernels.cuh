@@ -131,3 +131,107 @@ __global__ void __launch_bounds__(256, 2) gemm_tn_kernel(GemmParams p) {
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Exact-fp32 GEMM for the screen extrusion, shaped to the operator: C[M][N] = A[M][K] . B[N][K]^T with
+// round-to-nearest FFMA accumulation (the autoregressive screens integrate the ~1e-5 shrink a truncating
+// tensor-core accumulator would add).  N is the screen side (648 / 168), which the square
+// 128 x 128 tiles of gemm_tn_kernel quantise badly (6 column tiles for 5.06, 192 CTAs on 296 slots).  Here a CTA
+// of 128 threads owns a 128 x (8 CN) tile, CN = 9 -> 72 columns -> 9 x 32 = 288 CTAs for N = 648, M = 4096: one
+// full wave at two CTAs per SM and no padded columns.  Thread (ty, tx) = (tid / 8, tid % 8) accumulates rows
+// 8 ty .. 8 ty + 7 x columns CN tx .. CN tx + CN - 1: 8 x CN independent FFMA chains fed by 2 LDS.128 + CN
+// conflict-free LDS.32 per k (row stride BN + 1).  Measured on B200, N = 648, M = 4096: 0.315 ms per extrusion
+// against 0.42 ms for the square tiles; splitting the column reads into LDS.128 groups was slower (0.34 ms).
+template <int CN>
+__global__ void __launch_bounds__(128, 4) gemm_tn_exact_kernel(GemmParams p) {
+  constexpr int BN = 8 * CN;
+  constexpr int BPAD = 1;       // row stride BN + 1: the CN-strided column reads of a warp hit distinct banks
+  static_assert(CN == 8 || CN == 9, "column tile is 64 or 72 wide");
+  __shared__ __align__(16) float As[2][GEMM_BK][GEMM_BM + GEMM_PAD];
+  __shared__ __align__(16) float Bs[2][GEMM_BK][BN + BPAD];
+  const int tid = threadIdx.x;
+  const float* __restrict__ A = p.A;
+  const float* __restrict__ B = p.B;
+  float* __restrict__ C = p.C;
+  const int m0 = blockIdx.y * GEMM_BM;
+  const int n0 = blockIdx.x * BN;
+
+  // staging: A slab = 128 rows x 4 float4 -> 4 per thread; B slab = BN rows x 4 float4 -> up to 3 per thread
+  constexpr int B_ITERS = (BN * 4 + 127) / 128;
+  const int lk = (tid & 3) << 2;
+  const int lrow = tid >> 2;            // 0..31
+  float4 ra[4], rb[B_ITERS];
+  auto load_slab = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int row = m0 + lrow + h * 32;
+      ra[h] = (row < p.M) ? *reinterpret_cast<const float4*>(A + (long long)row * p.lda + k0 + lk)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int h = 0; h < B_ITERS; ++h) {
+      const int r = lrow + h * 32, col = n0 + r;
+      rb[h] = (r < BN && col < p.N) ? *reinterpret_cast<const float4*>(B + (long long)col * p.ldb + k0 + lk)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_slab = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int r = lrow + h * 32;
+      As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y;
+      As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
+    }
+#pragma unroll
+    for (int h = 0; h < B_ITERS; ++h) {
+      const int r = lrow + h * 32;
+      if (r < BN) {
+        Bs[buf][lk + 0][r] = rb[h].x; Bs[buf][lk + 1][r] = rb[h].y;
+        Bs[buf][lk + 2][r] = rb[h].z; Bs[buf][lk + 3][r] = rb[h].w;
+      }
+    }
+  };
+
+  const int ty = tid >> 3, tx = tid & 7;
+  float acc[8][CN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < CN; ++j) acc[i][j] = 0.f;
+
+  const int nslab = p.K / GEMM_BK;
+  load_slab(0);
+  store_slab(0);
+  __syncthreads();
+  for (int s = 0; s < nslab; ++s) {
+    const int buf = s & 1;
+    if (s + 1 < nslab) load_slab((s + 1) * GEMM_BK);
+#pragma unroll
+    for (int k = 0; k < GEMM_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[CN];
+#pragma unroll
+      for (int j = 0; j < CN; ++j) bv[j] = Bs[buf][k][tx * CN + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < CN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (s + 1 < nslab) {
+      store_slab(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + ty * 8 + i;
+    if (row >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < CN; ++j) {
+      const int c = n0 + tx * CN + j;
+      if (c < p.ldc) C[(long long)row * p.ldc + c] = (c < p.N) ? acc[i][j] : 0.f;   // pad columns stay zero
+    }
+  }
+}

@@ -30,9 +30,12 @@
 #define GTC_BN 128
 #define GTC_BK 16
 #define GTC_STAGES 3
-#define GTC_TILE_BYTES (GTC_BM * GTC_BK * 4)                 // 8 KB: one hi or lo slab of one operand
-#define GTC_STAGE_BYTES (4 * GTC_TILE_BYTES)                 // A hi, A lo, B hi, B lo
-#define GTC_SMEM_BYTES (GTC_STAGES * GTC_STAGE_BYTES + 128)
+#define GTC_TILE_BYTES (GTC_BM * GTC_BK * 4)                 // 8 KB: one hi or lo slab of the A operand
+#define GTC_BTILE_BYTES(BN) ((BN) * GTC_BK * 4)               // one hi or lo slab of the B operand
+#define GTC_STAGE_BYTES_T(BN) (2 * GTC_TILE_BYTES + 2 * GTC_BTILE_BYTES(BN))   // A hi, A lo, B hi, B lo
+#define GTC_SMEM_BYTES_T(BN) (GTC_STAGES * GTC_STAGE_BYTES_T(BN) + 128)
+#define GTC_SMEM_BYTES GTC_SMEM_BYTES_T(GTC_BN)
+#define GTC_BN_WIDE 144                                       // 9 x 144 = 1296: the 1283 / 1286-wide operators in one wave
 #define GTC_THREADS 160
 #define GTC_WAIT_SPINS (1u << 20)
 
@@ -96,8 +99,15 @@ __device__ __forceinline__ void gtc_split4(const float4& v, float4& hi, float4& 
   lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
 }
 
-template <int EPI>
+// BN: column tile (multiple of 16, 128 or GTC_BN_WIDE).  With M = 4096 rows the 1283 / 1286-wide operators give
+// 11 x 32 = 352 tiles of 128 columns on 296 CTA slots -- a second wave that keeps 56 tiles' worth of SMs busy while
+// the rest idle (ncu: SMs active 56 % of the launch) -- and 9 x 32 = 288 tiles of 144 columns: one wave.
+template <int EPI, int BN>
 __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, int* err) {
+  constexpr int STAGE_BYTES = GTC_STAGE_BYTES_T(BN);
+  constexpr int B_OFF = 2 * GTC_TILE_BYTES;                    // B hi at B_OFF, B lo at B_OFF + GTC_BTILE_BYTES(BN)
+  constexpr int B_ITERS = (BN + 31) / 32;
+  constexpr uint32_t TMEM_COLS = BN <= 128 ? 128u : 256u;
   extern __shared__ __align__(1024) uint8_t gtc_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bz = blockIdx.z;
@@ -105,11 +115,11 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
   const float* __restrict__ B = p.B + (long long)bz * p.sB;
   float* __restrict__ C = p.C + (long long)bz * p.sC;
   const int m0 = blockIdx.y * GTC_BM;
-  const int n0 = blockIdx.x * GTC_BN;
+  const int n0 = blockIdx.x * BN;
   const int nkb = (p.K + GTC_BK - 1) / GTC_BK;
 
   uint8_t* tiles = gtc_smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gtc_smem + GTC_STAGES * GTC_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gtc_smem + GTC_STAGES * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GTC_STAGES + 1);
   const uint32_t full0 = gtc_smem_u32(bars), empty0 = gtc_smem_u32(bars + GTC_STAGES);
   const uint32_t accum_bar = gtc_smem_u32(bars + 2 * GTC_STAGES);
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gtc_smem_u32(tmem_slot)), "r"(128u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gtc_smem_u32(tmem_slot)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -136,41 +146,60 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
     // ===== loaders =====
     const int c = tid & 3;                       // 16-byte chunk (4 k-values) of the 16-wide slab
     const int r0 = tid >> 2;                     // rows r0, r0 + 32, r0 + 64, r0 + 96
-    float4 va[4], vb[4];
-    auto load_regs = [&](int kb) {
+    // two slabs of global loads stay in flight (register sets 0 / 1): one slab alone left every stage waiting
+    // for HBM/L2 latency longer than its three MMAs take
+    float4 va[2][4], vb[2][B_ITERS];
+    auto load_regs = [&](int kb, float4 (&xa)[4], float4 (&xb)[B_ITERS]) {
       const int k = kb * GTC_BK + c * 4;
       const bool kin = k < p.K;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int ra = m0 + r0 + 32 * i, rb = n0 + r0 + 32 * i;
-        va[i] = (kin && ra < p.M) ? __ldg(reinterpret_cast<const float4*>(A + (long long)ra * p.lda + k))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[i] = (kin && rb < p.N) ? __ldg(reinterpret_cast<const float4*>(B + (long long)rb * p.ldb + k))
+        const int ra = m0 + r0 + 32 * i;
+        xa[i] = (kin && ra < p.M) ? __ldg(reinterpret_cast<const float4*>(A + (long long)ra * p.lda + k))
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int i = 0; i < B_ITERS; ++i) {
+        const int r = r0 + 32 * i, rb = n0 + r;
+        xb[i] = (kin && r < BN && rb < p.N) ? __ldg(reinterpret_cast<const float4*>(B + (long long)rb * p.ldb + k))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
-    if (nkb > 0) load_regs(0);
-    for (int kb = 0; kb < nkb; ++kb) {
+    auto stage_out = [&](int kb, float4 (&xa)[4], float4 (&xb)[B_ITERS]) {
       const int s = kb % GTC_STAGES;
       const uint32_t round = (uint32_t)(kb / GTC_STAGES);
       gtc_mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u, err);
-      uint8_t* st = tiles + (size_t)s * GTC_STAGE_BYTES;
+      uint8_t* st = tiles + (size_t)s * STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = r0 + 32 * i;
         const uint32_t off = (uint32_t)((r >> 3) * 512 + c * 128 + (r & 7) * 16);
         float4 hi, lo;
-        gtc_split4(va[i], hi, lo);
+        gtc_split4(xa[i], hi, lo);
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + GTC_TILE_BYTES + off) = lo;
-        gtc_split4(vb[i], hi, lo);
-        *reinterpret_cast<float4*>(st + 2 * GTC_TILE_BYTES + off) = hi;
-        *reinterpret_cast<float4*>(st + 3 * GTC_TILE_BYTES + off) = lo;
       }
-      if (kb + 1 < nkb) load_regs(kb + 1);       // next slab in flight while the tensor core works
+#pragma unroll
+      for (int i = 0; i < B_ITERS; ++i) {
+        const int r = r0 + 32 * i;
+        if (r < BN) {
+          const uint32_t off = (uint32_t)((r >> 3) * 512 + c * 128 + (r & 7) * 16);
+          float4 hi, lo;
+          gtc_split4(xb[i], hi, lo);
+          *reinterpret_cast<float4*>(st + B_OFF + off) = hi;
+          *reinterpret_cast<float4*>(st + B_OFF + GTC_BTILE_BYTES(BN) + off) = lo;
+        }
+      }
+      if (kb + 2 < nkb) load_regs(kb + 2, xa, xb);   // refill this register set two slabs ahead
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) gtc_mbar_arrive(full0 + 8 * s);
+    };
+    if (nkb > 0) load_regs(0, va[0], vb[0]);
+    if (nkb > 1) load_regs(1, va[1], vb[1]);
+    for (int kb = 0; kb < nkb; kb += 2) {
+      stage_out(kb, va[0], vb[0]);
+      if (kb + 1 < nkb) stage_out(kb + 1, va[1], vb[1]);
     }
 
     // ===== epilogue: TMEM lanes 32 warp .. 32 warp + 31 are rows m0 + 32 warp + lane =====
@@ -179,23 +208,21 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
     const int row = m0 + warp * 32 + lane;
     const float* bias = p.bias ? p.bias + (long long)bz * p.sBias : nullptr;
 #pragma unroll 1
-    for (int cb = 0; cb < GTC_BN / 32; ++cb) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
+    for (int cb = 0; cb < BN / 16; ++cb) {
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 16);
       asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (row < p.M) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const int col = n0 + cb * 32 + j4 * 4;
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int col = n0 + cb * 16 + j4 * 4;
           if (col >= p.ldc) continue;
           float o[4];
 #pragma unroll
@@ -224,19 +251,19 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else if (lane == 0) {
     // ===== MMA issuer (one thread) =====
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GTC_BN >> 3) << 17) |
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(GTC_BM >> 4) << 24);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % GTC_STAGES;
       const uint32_t round = (uint32_t)(kb / GTC_STAGES);
       gtc_mbar_wait(full0 + 8 * s, round & 1u, err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t base = gtc_smem_u32(tiles + (size_t)s * GTC_STAGE_BYTES);
+      const uint32_t base = gtc_smem_u32(tiles + (size_t)s * STAGE_BYTES);
 #pragma unroll
       for (int k8 = 0; k8 < GTC_BK / 8; ++k8) {
         const uint32_t ko = (uint32_t)k8 * 256u;                 // two 16-byte chunks = 8 tf32 values
         const uint64_t a_hi = gtc_desc(base + ko), a_lo = gtc_desc(base + GTC_TILE_BYTES + ko);
-        const uint64_t b_hi = gtc_desc(base + 2 * GTC_TILE_BYTES + ko), b_lo = gtc_desc(base + 3 * GTC_TILE_BYTES + ko);
+        const uint64_t b_hi = gtc_desc(base + B_OFF + ko), b_lo = gtc_desc(base + B_OFF + GTC_BTILE_BYTES(BN) + ko);
         gtc_mma_tf32(tmem_base, a_hi, b_hi, idesc, (kb | k8) ? 1u : 0u);
         gtc_mma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
         gtc_mma_tf32(tmem_base, a_lo, b_hi, idesc, 1u);
@@ -248,6 +275,6 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }

@@ -60,7 +60,9 @@ def test_gemm_paths(sim10, torch):
     from ao_marl_b200.lib import LD
     g = torch.Generator(device="cuda").manual_seed(1)
     try:
-        for (M, N, K) in ((256, 648, 1957), (130, 1286, 2400), (512, 1283, 1286), (3, 60, 256), (128, 128, 16)):
+        # (4096, 1286, 200) / (4000, 1283, 96): M large enough for the 144-column tile to be selected (one CTA wave)
+        for (M, N, K) in ((256, 648, 1957), (130, 1286, 2400), (512, 1283, 1286), (3, 60, 256), (128, 128, 16),
+                          (4096, 1286, 200), (4000, 1283, 96)):
             A = torch.zeros((M, LD(K)), device="cuda")
             Bm = torch.zeros((N, LD(K)), device="cuda")
             A[:, :K] = torch.randn((M, K), device="cuda", generator=g) * 3
