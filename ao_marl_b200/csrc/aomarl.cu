@@ -14,6 +14,7 @@
 #include "wfs_kernels.cuh"
 #include "wfs_mma.cuh"
 #include "wfs_tma.cuh"
+#include "wfs_pipe.cuh"
 
 static char g_create_error[512] = "";
 
@@ -127,6 +128,7 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     if (w && !strcmp(w, "simt")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_SIMT;
     if (w && !strcmp(w, "tensor_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_FAST;
     if (w && !strcmp(w, "tensor_reg")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_REG;
+    if (w && !strcmp(w, "tensor_pipe")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_PIPE;
   }
   *out = ctx;   // returned even on failure so that aom_last_error / aom_destroy work
   CU(cudaGetDevice(&ctx->device));
@@ -667,8 +669,15 @@ static int wfs_fast_prepare(aom_ctx* ctx) {
   return AOM_OK;
 }
 
-template <int FULL, int NL>
-static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, int grid, long long ipc, cudaStream_t st) {
+template <int FULL, int NL, int NW = WFT_WARPS, int MINB = 2, int NST = 2>
+static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) {
+  const long long total = (long long)p.E * p.nvalid;
+  // contiguous ranges of work items per CTA: about 8 waves of MINB CTAs per SM, at least 16 items per warp
+  long long grid = (long long)ctx->num_sms * MINB * 8;
+  long long ipc = (total + grid - 1) / grid;
+  if (ipc < 16 * NW) ipc = 16 * NW;
+  ipc = (ipc + NW - 1) / NW * NW;
+  grid = (total + ipc - 1) / ipc;
   WfsTmaParams P;
   memset(&P, 0, sizeof(P));
   P.p = p;
@@ -676,26 +685,49 @@ static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, int grid, long lo
   P.f.items_per_cta = ipc;
   { const char* d = getenv("AOM_WFS_DBG"); P.f.dbg = d ? atoi(d) : 0; }
   for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
-  const size_t smem = wft_smem_bytes<NL>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
+  const size_t smem = wft_smem_bytes<NL, NW, NST>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(wfs_frame_tma_kernel<FULL, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wfs_frame_tma_kernel<FULL, NL, NW, MINB, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_tma_kernel): %s", cudaGetErrorString(e));
     configured = smem;
   }
-  wfs_frame_tma_kernel<FULL, NL><<<grid, WFT_WARPS * 32, smem, st>>>(P);
+  wfs_frame_tma_kernel<FULL, NL, NW, MINB, NST><<<(unsigned)grid, NW * 32, smem, st>>>(P);
+  return AOM_OK;
+}
+
+template <int FULL, int NL, int DM>
+static int wfs_pipe_launch_t(aom_ctx* ctx, const WfsParams& p, int grid, long long ipc, cudaStream_t st) {
+  WfsTmaParams P;
+  memset(&P, 0, sizeof(P));
+  P.p = p;
+  P.f = ctx->fast;
+  P.f.items_per_cta = ipc;
+  for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
+  const size_t smem = wft_smem_bytes<NL>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(wfs_frame_pipe_kernel<FULL, NL, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_pipe_kernel): %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  wfs_frame_pipe_kernel<FULL, NL, DM><<<grid, WFT_WARPS * 32, smem, st>>>(P);
   return AOM_OK;
 }
 
 static int wfs_fast_launch(aom_ctx* ctx, const WfsParams& p, int full, cudaStream_t st) {
-  const long long total = (long long)p.E * p.nvalid;
-  // contiguous ranges of work items per CTA: about 8 waves of 2 CTAs per SM, at least 16 items per warp
-  long long grid = (long long)ctx->num_sms * 2 * 8;
-  long long ipc = (total + grid - 1) / grid;
-  if (ipc < 16 * WFT_WARPS) ipc = 16 * WFT_WARPS;
-  ipc = (ipc + WFT_WARPS - 1) / WFT_WARPS * WFT_WARPS;
-  grid = (total + ipc - 1) / ipc;
-#define WFT_GO(NL) return full ? wfs_fast_launch_t<1, NL>(ctx, p, (int)grid, ipc, st) : wfs_fast_launch_t<0, NL>(ctx, p, (int)grid, ipc, st)
+  if (ctx->opt[AOM_OPT_WFS_PATH] == AOM_WFS_TENSOR_PIPE && full && (p.n_layers == 1 || p.n_layers == 3)) {
+    // software-pipelined variant (wfs_pipe.cuh): measured equal to the staged kernel, kept as an experiment
+    const long long total = (long long)p.E * p.nvalid;
+    long long grid = (long long)ctx->num_sms * 2 * 8;
+    long long ipc = (total + grid - 1) / grid;
+    if (ipc < 16 * WFT_WARPS) ipc = 16 * WFT_WARPS;
+    ipc = (ipc + WFT_WARPS - 1) / WFT_WARPS * WFT_WARPS;
+    grid = (total + ipc - 1) / ipc;
+    if (p.n_layers == 3) return p.use_dm ? wfs_pipe_launch_t<1, 3, 1>(ctx, p, (int)grid, ipc, st) : wfs_pipe_launch_t<1, 3, 0>(ctx, p, (int)grid, ipc, st);
+    return p.use_dm ? wfs_pipe_launch_t<1, 1, 1>(ctx, p, (int)grid, ipc, st) : wfs_pipe_launch_t<1, 1, 0>(ctx, p, (int)grid, ipc, st);
+  }
+#define WFT_GO(NL) return full ? wfs_fast_launch_t<1, NL>(ctx, p, st) : wfs_fast_launch_t<0, NL>(ctx, p, st)
   switch (p.n_layers) {
     case 0: WFT_GO(0);
     case 1: WFT_GO(1);
@@ -762,12 +794,13 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
   long long cap = (long long)ctx->num_sms * 2 * 8;      // 2 resident CTAs per SM, 8 waves of work each
   int grid = (int)(blocks < cap ? blocks : cap);
   const int path = ctx->opt[AOM_OPT_WFS_PATH];
-  if (c.nfft == 64 && (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST)) {
+  const bool staged = (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST || path == AOM_WFS_TENSOR_PIPE);
+  if (c.nfft == 64 && staged) {
     rc = wfs_fast_prepare(ctx);
     if (rc) return rc;
   }
-  if (c.nfft == 64 && (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST) && ctx->fast_state == 1) {
-    rc = wfs_fast_launch(ctx, p, path == AOM_WFS_TENSOR, st);
+  if (c.nfft == 64 && staged && ctx->fast_state == 1) {
+    rc = wfs_fast_launch(ctx, p, path != AOM_WFS_TENSOR_FAST, st);
     if (rc) return rc;
   }
   else if (c.nfft == 64 && path != AOM_WFS_SIMT) {
@@ -795,7 +828,9 @@ extern "C" const char* aom_wfs_kernel(aom_ctx* ctx) {
   if (ctx->cfg.nfft != 64 || path == AOM_WFS_SIMT) return "wfs_frame_kernel";
   if (path == AOM_WFS_TENSOR_REG) return "wfs_frame_mma_kernel";
   if (wfs_fast_prepare(ctx) != AOM_OK) return "";
-  if (ctx->fast_state == 1) return "wfs_frame_tma_kernel";
+  if (ctx->fast_state == 1)
+    return (path == AOM_WFS_TENSOR_PIPE && (ctx->cfg.n_layers == 1 || ctx->cfg.n_layers == 3)) ? "wfs_frame_pipe_kernel"
+                                                                                             : "wfs_frame_tma_kernel";
   snprintf(ctx->err, sizeof(ctx->err), "staged sensor kernel not eligible: %s", ctx->fast_why);
   return "wfs_frame_mma_kernel";
 }
@@ -878,7 +913,7 @@ extern "C" int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream) {
 extern "C" int aom_set_option(aom_ctx* ctx, int option, int value) {
   if (!ctx) return AOM_ERR_INVALID;
   if (option < 0 || option >= AOM_OPT_COUNT) return fail(ctx, AOM_ERR_INVALID, "unknown option %d", option);
-  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_TENSOR_REG))
+  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_TENSOR_PIPE))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_WFS_PATH: value %d out of range", value);
   if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_SIMT))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_GEMM_PATH: value %d out of range", value);

@@ -112,30 +112,36 @@ __device__ __forceinline__ void wft_layer(const float* __restrict__ t, float fx,
   }
 }
 
-template <int NL>
+// NW warps per CTA, NST tile stages per warp (the volt buffers are always double)
+template <int NL, int NW = WFT_WARPS, int NST = 2>
 constexpr size_t wft_smem_bytes(int gw, int nvalid_smem) {
-  return (size_t)WFT_WARPS * 2 * (NL > 0 ? NL : 1) * WFT_TILE_STRIDE + WFT_WARPS * 2 * 8 +
-         8 * 32 * 16 + 12 * 32 * 16 + 256 * 4 + 2 * WFT_NG * 16 * 4 + WFT_WARPS * 2 * 32 * 4 +
+  return (size_t)NW * NST * (NL > 0 ? NL : 1) * WFT_TILE_STRIDE + NW * 2 * 8 +
+         8 * 32 * 16 + 12 * 32 * 16 + 256 * 4 + 2 * WFT_NG * 16 * 4 + NW * 2 * 32 * 4 +
          (((size_t)gw * gw * 2 + 15) & ~(size_t)15) + (size_t)nvalid_smem * 8;
 }
 
 // FULL = 1: three MMAs per product in both stages (fp32-grade); 0 drops the twiddle-lo pass of stage 2.
-template <int FULL, int NL>
-__global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const __grid_constant__ WfsTmaParams P) {
+// NW / MINB: warps per CTA and CTAs per SM the register allocation is bounded for.  NST: tile stages per warp;
+// with one stage the boxes of the next item are issued as soon as the current item has been sampled (the tiles
+// are consumed at the very start of an iteration, so they still have ~90 % of it to land) -- the smaller
+// footprint is what lets more warps share a scheduler: every warp runs latency bound, so throughput follows the
+// warp count.
+template <int FULL, int NL, int NW = WFT_WARPS, int MINB = 2, int NST = 2>
+__global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __grid_constant__ WfsTmaParams P) {
   const WfsParams& p = P.p;
   const WfsFast& f = P.f;
   extern __shared__ __align__(128) unsigned char wft_smem_raw[];
   unsigned char* sm = wft_smem_raw;
   constexpr int NLS = NL > 0 ? NL : 1;
   unsigned char* s_tiles = sm;                                             // [warp][stage][layer][WFT_TILE_STRIDE]
-  uint64_t* s_bar = (uint64_t*)(s_tiles + (size_t)WFT_WARPS * 2 * NLS * WFT_TILE_STRIDE);   // [warp][stage]
-  uint4* s_c1 = (uint4*)(s_bar + WFT_WARPS * 2);                           // [8][32]
+  uint64_t* s_bar = (uint64_t*)(s_tiles + (size_t)NW * NST * NLS * WFT_TILE_STRIDE);   // [warp][stage]
+  uint4* s_c1 = (uint4*)(s_bar + NW * 2);                                  // [8][32]
   uint4* s_c2 = s_c1 + 8 * 32;                                             // [12][32]
   float* s_half = (float*)(s_c2 + 12 * 32);                                // [256]
   float* s_fx = s_half + 256;                                              // [NG][16]
   float* s_fy = s_fx + WFT_NG * 16;                                        // [NG][16]
   float* s_vall = s_fy + WFT_NG * 16;                                      // [warp][stage][32]
-  short* s_amap = (short*)(s_vall + WFT_WARPS * 2 * 32);
+  short* s_amap = (short*)(s_vall + NW * 2 * 32);
   uint2* s_sub = (uint2*)((unsigned char*)s_amap + ((f.GW * f.GW * 2 + 15) & ~15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,13 +154,13 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
   for (int i = threadIdx.x; i < f.GW * f.GW; i += blockDim.x) s_amap[i] = f.amap[i];
   if (f.sub_in_smem)
     for (int i = threadIdx.x; i < p.nvalid; i += blockDim.x) s_sub[i] = f.sub[i];
-  if (threadIdx.x < WFT_WARPS * 2)
+  if (threadIdx.x < NW * 2)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wft_smem_u32(s_bar + threadIdx.x)) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
   const uint2* sub = f.sub_in_smem ? s_sub : f.sub;
-  unsigned char* my_tiles = s_tiles + (size_t)warp * 2 * NLS * WFT_TILE_STRIDE;
+  unsigned char* my_tiles = s_tiles + (size_t)warp * NST * NLS * WFT_TILE_STRIDE;
   const uint32_t my_tiles_u32 = wft_smem_u32(my_tiles);
   const uint32_t my_bar_u32 = wft_smem_u32(s_bar + warp * 2);
   float* s_v = s_vall + warp * 2 * 32;
@@ -176,10 +182,10 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
   uint32_t n_xy = 0, n_pm = 0, n_d = 0;      // n_d: 2 bits per layer = tile origin column & 3
   float n_v = 0.f;
   bool n_seam = false;
-  auto prefetch = [&](int pe, int pk, int stage) {
+  auto prefetch = [&](int pe, int pk, int stage, bool tiles, bool aux) {
     const uint2 sb = sub[pk];
     n_xy = sb.x;
-    if (NL > 0) {
+    if (NL > 0 && tiles) {
       if (pe != ring_e) {
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
@@ -211,15 +217,17 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
           wft_tma_load_3d(my_tiles_u32 + (stage * NL + l) * WFT_TILE_STRIDE, &P.maps[l], tc[l], tr[l], pe, bar);
       }
     }
-    n_v = 0.f;
-    if (p.use_dm && lane < 18) {
-      int idx = (lane < 16) ? (int)s_amap[(int)sb.y + (lane >> 2) * f.GW + (lane & 3)] : p.pzt_nact + lane - 16;
-      if (idx >= 0) n_v = __ldg(p.volts + (size_t)pe * p.ldv + idx);
+    if (aux) {
+      n_v = 0.f;
+      if (p.use_dm && lane < 18) {
+        int idx = (lane < 16) ? (int)s_amap[(int)sb.y + (lane >> 2) * f.GW + (lane & 3)] : p.pzt_nact + lane - 16;
+        if (idx >= 0) n_v = __ldg(p.volts + (size_t)pe * p.ldv + idx);
+      }
+      n_pm = f.pmask[(size_t)pk * 32 + lane];
     }
-    n_pm = f.pmask[(size_t)pk * 32 + lane];
   };
 
-  prefetch(e, k, 0);
+  prefetch(e, k, 0, true, true);
   s_v[lane] = n_v;
   __syncwarp();
   // De-phase the warps that share a scheduler: identical work per iteration would otherwise keep them in
@@ -229,19 +237,20 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
     if (stagger_ns && (warp & 4)) __nanosleep(stagger_ns);
   }
 
-  for (int it = 0; w < end; ++it, w += WFT_WARPS) {
+  for (int it = 0; w < end; ++it, w += NW) {
     const int s = it & 1;
+    const int ts = (NST == 2) ? s : 0;          // tile stage of the current item
     const uint32_t c_xy = n_xy, c_pm = n_pm, c_d = n_d;
     const bool c_seam = n_seam;
     const int ce = e, ck = k;
     const int x0 = (int)(c_xy & 0xffffu), y0 = (int)(c_xy >> 16);
 
     // ---- next work item ----
-    const bool has_next = (w + WFT_WARPS) < end;
+    const bool has_next = (w + NW) < end;
     if (has_next) {
-      k += WFT_WARPS;
+      k += NW;
       if (k >= p.nvalid) { k -= p.nvalid; e += 1; }
-      prefetch(e, k, s ^ 1);
+      prefetch(e, k, s ^ 1, NST == 2, true);
     }
 
     // ---- static planes of the current subaperture (L2-resident tables), issued before the wait ----
@@ -265,8 +274,8 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
     const bool dbg_nofield = f.dbg & 2, dbg_nomma = f.dbg & 1;
     if (NL > 0) {
       if (!c_seam) {
-        wft_mbar_wait(my_bar_u32 + s * 8, (phase_bits >> s) & 1u, f.err);
-        phase_bits ^= (1u << s);
+        wft_mbar_wait(my_bar_u32 + ts * 8, (phase_bits >> ts) & 1u, f.err);
+        phase_bits ^= (1u << ts);
       } else {
         // tile straddles the torus seam: fill the stage with wrapped plain loads
 #pragma unroll 1
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
           const float* scr = p.layer[l].screen + (size_t)ce * N * N;
           int c0 = x0 + p.layer[l].ix + p.layer[l].ox[ce];  c0 -= (c0 >= N) ? N : 0;  c0 -= (c0 >= N) ? N : 0;
           int r0 = y0 + p.layer[l].iy + p.layer[l].oy[ce];  r0 -= (r0 >= N) ? N : 0;  r0 -= (r0 >= N) ? N : 0;
-          float* tile = reinterpret_cast<float*>(my_tiles + (s * NL + l) * WFT_TILE_STRIDE);
+          float* tile = reinterpret_cast<float*>(my_tiles + (ts * NL + l) * WFT_TILE_STRIDE);
           for (int i = lane; i < WFT_TILE_H * WFT_TILE_H; i += 32) {
             const int r = i / WFT_TILE_H, c = i - r * WFT_TILE_H;
             int rr = r0 + r;  rr -= (rr >= N) ? N : 0;
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
         if (dbg_nofield) break;
-        const float* t = reinterpret_cast<const float*>(my_tiles + (s * NL + l) * WFT_TILE_STRIDE) + lane_off;
+        const float* t = reinterpret_cast<const float*>(my_tiles + (ts * NL + l) * WFT_TILE_STRIDE) + lane_off;
         const float fx = p.layer[l].fx, fy = p.layer[l].fy;
         switch ((c_d >> (2 * l)) & 3u) {
           case 0: wft_layer<0>(t, fx, fy, ph); break;
@@ -296,6 +305,10 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_tma_kernel(const 
           case 2: wft_layer<2>(t, fx, fy, ph); break;
           default: wft_layer<3>(t, fx, fy, ph); break;
         }
+      }
+      if (NST == 1 && has_next) {
+        __syncwarp();                          // every lane has drained the stage before lane 0 re-arms it
+        prefetch(e, k, 0, true, false);
       }
     }
 

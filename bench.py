@@ -28,7 +28,8 @@ if ROOT not in sys.path:
 # DRAM bytes per environment per launch of the sensor kernel from `ncu --set full` (dram__bytes_read.sum +
 # dram__bytes_write.sum of one launch at E = 1024, divided by 1024): profiles/r01_wfs_tma_E1024_metrics.csv,
 # profiles/r01_wfs_mma_E1024_metrics.csv.  Used for roofline.traffic (scaled to the E of this run).
-NCU_DRAM_BYTES_PER_ENV = {("40x40", "wfs_frame_tma_kernel"): (4.108122e9 + 13.919744e6) / 1024,
+NCU_DRAM_BYTES_PER_ENV = {("40x40", "wfs_frame_pipe_kernel"): (4.108122e9 + 13.919744e6) / 1024,   # same tiles / boxes
+                          ("40x40", "wfs_frame_tma_kernel"): (4.108122e9 + 13.919744e6) / 1024,
                           ("40x40", "wfs_frame_mma_kernel"): (4.062998e9 + 18.132992e6) / 1024}
 
 WORKLOADS = {
@@ -52,7 +53,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 4096 / 1024)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt", "tensor_reg"],
+    ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt", "tensor_reg", "tensor_pipe"],
                     help="Shack-Hartmann frame kernel (tensor = default product path)")
     ap.add_argument("--wfs-dbg", type=int, default=0, help=argparse.SUPPRESS)   # kernel development switches
     return ap.parse_args()

@@ -147,7 +147,9 @@ enum {
                               default; geometries the staged kernel does not cover fall back to AOM_WFS_TENSOR_REG) */
   AOM_WFS_TENSOR_FAST = 1, /* same, twiddle low parts dropped in stage 2 (slopes ~1e-5 relative) */
   AOM_WFS_SIMT = 2,        /* float32 shared-memory FFT on the FP32 pipe (cross-check path) */
-  AOM_WFS_TENSOR_REG = 3   /* tensor-pipe DFT fed by plain global loads (previous generation; cross-check path) */
+  AOM_WFS_TENSOR_REG = 3,  /* tensor-pipe DFT fed by plain global loads (generation 2; cross-check path) */
+  AOM_WFS_TENSOR_PIPE = 4  /* staged kernel software-pipelined across subapertures inside each warp (experiment: measured
+                              equal to the default; 1- and 3-layer atmospheres, otherwise the default kernel runs) */
 };
 
 enum {
@@ -185,7 +187,7 @@ int aom_set_layer(aom_ctx* ctx, int layer, float deltax, float deltay, float amp
 int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* stream);
 
 /* Name of the kernel the next aom_comp_wfs_image will launch under the current AOM_OPT_WFS_PATH
- * ("wfs_frame_tma_kernel", "wfs_frame_mma_kernel" or "wfs_frame_kernel"); when the staged kernel is not
+ * ("wfs_frame_pipe_kernel", "wfs_frame_tma_kernel", "wfs_frame_mma_kernel" or "wfs_frame_kernel"); when the staged kernel is not
  * eligible for the geometry, aom_last_error() says why. */
 const char* aom_wfs_kernel(aom_ctx* ctx);
 

@@ -170,10 +170,12 @@ def test_wfs_paths_agree(sim10, static10, torch):
     sim10.set_dm_volts(torch.as_tensor(volts, device="cuda"))
     out = {}
     try:
-        for path in ("simt", "tensor", "tensor_fast", "tensor_reg"):
+        for path in ("simt", "tensor", "tensor_fast", "tensor_reg", "tensor_pipe"):
             sim10.set_wfs_path(path)
             if path in ("tensor", "tensor_fast"):
                 assert sim10.wfs_kernel() == "wfs_frame_tma_kernel", sim10.lib.aom_last_error(sim10._ctx)
+            if path == "tensor_pipe":
+                assert sim10.wfs_kernel() == "wfs_frame_pipe_kernel", sim10.lib.aom_last_error(sim10._ctx)
             sim10.comp_wfs_image(keep_image=True, noise=-1.0)
             sim10.do_centroids()
             out[path] = (sim10.rows("SLOPES", static10.nslopes).cpu().numpy().copy(),
@@ -183,12 +185,13 @@ def test_wfs_paths_agree(sim10, static10, torch):
     assert relerr(out["tensor"][1], out["simt"][1]) < 2e-5
     assert relerr(out["tensor"][0], out["simt"][0]) < 2e-5
     assert relerr(out["tensor_fast"][0], out["simt"][0]) < 5e-4
-    assert relerr(out["tensor_reg"][1], out["simt"][1]) < 2e-5
-    assert relerr(out["tensor_reg"][0], out["simt"][0]) < 2e-5
+    for path in ("tensor_reg", "tensor_pipe"):
+        assert relerr(out[path][1], out["simt"][1]) < 2e-5
+        assert relerr(out[path][0], out["simt"][0]) < 2e-5
 
 
 def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
-    """The TMA-staged kernel against the float32 FFT kernel while the torus seam sweeps through the pupil
+    """The TMA-staged kernels against the float32 FFT kernel while the torus seam sweeps through the pupil
     (tiles that straddle it take the plain-load fill), with and without the image / normalisation path."""
     seeds = np.array([31, 32, 33, 34], dtype=np.int64)
     sim10.reset(seeds)
@@ -201,13 +204,14 @@ def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
             for _ in range(3):
                 sim10.move_atmos()
             res = {}
-            for path in ("simt", "tensor"):
+            for path in ("simt", "tensor", "tensor_pipe"):
                 sim10.set_wfs_path(path)
                 sim10.comp_wfs_image(keep_image=(it % 2 == 0), noise=-1.0)
                 sim10.do_centroids()
                 res[path] = sim10.rows("SLOPES", n).cpu().numpy().copy()
             sim10.check_device()
             assert relerr(res["tensor"], res["simt"]) < 2e-5, it
+            assert relerr(res["tensor_pipe"], res["simt"]) < 2e-5, it
     finally:
         sim10.set_wfs_path("tensor")
 
@@ -373,7 +377,7 @@ def test_40x40_kernel_generations_agree(system40, torch):
             for _ in range(1 + 40 * it):
                 sim.move_atmos()
             res = {}
-            for path in ("simt", "tensor", "tensor_reg"):
+            for path in ("simt", "tensor", "tensor_reg", "tensor_pipe"):
                 sim.set_wfs_path(path)
                 sim.comp_wfs_image(noise=-1.0)
                 sim.do_centroids()
@@ -382,6 +386,7 @@ def test_40x40_kernel_generations_agree(system40, torch):
             assert np.abs(res["simt"]).max() > 1e-3
             assert relerr(res["tensor"], res["simt"]) < 2e-5, it
             assert relerr(res["tensor_reg"], res["simt"]) < 2e-5, it
+            assert relerr(res["tensor_pipe"], res["simt"]) < 2e-5, it
     finally:
         sim.set_wfs_path("tensor")
 
