@@ -8,26 +8,33 @@ __device__ __forceinline__ void mma(float (&c)[4], uint32_t a0, uint32_t a1, uin
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__global__ void k(int w_mma, int iters, float* out, long long* cyc) {
+template <int ilp>
+__global__ void k(int w_mma, int iters, int distinct, float* out, long long* cyc) {
   const int warp = threadIdx.x >> 5;
   float acc[8][4];
   for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float f[16];
   for (int i = 0; i < 16; ++i) f[i] = threadIdx.x * 0.001f + i;
   uint32_t a = 0x3c003c00u + threadIdx.x, b = 0x38003800u;
+  uint32_t av[16], bv[8];
+  for (int i = 0; i < 16; ++i) av[i] = a + 7 * i + (distinct ? i * threadIdx.x : 0);
+  for (int i = 0; i < 8; ++i) bv[i] = b + 3 * i + (distinct ? i * threadIdx.x : 0);
   __syncthreads();
   long long t0 = clock64();
   if (warp < w_mma) {
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mma(acc[i], a, a, a, a, b, b);
+      for (int i = 0; i < 8; ++i) {
+        if (distinct) mma(acc[i], av[(4 * i) & 15], av[(4 * i + 1) & 15], av[(4 * i + 2) & 15], av[(4 * i + 3) & 15], bv[(2 * i) & 7], bv[(2 * i + 1) & 7]);
+        else mma(acc[i], a, a, a, a, b, b);
+      }
     }
   } else {
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = fmaf(f[i], 1.0001f, 0.5f);
+        for (int i = 0; i < 16; ++i) f[i % ilp] = fmaf(f[i % ilp], 1.0001f, 0.5f);
     }
   }
   long long t1 = clock64();
@@ -44,9 +51,13 @@ int main() {
   const int iters = 2000;
   // configurations: (warps per CTA, of which MMA warps); warp w runs on scheduler w % 4
   int cfg[][2] = {{4, 4}, {8, 8}, {16, 16}, {4, 0}, {8, 0}, {16, 0}, {8, 4}, {16, 4}, {16, 8}, {12, 4}, {16, 12}};
+  for (int mode = 0; mode < 4; ++mode)
   for (auto& c : cfg) {
     const int W = c[0], wm = c[1];
-    k<<<148, W * 32>>>(wm, iters, out, cyc);
+    const int distinct = mode & 1, lowilp = mode >> 1;
+    if (c == cfg[0]) printf("---- distinct operand registers: %d, FFMA chains per warp: %d\n", distinct, lowilp ? 2 : 16);
+    if (lowilp) k<2><<<148, W * 32>>>(wm, iters, distinct, out, cyc);
+    else k<16><<<148, W * 32>>>(wm, iters, distinct, out, cyc);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, cyc, W * 8, cudaMemcpyDeviceToHost);
     double cm = 0, cf = 0;

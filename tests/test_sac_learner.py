@@ -175,3 +175,50 @@ def test_gradient_allreduce_gloo_world2(tmp_path):
         assert torch.equal(r0["critic"][k], r1["critic"][k])
         assert torch.allclose(r0["critic"][k], L.critic_state_dict(1)[k], rtol=1e-4, atol=1e-6), k
     assert torch.allclose(r0["la"], L.log_alpha.detach(), atol=1e-6)
+
+
+NCCL_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+from ao_marl_b200.rl.sac import BatchedSAC
+from test_sac_learner import SAC, _batch
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+L = BatchedSAC([9, 5], [4, 2], SAC, device="cuda", seed=7, dist=dist, memory_size=8)
+ref = BatchedSAC([9, 5], [4, 2], SAC, device="cuda", seed=7, memory_size=8)
+for it in range(3):
+    cpu = BatchedSAC([9, 5], [4, 2], SAC, device="cpu", seed=7, memory_size=8) if it == 0 else cpu
+    (s, a, r, s2, m), (n0, n1) = _batch(cpu, 16, 50 + it)
+    full = [x.cuda() for x in (s, a, r, s2, m)]
+    noise = [x.cuda() for x in (n0, n1)]
+    h = slice(0, 8) if rank == 0 else slice(8, 16)
+    L.update(tuple(x[:, h] for x in full), tuple(x[:, h] for x in noise))
+    ref.update(tuple(full), tuple(noise))
+flat = torch.cat([p.detach().reshape(-1) for p in L.actor_params + L.critic_params] + [L.log_alpha.detach()])
+gathered = [torch.empty_like(flat) for _ in range(2)]
+dist.all_gather(gathered, flat)
+flat_ref = torch.cat([p.detach().reshape(-1) for p in ref.actor_params + ref.critic_params] + [ref.log_alpha.detach()])
+ok_same = bool(torch.equal(gathered[0], gathered[1]))
+err = float((flat - flat_ref).abs().max() / flat_ref.abs().max())
+if rank == 0:
+    print("NCCL_SAC same=%%s err=%%.3e" %% (ok_same, err))
+    assert ok_same and err < 2e-4, (ok_same, err)
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.gpu
+def test_gradient_allreduce_nccl_two_gpus(tmp_path):
+    """Same check as the gloo test on two real GPUs over NCCL (skipped on a single-GPU box)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    script = tmp_path / "nccl_worker.py"
+    script.write_text(NCCL_WORKER % dict(root=ROOT))
+    port = 29500 + os.getpid() % 400
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "NCCL_SAC same=True" in r.stdout
