@@ -669,7 +669,7 @@ static int wfs_fast_prepare(aom_ctx* ctx) {
   return AOM_OK;
 }
 
-template <int FULL, int NL, int NW = WFT_WARPS, int MINB = 2, int NST = 2>
+template <int FULL, int NL, int NW = WFT_WARPS, int MINB = 2, int NST = 2, int TOKEN = 0>
 static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) {
   const long long total = (long long)p.E * p.nvalid;
   // contiguous ranges of work items per CTA: about 8 waves of MINB CTAs per SM, at least 16 items per warp
@@ -688,11 +688,11 @@ static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) 
   const size_t smem = wft_smem_bytes<NL, NW, NST>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(wfs_frame_tma_kernel<FULL, NL, NW, MINB, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wfs_frame_tma_kernel<FULL, NL, NW, MINB, NST, TOKEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_tma_kernel): %s", cudaGetErrorString(e));
     configured = smem;
   }
-  wfs_frame_tma_kernel<FULL, NL, NW, MINB, NST><<<(unsigned)grid, NW * 32, smem, st>>>(P);
+  wfs_frame_tma_kernel<FULL, NL, NW, MINB, NST, TOKEN><<<(unsigned)grid, NW * 32, smem, st>>>(P);
   return AOM_OK;
 }
 

@@ -126,8 +126,13 @@ constexpr size_t wft_smem_bytes(int gw, int nvalid_smem) {
 // are consumed at the very start of an iteration, so they still have ~90 % of it to land) -- the smaller
 // footprint is what lets more warps share a scheduler: every warp runs latency bound, so throughput follows the
 // warp count.
-template <int FULL, int NL, int NW = WFT_WARPS, int MINB = 2, int NST = 2>
+// TOKEN: experiment -- the warps that share a scheduler (warp % 4) take turns on the tensor pipe (a warp runs its
+// two MMA stages only while it holds the scheduler's token), to test whether identical warps convoy on the pipe.
+// Measured 13.5 ms against 10.8 ms without (16 warps, one CTA per SM): serialising the MMA phases exposes their
+// latency-bound critical path; kept off.
+template <int FULL, int NL, int NW = WFT_WARPS, int MINB = 2, int NST = 2, int TOKEN = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __grid_constant__ WfsTmaParams P) {
+  __shared__ unsigned int s_tok[4];
   const WfsParams& p = P.p;
   const WfsFast& f = P.f;
   extern __shared__ __align__(128) unsigned char wft_smem_raw[];
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
   for (int i = threadIdx.x; i < f.GW * f.GW; i += blockDim.x) s_amap[i] = f.amap[i];
   if (f.sub_in_smem)
     for (int i = threadIdx.x; i < p.nvalid; i += blockDim.x) s_sub[i] = f.sub[i];
+  if (threadIdx.x < 4) s_tok[threadIdx.x] = 0u;
   if (threadIdx.x < NW * 2)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wft_smem_u32(s_bar + threadIdx.x)) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -392,6 +398,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
         for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int c = 0; c < 4; ++c) T[a][mt][j][c] = 0.f;
+    if (TOKEN) {
+      if (lane == 0)
+        while (atomicCAS(&s_tok[warp & 3], 0u, 1u) != 0u) __nanosleep(40);
+      __syncwarp();
+    }
     if (!dbg_nomma) {
       uint32_t nxi_h[2][2], nxi_l[2][2];
 #pragma unroll
@@ -483,6 +494,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
         c = fmaf(yi[u][3], yi[u][3], c);
         pix[u][b] = a + c;
       }
+    }
+
+    if (TOKEN) {
+      __syncwarp();
+      if (lane == 0) atomicExch(&s_tok[warp & 3], 0u);
     }
 
     // ---- flux normalisation, noise, centre of gravity ----
