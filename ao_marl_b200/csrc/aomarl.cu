@@ -15,6 +15,7 @@
 #include "wfs_mma.cuh"
 #include "wfs_tma.cuh"
 #include "wfs_pipe.cuh"
+#include "wfs_tc.cuh"
 
 static char g_create_error[512] = "";
 
@@ -59,7 +60,7 @@ struct aom_ctx {
   int fast_state;            // 0 = not prepared, 1 = eligible, -1 = not eligible (fast_why says why)
   char fast_why[160];
   WfsFast fast;
-  void* fast_dev[6];
+  void* fast_dev[7];
   CUtensorMap fast_maps[WFT_MAX_LAYERS];
   size_t fast_smem;
 };
@@ -129,6 +130,7 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     if (w && !strcmp(w, "tensor_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_FAST;
     if (w && !strcmp(w, "tensor_reg")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_REG;
     if (w && !strcmp(w, "tensor_pipe")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_PIPE;
+    if (w && !strcmp(w, "tcgen05")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TCGEN05;
   }
   *out = ctx;   // returned even on failure so that aom_last_error / aom_destroy work
   CU(cudaGetDevice(&ctx->device));
@@ -554,7 +556,8 @@ static int wfs_fast_prepare(aom_ctx* ctx) {
   float h_fxy[2 * WFT_NG * 16];
   uint4* h_c1 = (uint4*)malloc(8 * 32 * sizeof(uint4));
   uint4* h_c2 = (uint4*)malloc(12 * 32 * sizeof(uint4));
-  bool ok = h_sub && h_pm && h_amap && h_c1 && h_c2;
+  unsigned short* h_b2 = (unsigned short*)calloc(2 * WTC_B_BYTES / 2, sizeof(unsigned short));
+  bool ok = h_sub && h_pm && h_amap && h_c1 && h_c2 && h_b2;
   if (ok) {
     for (int i = 0; i < GW * GW; ++i) h_amap[i] = -1;
     if (dm)
@@ -623,15 +626,30 @@ static int wfs_fast_prepare(aom_ctx* ctx) {
         h_c2[(b * 3 + 2) * 32 + lane] = make_uint4(nh[0], nh[1], nl[0], nl[1]);
       }
   }
+  if (ok) {
+    // stage-2 B tiles of the tcgen05 kernel (wfs_tc.cuh): row n = 2 iota + {Yr, Yi}, K = {Tr(y), Ti(y)},
+    // UMMA canonical K-major no-swizzle layout (8-row x 16-byte core matrices, LBO 128 B, SBO 512 B)
+    for (int n = 0; n < 64; ++n)
+      for (int kk = 0; kk < 32; ++kk) {
+        const int iota = n >> 1, pout = n & 1, pin = kk >> 4, y = kk & 15;
+        const double wr = wft_w(y, iota, 0), wi = wft_w(y, iota, 1);
+        const double v = pout == 0 ? (pin == 0 ? wr : -wi) : (pin == 0 ? wi : wr);
+        const __half hi = __float2half_rn((float)v);
+        const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+        const size_t off = (size_t)(n >> 3) * 512 + (size_t)(kk >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(kk & 7) * 2;
+        memcpy((unsigned char*)h_b2 + off, &hi, 2);
+        memcpy((unsigned char*)h_b2 + WTC_B_BYTES + off, &lo, 2);
+      }
+  }
   cudaError_t ce = cudaSuccess;
-  const void* srcs[6] = {h_sub, h_amap, h_pm, h_c1, h_c2, h_fxy};
-  const size_t sizes[6] = {(size_t)nv * sizeof(uint2), (size_t)GW * GW * sizeof(short), (size_t)nv * 32,
-                           8 * 32 * sizeof(uint4), 12 * 32 * sizeof(uint4), sizeof(h_fxy)};
-  for (int i = 0; i < 6 && ok && ce == cudaSuccess; ++i) {
+  const void* srcs[7] = {h_sub, h_amap, h_pm, h_c1, h_c2, h_fxy, h_b2};
+  const size_t sizes[7] = {(size_t)nv * sizeof(uint2), (size_t)GW * GW * sizeof(short), (size_t)nv * 32,
+                           8 * 32 * sizeof(uint4), 12 * 32 * sizeof(uint4), sizeof(h_fxy), (size_t)2 * WTC_B_BYTES};
+  for (int i = 0; i < 7 && ok && ce == cudaSuccess; ++i) {
     ce = cudaMalloc(&ctx->fast_dev[i], sizes[i]);
     if (ce == cudaSuccess) ce = cudaMemcpy(ctx->fast_dev[i], srcs[i], sizes[i], cudaMemcpyHostToDevice);
   }
-  free(h_sub); free(h_pm); free(h_amap); free(h_c1); free(h_c2);
+  free(h_sub); free(h_pm); free(h_amap); free(h_c1); free(h_c2); free(h_b2);
   if (ce != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "wfs_fast_prepare: %s", cudaGetErrorString(ce));
   if (!ok) FAST_NO("derived tables out of range");
 
@@ -696,6 +714,33 @@ static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) 
   return AOM_OK;
 }
 
+template <int NL>
+static int wfs_tc_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) {
+  const long long total = (long long)p.E * p.nvalid;
+  // one CTA of 16 warps per SM, about 8 waves, contiguous ranges of work items, at least 8 items per warp
+  long long grid = (long long)ctx->num_sms * 8;
+  long long ipc = (total + grid - 1) / grid;
+  if (ipc < 8 * WTC_WARPS) ipc = 8 * WTC_WARPS;
+  ipc = (ipc + WTC_WARPS - 1) / WTC_WARPS * WTC_WARPS;
+  grid = (total + ipc - 1) / ipc;
+  WfsTcParams P;
+  memset(&P, 0, sizeof(P));
+  P.p = p;
+  P.f = ctx->fast;
+  P.f.items_per_cta = ipc;
+  P.b2 = (const uint4*)ctx->fast_dev[6];
+  for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
+  const size_t smem = wtc_smem_bytes<NL>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(wfs_frame_tc_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_tc_kernel): %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  wfs_frame_tc_kernel<NL><<<(unsigned)grid, WTC_WARPS * 32, smem, st>>>(P);
+  return AOM_OK;
+}
+
 template <int FULL, int NL, int DM>
 static int wfs_pipe_launch_t(aom_ctx* ctx, const WfsParams& p, int grid, long long ipc, cudaStream_t st) {
   WfsTmaParams P;
@@ -716,6 +761,13 @@ static int wfs_pipe_launch_t(aom_ctx* ctx, const WfsParams& p, int grid, long lo
 }
 
 static int wfs_fast_launch(aom_ctx* ctx, const WfsParams& p, int full, cudaStream_t st) {
+  if (ctx->opt[AOM_OPT_WFS_PATH] == AOM_WFS_TCGEN05 && full) {
+    switch (p.n_layers) {
+      case 0: return wfs_tc_launch_t<0>(ctx, p, st);
+      case 1: return wfs_tc_launch_t<1>(ctx, p, st);
+      case 3: return wfs_tc_launch_t<3>(ctx, p, st);
+    }
+  }
   if (ctx->opt[AOM_OPT_WFS_PATH] == AOM_WFS_TENSOR_PIPE && full && (p.n_layers == 1 || p.n_layers == 3)) {
     // software-pipelined variant (wfs_pipe.cuh): measured equal to the staged kernel, kept as an experiment
     const long long total = (long long)p.E * p.nvalid;
@@ -794,7 +846,8 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
   long long cap = (long long)ctx->num_sms * 2 * 8;      // 2 resident CTAs per SM, 8 waves of work each
   int grid = (int)(blocks < cap ? blocks : cap);
   const int path = ctx->opt[AOM_OPT_WFS_PATH];
-  const bool staged = (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST || path == AOM_WFS_TENSOR_PIPE);
+  const bool staged = (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST || path == AOM_WFS_TENSOR_PIPE ||
+                       path == AOM_WFS_TCGEN05);
   if (c.nfft == 64 && staged) {
     rc = wfs_fast_prepare(ctx);
     if (rc) return rc;
@@ -828,6 +881,9 @@ extern "C" const char* aom_wfs_kernel(aom_ctx* ctx) {
   if (ctx->cfg.nfft != 64 || path == AOM_WFS_SIMT) return "wfs_frame_kernel";
   if (path == AOM_WFS_TENSOR_REG) return "wfs_frame_mma_kernel";
   if (wfs_fast_prepare(ctx) != AOM_OK) return "";
+  if (ctx->fast_state == 1 && path == AOM_WFS_TCGEN05 &&
+      (ctx->cfg.n_layers == 0 || ctx->cfg.n_layers == 1 || ctx->cfg.n_layers == 3))
+    return "wfs_frame_tc_kernel";
   if (ctx->fast_state == 1)
     return (path == AOM_WFS_TENSOR_PIPE && (ctx->cfg.n_layers == 1 || ctx->cfg.n_layers == 3)) ? "wfs_frame_pipe_kernel"
                                                                                              : "wfs_frame_tma_kernel";
@@ -913,7 +969,7 @@ extern "C" int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream) {
 extern "C" int aom_set_option(aom_ctx* ctx, int option, int value) {
   if (!ctx) return AOM_ERR_INVALID;
   if (option < 0 || option >= AOM_OPT_COUNT) return fail(ctx, AOM_ERR_INVALID, "unknown option %d", option);
-  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_TENSOR_PIPE))
+  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_TCGEN05))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_WFS_PATH: value %d out of range", value);
   if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_SIMT))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_GEMM_PATH: value %d out of range", value);

@@ -262,7 +262,7 @@ class Simulator:
         self.lib.aom_device_count_launches(self._ctx, ctypes.byref(n))
         return n.value
 
-    WFS_PATHS = {"tensor": 0, "tensor_fast": 1, "simt": 2, "tensor_reg": 3, "tensor_pipe": 4}
+    WFS_PATHS = {"tensor": 0, "tensor_fast": 1, "simt": 2, "tensor_reg": 3, "tensor_pipe": 4, "tcgen05": 5}
 
     def set_wfs_path(self, name):
         """Select the Shack-Hartmann frame kernel: 'tensor' (default), 'tensor_fast', 'tensor_reg' or 'simt'."""

@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 4096 / 1024)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt", "tensor_reg", "tensor_pipe"],
+    ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt", "tensor_reg", "tensor_pipe", "tcgen05"],
                     help="Shack-Hartmann frame kernel (tensor = default product path)")
     ap.add_argument("--wfs-dbg", type=int, default=0, help=argparse.SUPPRESS)   # kernel development switches
     return ap.parse_args()

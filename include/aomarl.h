@@ -148,8 +148,9 @@ enum {
   AOM_WFS_TENSOR_FAST = 1, /* same, twiddle low parts dropped in stage 2 (slopes ~1e-5 relative) */
   AOM_WFS_SIMT = 2,        /* float32 shared-memory FFT on the FP32 pipe (cross-check path) */
   AOM_WFS_TENSOR_REG = 3,  /* tensor-pipe DFT fed by plain global loads (generation 2; cross-check path) */
-  AOM_WFS_TENSOR_PIPE = 4  /* staged kernel software-pipelined across subapertures inside each warp (experiment: measured
+  AOM_WFS_TENSOR_PIPE = 4, /* staged kernel software-pipelined across subapertures inside each warp (experiment: measured
                               equal to the default; 1- and 3-layer atmospheres, otherwise the default kernel runs) */
+  AOM_WFS_TCGEN05 = 5      /* staged kernel with stage 2 of the DFT on tcgen05 / TMEM (0-, 1- and 3-layer atmospheres) */
 };
 
 enum {

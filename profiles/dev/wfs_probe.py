@@ -15,14 +15,16 @@ r = np.random.default_rng(0)
 sim.set_dm_volts(torch.as_tensor((r.standard_normal((4, t.nactu)) * 10).astype(np.float32), device="cuda"))
 print("kernel:", sim.wfs_kernel(), sim.lib.aom_last_error(sim._ctx))
 out = {}
-for path in ("simt", "tensor"):
+paths = ("simt",) + tuple(sys.argv[2:] or ["tensor"])
+for path in paths:
     sim.set_wfs_path(path)
     sim.comp_wfs_image(atmos=(mode == "atmos"), dms=True, keep_image=True, noise=-1.0)
     sim.do_centroids()
     torch.cuda.synchronize()
     out[path] = (sim.rows("SLOPES", t.nslopes).cpu().numpy().copy(), sim.buffer("BINCUBE").cpu().numpy().copy())
-    print(path, "ok", float(np.abs(out[path][0]).max()))
+    print(path, sim.wfs_kernel(), "ok", float(np.abs(out[path][0]).max()))
 sim.check_device()
-for i in (0, 1):
-    a, b = out["tensor"][i], out["simt"][i]
-    print("relerr", i, float(np.abs(a - b).max() / np.abs(b).max()))
+for path in paths[1:]:
+    for i in (0, 1):
+        a, b = out[path][i], out["simt"][i]
+        print(path, "relerr", "slopes" if i == 0 else "cube", float(np.abs(a - b).max() / np.abs(b).max()))

@@ -170,12 +170,14 @@ def test_wfs_paths_agree(sim10, static10, torch):
     sim10.set_dm_volts(torch.as_tensor(volts, device="cuda"))
     out = {}
     try:
-        for path in ("simt", "tensor", "tensor_fast", "tensor_reg", "tensor_pipe"):
+        for path in ("simt", "tensor", "tensor_fast", "tensor_reg", "tensor_pipe", "tcgen05"):
             sim10.set_wfs_path(path)
             if path in ("tensor", "tensor_fast"):
                 assert sim10.wfs_kernel() == "wfs_frame_tma_kernel", sim10.lib.aom_last_error(sim10._ctx)
             if path == "tensor_pipe":
                 assert sim10.wfs_kernel() == "wfs_frame_pipe_kernel", sim10.lib.aom_last_error(sim10._ctx)
+            if path == "tcgen05":
+                assert sim10.wfs_kernel() == "wfs_frame_tc_kernel", sim10.lib.aom_last_error(sim10._ctx)
             sim10.comp_wfs_image(keep_image=True, noise=-1.0)
             sim10.do_centroids()
             out[path] = (sim10.rows("SLOPES", static10.nslopes).cpu().numpy().copy(),
@@ -185,7 +187,7 @@ def test_wfs_paths_agree(sim10, static10, torch):
     assert relerr(out["tensor"][1], out["simt"][1]) < 2e-5
     assert relerr(out["tensor"][0], out["simt"][0]) < 2e-5
     assert relerr(out["tensor_fast"][0], out["simt"][0]) < 5e-4
-    for path in ("tensor_reg", "tensor_pipe"):
+    for path in ("tensor_reg", "tensor_pipe", "tcgen05"):
         assert relerr(out[path][1], out["simt"][1]) < 2e-5
         assert relerr(out[path][0], out["simt"][0]) < 2e-5
 
@@ -204,7 +206,7 @@ def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
             for _ in range(3):
                 sim10.move_atmos()
             res = {}
-            for path in ("simt", "tensor", "tensor_pipe"):
+            for path in ("simt", "tensor", "tensor_pipe", "tcgen05"):
                 sim10.set_wfs_path(path)
                 sim10.comp_wfs_image(keep_image=(it % 2 == 0), noise=-1.0)
                 sim10.do_centroids()
@@ -212,6 +214,7 @@ def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
             sim10.check_device()
             assert relerr(res["tensor"], res["simt"]) < 2e-5, it
             assert relerr(res["tensor_pipe"], res["simt"]) < 2e-5, it
+            assert relerr(res["tcgen05"], res["simt"]) < 2e-5, it
     finally:
         sim10.set_wfs_path("tensor")
 
@@ -377,7 +380,7 @@ def test_40x40_kernel_generations_agree(system40, torch):
             for _ in range(1 + 40 * it):
                 sim.move_atmos()
             res = {}
-            for path in ("simt", "tensor", "tensor_reg", "tensor_pipe"):
+            for path in ("simt", "tensor", "tensor_reg", "tensor_pipe", "tcgen05"):
                 sim.set_wfs_path(path)
                 sim.comp_wfs_image(noise=-1.0)
                 sim.do_centroids()
@@ -387,6 +390,7 @@ def test_40x40_kernel_generations_agree(system40, torch):
             assert relerr(res["tensor"], res["simt"]) < 2e-5, it
             assert relerr(res["tensor_reg"], res["simt"]) < 2e-5, it
             assert relerr(res["tensor_pipe"], res["simt"]) < 2e-5, it
+            assert relerr(res["tcgen05"], res["simt"]) < 2e-5, it
     finally:
         sim.set_wfs_path("tensor")
 
