@@ -701,7 +701,6 @@ static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) 
   P.p = p;
   P.f = ctx->fast;
   P.f.items_per_cta = ipc;
-  { const char* d = getenv("AOM_WFS_DBG"); P.f.dbg = d ? atoi(d) : 0; }
   for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
   const size_t smem = wft_smem_bytes<NL, NW, NST>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
   static size_t configured = 0;

@@ -51,7 +51,7 @@ struct WfsFast {
   int GW;                    // side of the padded actuator map
   int sub_in_smem;           // stage the subaperture table in shared memory
   int* err;                  // device error word (bounded waits)
-  int dbg;                   // development switches (AOM_WFS_DBG): 1 = skip the MMAs, 2 = skip the field arithmetic
+  int dbg;                   // unused (development switches of round 1)
   long long items_per_cta;
 };
 
@@ -181,8 +181,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
 
   int e = (int)(w / p.nvalid), k = (int)(w % p.nvalid);
   int ring_e = -1;
-  int rx[NLS], ry[NLS];                       // x0-independent part of the tile origin: ix + ox[e], iy + oy[e]
+  int rx[NLS], ry[NLS];                       // x0-independent part of the tile origin: (ix + ox[e]) mod N, (iy + oy[e]) mod N
   uint32_t phase_bits = 0;
+  const int amap_lane = (lane >> 2) * f.GW + (lane & 3);
+  const int tt_lane = (2 * g + p.tt_off) * p.tt_dim + 4 * q + p.tt_off;      // this lane's pixel (2g, 4q) in the tip-tilt planes
+  const float* const tt_plane1 = p.tt_planes + (size_t)p.tt_dim * p.tt_dim;
 
   // ---- prefetch of one work item into `stage`: TMA boxes, neighbourhood volts, pupil byte ----
   uint32_t n_xy = 0, n_pm = 0, n_d = 0;      // n_d: 2 bits per layer = tile origin column & 3
@@ -195,8 +198,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
       if (pe != ring_e) {
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
-          rx[l] = p.layer[l].ix + p.layer[l].ox[pe];
-          ry[l] = p.layer[l].iy + p.layer[l].oy[pe];
+          const int N = p.layer[l].N;
+          int a = p.layer[l].ix + p.layer[l].ox[pe];  a -= (a >= N) ? N : 0;
+          int b = p.layer[l].iy + p.layer[l].oy[pe];  b -= (b >= N) ? N : 0;
+          rx[l] = a; ry[l] = b;
         }
         ring_e = pe;
       }
@@ -207,8 +212,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
         const int N = p.layer[l].N;
-        int c = x0 + rx[l];  c -= (c >= N) ? N : 0;  c -= (c >= N) ? N : 0;
-        int r = y0 + ry[l];  r -= (r >= N) ? N : 0;  r -= (r >= N) ? N : 0;
+        int c = x0 + rx[l];  c -= (c >= N) ? N : 0;
+        int r = y0 + ry[l];  r -= (r >= N) ? N : 0;
         tc[l] = c & ~3; tr[l] = r;
         dbits |= (uint32_t)(c & 3) << (2 * l);
         seam |= (c + WFT_TILE_H > N) | (r + WFT_TILE_H > N);
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
     if (aux) {
       n_v = 0.f;
       if (p.use_dm && lane < 18) {
-        int idx = (lane < 16) ? (int)s_amap[(int)sb.y + (lane >> 2) * f.GW + (lane & 3)] : p.pzt_nact + lane - 16;
+        int idx = (lane < 16) ? (int)s_amap[(int)sb.y + amap_lane] : p.pzt_nact + lane - 16;
         if (idx >= 0) n_v = __ldg(p.volts + (size_t)pe * p.ldv + idx);
       }
       n_pm = f.pmask[(size_t)pk * 32 + lane];
@@ -236,13 +241,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
   prefetch(e, k, 0, true, true);
   s_v[lane] = n_v;
   __syncwarp();
-  // De-phase the warps that share a scheduler: identical work per iteration would otherwise keep them in
-  // lock step, all in the field arithmetic or all queueing on the tensor pipe at the same time.
-  {
-    const unsigned stagger_ns = (unsigned)(f.dbg >> 4);
-    if (stagger_ns && (warp & 4)) __nanosleep(stagger_ns);
-  }
-
   for (int it = 0; w < end; ++it, w += NW) {
     const int s = it & 1;
     const int ts = (NST == 2) ? s : 0;          // tile stage of the current item
@@ -262,12 +260,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
     // ---- static planes of the current subaperture (L2-resident tables), issued before the wait ----
     float4 tta[2], ttb[2];
     if (p.use_dm) {
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const size_t to = (size_t)(y0 + 2 * g + r + p.tt_off) * p.tt_dim + (x0 + 4 * q + p.tt_off);
-        tta[r] = __ldg(reinterpret_cast<const float4*>(p.tt_planes + to));
-        ttb[r] = __ldg(reinterpret_cast<const float4*>(p.tt_planes + (size_t)p.tt_dim * p.tt_dim + to));
-      }
+      const int to = y0 * p.tt_dim + x0 + tt_lane;
+      tta[0] = __ldg(reinterpret_cast<const float4*>(p.tt_planes + to));
+      tta[1] = __ldg(reinterpret_cast<const float4*>(p.tt_planes + to + p.tt_dim));
+      ttb[0] = __ldg(reinterpret_cast<const float4*>(tt_plane1 + to));
+      ttb[1] = __ldg(reinterpret_cast<const float4*>(tt_plane1 + to + p.tt_dim));
     }
 
     float ph[2][4];
@@ -277,7 +274,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
       for (int c = 0; c < 4; ++c) ph[r][c] = 0.f;
 
     // ---- atmosphere: bilinear sample of the staged tiles ----
-    const bool dbg_nofield = f.dbg & 2, dbg_nomma = f.dbg & 1;
     if (NL > 0) {
       if (!c_seam) {
         wft_mbar_wait(my_bar_u32 + ts * 8, (phase_bits >> ts) & 1u, f.err);
@@ -302,7 +298,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
       }
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
-        if (dbg_nofield) break;
         const float* t = reinterpret_cast<const float*>(my_tiles + (ts * NL + l) * WFT_TILE_STRIDE) + lane_off;
         const float fx = p.layer[l].fx, fy = p.layer[l].fy;
         switch ((c_d >> (2 * l)) & 3u) {
@@ -319,7 +314,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
     }
 
     // ---- mirrors: separable stamps of the 4 x 4 lattice neighbourhood + two tip-tilt planes ----
-    if (p.use_dm && !dbg_nofield) {
+    if (p.use_dm) {
       const float* V = s_v + s * 32;
       float u[2][WFT_NG];
 #pragma unroll
@@ -361,12 +356,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
 
     // ---- complex field -> fp16 hi / lo B fragments of stage 1 (row 2g + j feeds n-tile j) ----
     uint32_t xr_h[2][2], xr_l[2][2], xi_h[2][2], xi_l[2][2];
-    if (dbg_nofield) {
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) { xr_h[r][c] = 0x3c003c00u ^ c_pm; xr_l[r][c] = c_xy; xi_h[r][c] = c_pm; xi_l[r][c] = c_xy >> 3; }
-    } else
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const float4 hf = *reinterpret_cast<const float4*>(s_half + (2 * g + r) * 16 + 4 * q);
@@ -403,7 +392,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
         while (atomicCAS(&s_tok[warp & 3], 0u, 1u) != 0u) __nanosleep(40);
       __syncwarp();
     }
-    if (!dbg_nomma) {
+    {
       uint32_t nxi_h[2][2], nxi_l[2][2];
 #pragma unroll
       for (int j = 0; j < 2; ++j)
@@ -431,8 +420,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
       WFT_S1(wr_h, wi_h, xr_l, xi_l, nxi_l)
       WFT_S1(wr_l, wi_l, xr_h, xi_h, nxi_h)
 #undef WFT_S1
-    } else {
-      T[0][0][0][0] = __uint_as_float(xr_h[0][0]); T[1][1][1][1] = __uint_as_float(xi_l[1][1]);
     }
 
     // ---- stage-2 A fragments: a0 = tile(j=0) c0,c1  a1 = tile(j=0) c2,c3  a2 = tile(j=1) c0,c1  a3 = tile(j=1) c2,c3 ----
@@ -463,7 +450,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int c = 0; c < 4; ++c) { yr[u][c] = 0.f; yi[u][c] = 0.f; }
-      if (!dbg_nomma) {
+      {
         // Yr = Tr.Wr - Ti.Wi     Yi = Tr.Wi + Ti.Wr
 #pragma unroll
         for (int u = 0; u < 2; ++u) { wfm_mma(yr[u], tr_h[u], ch.x, ch.y); wfm_mma(yi[u], tr_h[u], ch.z, ch.w); }
@@ -479,8 +466,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
 #pragma unroll
           for (int u = 0; u < 2; ++u) { wfm_mma(yr[u], ti_h[u], cn.z, cn.w); wfm_mma(yi[u], ti_h[u], cl.x, cl.y); }
         }
-      } else {
-        yr[0][0] = __uint_as_float(tr_h[0].x ^ ch.x); yi[1][3] = __uint_as_float(ti_l[1].w ^ cn.y);
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -548,8 +533,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
       sy += __shfl_xor_sync(0xffffffffu, sy, sft);
     }
     if (lane == 0) {
-      const float gx = (s0 > 0.f) ? sx / s0 : p.cog_offset;
-      const float gy = (s0 > 0.f) ? sy / s0 : p.cog_offset;
+      const float inv = __frcp_rn(s0);
+      const float gx = (s0 > 0.f) ? sx * inv : p.cog_offset;
+      const float gy = (s0 > 0.f) ? sy * inv : p.cog_offset;
       float* sl = p.slopes + (size_t)ce * p.lds;
       sl[ck] = (gx - p.cog_offset) * p.pixsize;
       sl[p.nvalid + ck] = (gy - p.cog_offset) * p.pixsize;

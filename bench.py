@@ -55,7 +55,6 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt", "tensor_reg", "tensor_pipe", "tcgen05"],
                     help="Shack-Hartmann frame kernel (tensor = default product path)")
-    ap.add_argument("--wfs-dbg", type=int, default=0, help=argparse.SUPPRESS)   # kernel development switches
     return ap.parse_args()
 
 
@@ -252,8 +251,6 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
 
-    if args.wfs_dbg:
-        os.environ["AOM_WFS_DBG"] = str(args.wfs_dbg)   # read by the library at every launch; timings only
     ev = torch.cuda.Event
     wfs_events = []
 
