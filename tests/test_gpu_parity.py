@@ -493,3 +493,32 @@ def test_denoiser_in_the_centroid_path(torch):
         sim.check_device()
     finally:
         sim.close()
+
+
+def test_40x40_closed_loop_statistics_against_reference(system40, torch):
+    """The only pin against the real COMPASS simulator: the reference authors committed per-feature statistics of
+    1000-frame integrator loops (state_normalization/*.pickle, exported to ao_marl_b200/data/normalization).  The
+    closed-loop slope rms and the normalised state blocks of the batched simulator must sit in the same
+    distribution (different RNG, so a distribution-level gate: SURVEY.md 8(c))."""
+    from ao_marl_b200.rl.layout import load_normalization
+    sim, t, rl = system40
+    norm, _ = load_normalization("production_sh_40x40_8m_3layers.py")
+    sim.reset(np.arange(6, dtype=np.int64) + 2000)
+    for _ in range(80):
+        sim.step(mode=2)
+    sl, st = [], []
+    for _ in range(160):
+        sim.step(mode=2)
+        sl.append(sim.rows("SLOPES", t.nslopes).std(dim=1).clone())
+        st.append(sim.rows("STATE", rl.state_dim).clone())
+    rms = float(torch.stack(sl).mean())
+    ref = float(norm["wfs"]["std"].mean())
+    assert abs(rms / ref - 1) < 0.3, (rms, ref)
+    # state = (v2m . x - mean_ref) / std_ref per mode: with the reference's own statistics every block has to
+    # come out roughly standard (rms over frames, environments and modes; TT and high orders included)
+    S = torch.stack(st)                                        # [frames, E, state_dim]
+    for key in ("dm_before_linear", "dm_residual"):
+        a, b = rl.indices_of_state[key]
+        blk = S[:, :, a:b]
+        spread = float(blk.std(dim=(0, 1)).median())
+        assert 0.5 < spread < 2.0, (key, spread)
