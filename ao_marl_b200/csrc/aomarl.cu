@@ -361,7 +361,14 @@ static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long
       if (w < waste) { waste = w; best = cn; }
     }
     const int bn = 8 * best;
-    dim3 grid((N + bn - 1) / bn, (M + GEMM_BM - 1) / GEMM_BM, 1);
+    // two K halves per tile when the tiles alone leave the SMs at two CTAs (8 warps) each
+    const int tiles = ((N + bn - 1) / bn) * ((M + GEMM_BM - 1) / GEMM_BM);
+    const int ksplit = (tiles <= 2 * ctx->num_sms && K >= 512) ? 2 : 1;
+    if (ksplit > 1) {
+      cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st);
+      if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((N + bn - 1) / bn, (M + GEMM_BM - 1) / GEMM_BM, ksplit);
     if (best == 8) gemm_tn_exact_kernel<8><<<grid, 128, 0, st>>>(p);
     else gemm_tn_exact_kernel<9><<<grid, 128, 0, st>>>(p);
   } else {

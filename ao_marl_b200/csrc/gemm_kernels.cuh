@@ -199,13 +199,19 @@ __global__ void __launch_bounds__(128, 4) gemm_tn_exact_kernel(GemmParams p) {
 #pragma unroll
     for (int j = 0; j < CN; ++j) acc[i][j] = 0.f;
 
-  const int nslab = p.K / GEMM_BK;
-  load_slab(0);
+  // split K over gridDim.z CTAs (partial sums are added with red.global.add onto a zeroed C: two round-to-nearest
+  // partial sums, commutative, so the result stays deterministic and unbiased)
+  const int nslab_all = p.K / GEMM_BK;
+  const int per = (nslab_all + gridDim.z - 1) / gridDim.z;
+  const int slab0 = blockIdx.z * per;
+  const int nslab = min(per, nslab_all - slab0);
+  if (nslab <= 0) return;
+  load_slab(slab0 * GEMM_BK);
   store_slab(0);
   __syncthreads();
   for (int s = 0; s < nslab; ++s) {
     const int buf = s & 1;
-    if (s + 1 < nslab) load_slab((s + 1) * GEMM_BK);
+    if (s + 1 < nslab) load_slab((slab0 + s + 1) * GEMM_BK);
 #pragma unroll
     for (int k = 0; k < GEMM_BK; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
@@ -231,7 +237,11 @@ __global__ void __launch_bounds__(128, 4) gemm_tn_exact_kernel(GemmParams p) {
 #pragma unroll
     for (int j = 0; j < CN; ++j) {
       const int c = n0 + tx * CN + j;
-      if (c < p.ldc) C[(long long)row * p.ldc + c] = (c < p.N) ? acc[i][j] : 0.f;   // pad columns stay zero
+      if (gridDim.z > 1) {
+        if (c < p.N) atomicAdd(C + (long long)row * p.ldc + c, acc[i][j]);
+      } else if (c < p.ldc) {
+        C[(long long)row * p.ldc + c] = (c < p.N) ? acc[i][j] : 0.f;   // pad columns stay zero
+      }
     }
   }
 }
