@@ -379,9 +379,9 @@ def run_ours(args):
                          "peak_source": "measured" if peaks else "fallback",
                          "ms_per_launch": wfs_ms, "share_of_step": wfs_ms / (ms / args.steps),
                          "fp32_tflops_algorithmic": flops_per_frame * E / (wfs_ms * 1e-3) / 1e12,
-                         "note": "issue-slot bound: 144 legacy HMMA (3 x fp16 split DFT in registers) cost ~6 issue cycles "
-                                 "each next to ~1030 other warp instructions per subaperture; not HBM bound: "
-                                 "see DESIGN.md" if args.wfs_path != "simt" else
+                         "note": "latency bound at 4 warps per scheduler (~1180 warp instructions per subaperture at ~0.5 "
+                                 "IPC; HMMA pipe 50 %, DRAM 19 %): neither HBM nor tensor bound, see DESIGN.md section 4"
+                                 if args.wfs_path != "simt" else
                                  "issue-bound on the FP32 pipe (SIMT pruned FFT), not on HBM: see DESIGN.md"},
             "e2e": {"value": k_e2e * E * world / (ms_e2e * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": int(E * rl.action_dim * 4),
