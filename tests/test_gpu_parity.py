@@ -522,3 +522,48 @@ def test_40x40_closed_loop_statistics_against_reference(system40, torch):
         blk = S[:, :, a:b]
         spread = float(blk.std(dim=(0, 1)).median())
         assert 0.5 < spread < 2.0, (key, spread)
+
+
+def test_single_environment_keeps_the_reference_shapes(torch):
+    """Drop-in surface with E == 1 (what ao_env.py / train_rpc.py see): numpy float32 arrays of the reference's shapes,
+    the reference's error behaviour (rtcCompass.py:471-472 raises ValueError("Dimension mismatch")), and the same step
+    sequencing as AoEnv.reset / rl_step / linear_step (ao_env.py:336-354, 871-939)."""
+    from ao_marl_b200.env.ao_env import AoEnv
+    from ao_marl_b200.env.config_rl import Config
+    cfg = Config(parameters_telescope="production_sh_10x10_2m.py", n_zernike_start_end=[0, 80],
+                 n_reverse_filtered_from_cmat=5)
+    env = AoEnv(cfg, n_env=1, world_size=3, initial_seed=1234)
+    sup = env.supervisor
+    try:
+        s = env.reset()
+        assert isinstance(s, np.ndarray) and s.dtype == np.float32 and s.shape == (env.state_size,) == (4 * 82,)
+        d = env.linear_step(return_dict=True)
+        assert list(d) == ["dm_history_2", "dm_history_1", "dm_before_linear", "dm_residual"]
+        assert all(v.shape == (82,) for v in d.values())
+        slopes = sup.rtc.get_slopes(0)
+        assert isinstance(slopes, np.ndarray) and slopes.shape == (128,) and slopes.dtype == np.float32
+        assert sup.rtc.get_command(0).shape == (90,) and sup.rtc.get_err(0).shape == (90,)
+        assert sup.rtc.get_voltages(0).shape == (90,)
+        assert sup.modes2volts.shape == (90, 87) and sup.volts2modes.shape == (87, 90)
+        assert sup.wfs.get_wfs_image(0).shape == (160, 160)
+        assert sup.wfs.get_wfs_phase(0).shape == (164, 164)
+        assert sup.atmos.get_atmos_layer(0).shape == (168, 168)
+        se, le, var, avg = sup.target.get_strehl(0)
+        assert all(isinstance(x, float) for x in (se, le, var, avg))
+        with pytest.raises(ValueError):
+            sup.rtc.set_command(0, np.zeros(91, np.float32))
+        a = np.zeros(env.action_size, np.float32)
+        r, done, info = env.rl_step(a)
+        assert isinstance(r, float) and r <= 0.0 and done is False
+        s2 = env.linear_step()
+        assert s2.shape == s.shape and np.isfinite(s2).all() and np.abs(s2 - s).max() > 0
+        # set_command / get_command round trip in the reference's units
+        com = np.linspace(-1, 1, 90).astype(np.float32)
+        sup.rtc.set_command(0, com)
+        assert np.array_equal(sup.rtc.get_command(0), com)
+        g0 = sup.rtc._rtc.d_control[0].gain
+        env.set_gain(0.25)
+        assert abs(sup.rtc._rtc.d_control[0].gain - 0.25) < 1e-7 and g0 != 0.25
+        env.sim.check_device()
+    finally:
+        env.sim.close()
