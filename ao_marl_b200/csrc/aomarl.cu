@@ -63,6 +63,12 @@ struct aom_ctx {
   void* fast_dev[7];
   CUtensorMap fast_maps[WFT_MAX_LAYERS];
   size_t fast_smem;
+  // aom_step runs the turbulence update next to the actor / controller GEMMs on a second stream
+  cudaStream_t side_stream;
+  cudaEvent_t ev_fork, ev_join;
+  // device time of the sensor kernel (AOM_OPT_TIME_WFS): event pairs around its launches, read by aom_wfs_time_ms
+  cudaEvent_t wev[2][AOM_WFS_TIMERS];
+  int wev_n;
 };
 
 static int fail(aom_ctx* c, int code, const char* fmt, ...) {
@@ -191,6 +197,9 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     CU(dalloc(&ctx->aHO, A * E * ctx->ld_aho));
   }
   CU(dalloc(&ctx->d_err, 1));
+  CU(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   CU(cudaFuncSetAttribute(gemm_tc_kernel<0, GTC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tc_kernel<1, GTC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tc_kernel<0, GTC_BN_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GTC_SMEM_BYTES_T(GTC_BN_WIDE)));
@@ -213,6 +222,12 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
                   ctx->action_mean, ctx->strehl, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO, ctx->d_err};
   for (void* b : bufs) cudaFree(b);
   for (void* b : ctx->fast_dev) cudaFree(b);
+  for (int i = 0; i < AOM_WFS_TIMERS; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->wev[j][i]) cudaEventDestroy(ctx->wev[j][i]);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (int t = 0; t < AOM_T_COUNT; ++t) free(ctx->htab[t]);
   free(ctx);
 }
@@ -710,11 +725,9 @@ static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) 
   P.f.items_per_cta = ipc;
   for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
   const size_t smem = wft_smem_bytes<NL, NW, NST>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
-  static size_t configured = 0;
-  if (smem > configured) {
+  {
     cudaError_t e = cudaFuncSetAttribute(wfs_frame_tma_kernel<FULL, NL, NW, MINB, NST, TOKEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_tma_kernel): %s", cudaGetErrorString(e));
-    configured = smem;
   }
   wfs_frame_tma_kernel<FULL, NL, NW, MINB, NST, TOKEN><<<(unsigned)grid, NW * 32, smem, st>>>(P);
   return AOM_OK;
@@ -737,11 +750,9 @@ static int wfs_tc_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) {
   P.b2 = (const uint4*)ctx->fast_dev[6];
   for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
   const size_t smem = wtc_smem_bytes<NL>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
-  static size_t configured = 0;
-  if (smem > configured) {
+  {
     cudaError_t e = cudaFuncSetAttribute(wfs_frame_tc_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_tc_kernel): %s", cudaGetErrorString(e));
-    configured = smem;
   }
   wfs_frame_tc_kernel<NL><<<(unsigned)grid, WTC_WARPS * 32, smem, st>>>(P);
   return AOM_OK;
@@ -756,11 +767,9 @@ static int wfs_pipe_launch_t(aom_ctx* ctx, const WfsParams& p, int grid, long lo
   P.f.items_per_cta = ipc;
   for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
   const size_t smem = wft_smem_bytes<NL>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
-  static size_t configured = 0;
-  if (smem > configured) {
+  {
     cudaError_t e = cudaFuncSetAttribute(wfs_frame_pipe_kernel<FULL, NL, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_pipe_kernel): %s", cudaGetErrorString(e));
-    configured = smem;
   }
   wfs_frame_pipe_kernel<FULL, NL, DM><<<grid, WFT_WARPS * 32, smem, st>>>(P);
   return AOM_OK;
@@ -852,6 +861,12 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
   long long cap = (long long)ctx->num_sms * 2 * 8;      // 2 resident CTAs per SM, 8 waves of work each
   int grid = (int)(blocks < cap ? blocks : cap);
   const int path = ctx->opt[AOM_OPT_WFS_PATH];
+  const bool timed = ctx->opt[AOM_OPT_TIME_WFS] && ctx->wev_n < AOM_WFS_TIMERS;
+  if (timed) {
+    for (int j = 0; j < 2; ++j)
+      if (!ctx->wev[j][ctx->wev_n]) CU(cudaEventCreate(&ctx->wev[j][ctx->wev_n]));
+    CU(cudaEventRecord(ctx->wev[0][ctx->wev_n], st));
+  }
   const bool staged = (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST || path == AOM_WFS_TENSOR_PIPE ||
                        path == AOM_WFS_TCGEN05);
   if (c.nfft == 64 && staged) {
@@ -876,8 +891,27 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
   else if (c.nfft == 64) wfs_frame_kernel<4><<<grid, WFS_WARPS * 32, wfs_smem_bytes<4>(), st>>>(p);
   else wfs_frame_kernel<8><<<grid, WFS_WARPS * 32, wfs_smem_bytes<8>(), st>>>(p);
   KCHECK();
+  if (timed) {
+    CU(cudaEventRecord(ctx->wev[1][ctx->wev_n], st));
+    ctx->wev_n++;
+  }
   ctx->frame++;
   ctx->cube_override = nullptr;
+  return AOM_OK;
+}
+
+extern "C" int aom_wfs_time_ms(aom_ctx* ctx, float* mean_ms, int* count) {
+  if (!ctx || !mean_ms || !count) return fail(ctx, AOM_ERR_INVALID, "null argument");
+  double sum = 0.0;
+  for (int i = 0; i < ctx->wev_n; ++i) {
+    float ms = 0.f;
+    CU(cudaEventSynchronize(ctx->wev[1][i]));
+    CU(cudaEventElapsedTime(&ms, ctx->wev[0][i], ctx->wev[1][i]));
+    sum += ms;
+  }
+  *count = ctx->wev_n;
+  *mean_ms = ctx->wev_n ? (float)(sum / ctx->wev_n) : 0.f;
+  ctx->wev_n = 0;
   return AOM_OK;
 }
 
@@ -977,6 +1011,7 @@ extern "C" int aom_set_option(aom_ctx* ctx, int option, int value) {
   if (option < 0 || option >= AOM_OPT_COUNT) return fail(ctx, AOM_ERR_INVALID, "unknown option %d", option);
   if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_TCGEN05))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_WFS_PATH: value %d out of range", value);
+  if (option == AOM_OPT_TIME_WFS) ctx->wev_n = 0;
   if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_SIMT))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_GEMM_PATH: value %d out of range", value);
   ctx->opt[option] = value;
@@ -1126,6 +1161,17 @@ extern "C" int aom_actor_forward(aom_ctx* ctx, int eval_mode, void* stream) {
 extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   if (!ctx) return AOM_ERR_INVALID;
   int rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // The turbulence update (exact-fp32 extrusion GEMMs on the FP32 pipe) touches only the screens, the rl
+  // half-step (tensor-core GEMMs of the actors and the modal projections) only the controller state: they run
+  // side by side on two streams and join before the sensor frame.
+  const bool fork = ctx->cfg.n_layers > 0 && ctx->seeded;
+  if (fork) {
+    CU(cudaEventRecord(ctx->ev_fork, st));
+    CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    rc = aom_move_atmos(ctx, ctx->side_stream); if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  }
   // rl half-step: TrainerRPC.env_step -> AoEnv.rl_step -> RlSupervisor.next_part_two (rlSupervisor.py:900-947)
   if (mode == 0) { rc = aom_actor_forward(ctx, eval_mode, stream); if (rc) return rc; }
   if (mode != 2) { rc = aom_rl_control(ctx, nullptr, stream); if (rc) return rc; }
@@ -1133,7 +1179,8 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   if (ctx->reward) { rc = aom_reward(ctx, 1000.f, stream); if (rc) return rc; }
   // linear half-step: AoEnv.linear_step -> RlSupervisor.next_part_one (rlSupervisor.py:1015-1051)
   rc = aom_state_begin(ctx, stream); if (rc) return rc;
-  rc = aom_move_atmos(ctx, stream); if (rc) return rc;
+  if (fork) CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  else { rc = aom_move_atmos(ctx, stream); if (rc) return rc; }
   rc = aom_comp_wfs_image(ctx, 3, ctx->cfg.noise, stream); if (rc) return rc;
   rc = aom_do_centroids(ctx, stream); if (rc) return rc;
   rc = aom_do_control(ctx, stream); if (rc) return rc;

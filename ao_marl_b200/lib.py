@@ -48,7 +48,7 @@ B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
-           "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_raytrace_wfs",
+           "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_wfs_time_ms", "aom_raytrace_wfs",
            "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
            "aom_set_gain", "aom_set_loop", "aom_reset_dm", "aom_set_dm_volts", "aom_rl_control",
            "aom_state_begin", "aom_state_end", "aom_reward", "aom_actor_forward", "aom_step", "aom_gemm_tn",
@@ -88,6 +88,7 @@ def load_library():
     lib.aom_set_layer.argtypes = [vp, i32, f32, f32, f32]
     lib.aom_comp_wfs_image.argtypes = [vp, i32, f32, vp]
     lib.aom_raytrace_wfs.argtypes = [vp, i32, vp]
+    lib.aom_wfs_time_ms.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32)]
     lib.aom_wfs_kernel.argtypes = [vp]
     lib.aom_wfs_kernel.restype = ctypes.c_char_p
     lib.aom_set_bincube.argtypes = [vp, vp, vp]
@@ -271,6 +272,16 @@ class Simulator:
     def wfs_kernel(self):
         """Name of the kernel the next frame launches (and, via last_error, why the staged one is not used)."""
         return self.lib.aom_wfs_kernel(self._ctx).decode()
+
+    def time_wfs(self, on=True):
+        """Bracket every sensor-kernel launch with CUDA events (read the mean with wfs_time_ms)."""
+        self._check(self.lib.aom_set_option(self._ctx, 2, 1 if on else 0), "aom_set_option")
+
+    def wfs_time_ms(self):
+        """(mean device time in ms, number of launches) of the sensor kernel since the last call."""
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        self._check(self.lib.aom_wfs_time_ms(self._ctx, ctypes.byref(ms), ctypes.byref(n)), "aom_wfs_time_ms")
+        return float(ms.value), int(n.value)
 
     GEMM_PATHS = {"tcgen05": 0, "simt": 1}
 

@@ -252,27 +252,11 @@ def run_ours(args):
     t_build = time.perf_counter() - t_build
 
     ev = torch.cuda.Event
-    wfs_events = []
 
-    def one_step(record):
-        # TrainerRPC.episode body (train_rpc.py:503-553) sequenced through the C ABI
-        sim.actor_forward(False)
-        sim.rl_control()
-        sim.apply_control(True)
-        sim.reward(rl.reward_factor)
-        sim.state_begin()
-        sim.move_atmos()
-        if record:
-            a, b = ev(enable_timing=True), ev(enable_timing=True)
-            a.record()
-            sim.comp_wfs_image()
-            b.record()
-            wfs_events.append((a, b))
-        else:
-            sim.comp_wfs_image()
-        sim.do_centroids()
-        sim.do_control()
-        sim.state_end()
+    def one_step():
+        # TrainerRPC.episode body (train_rpc.py:503-553): one aom_step = actors, rl_control, apply_control, reward,
+        # move_atmos (on the library's second stream, next to the actor GEMMs), sensor frame, centroids, control, state
+        sim.step(mode=0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -281,23 +265,25 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        one_step(False)
+        one_step()
     sampler = ClockSampler(local_rank)
     barrier()
+    sim.time_wfs(True)                # CUDA events around the sensor-kernel launches, on the launching stream
     sampler.start()
     l0 = sim.launches()
     torch.cuda.profiler.start()      # ncu --profile-from-start off captures the timed region only
     e0, e1 = ev(enable_timing=True), ev(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        one_step(True)
+        one_step()
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = sim.launches() - l0
     ms = e0.elapsed_time(e1)
-    wfs_ms = float(np.mean([a.elapsed_time(b) for a, b in wfs_events]))
+    wfs_ms, _ = sim.wfs_time_ms()
+    sim.time_wfs(False)
 
     # end to end through host buffers: the actions of every step come from pinned host memory (H2D) and go back to
     # it (D2H) -- the host is in the action loop, as in the reference's env.step -- and the step's state and rewards

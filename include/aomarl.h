@@ -22,6 +22,7 @@ extern "C" {
 #endif
 
 #define AOM_MAX_LAYERS 8
+#define AOM_WFS_TIMERS 64             /* sensor-kernel launches timed between two aom_wfs_time_ms calls */
 #define AOM_LD(n) (((n) + 15) & ~15)
 
 typedef struct aom_ctx aom_ctx;
@@ -140,6 +141,7 @@ typedef enum aom_buffer {
 typedef enum aom_option {
   AOM_OPT_WFS_PATH = 0, /* which Shack-Hartmann frame kernel serves the Nfft = 64 geometry */
   AOM_OPT_GEMM_PATH,    /* which GEMM kernel serves the env-batched contractions */
+  AOM_OPT_TIME_WFS,     /* != 0: bracket every sensor-kernel launch with CUDA events (read with aom_wfs_time_ms) */
   AOM_OPT_COUNT
 } aom_option;
 enum {
@@ -191,6 +193,10 @@ int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* stream);
  * ("wfs_frame_pipe_kernel", "wfs_frame_tma_kernel", "wfs_frame_mma_kernel" or "wfs_frame_kernel"); when the staged kernel is not
  * eligible for the geometry, aom_last_error() says why. */
 const char* aom_wfs_kernel(aom_ctx* ctx);
+
+/* Mean device time (ms) of the sensor-kernel launches recorded since the last call (AOM_OPT_TIME_WFS; at most
+ * AOM_WFS_TIMERS launches are kept); synchronises on the recorded events. */
+int aom_wfs_time_ms(aom_ctx* ctx, float* mean_ms, int* count);
 
 /* Materialise the pupil-plane phase seen by the sensor (wfs.get_wfs_phase) into AOM_B_PHASE. */
 int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream);
