@@ -567,3 +567,36 @@ def test_single_environment_keeps_the_reference_shapes(torch):
         env.sim.check_device()
     finally:
         env.sim.close()
+
+
+def test_normalization_producer_against_reference_statistics(static10, oracle_imat10, torch, tmp_path):
+    """ao_marl_b200.tools.obtain_normalization (the reference's normalization_loop, batched over the seeds): its
+    statistics land in the distribution of the ones the reference authors committed for the same parameter file,
+    and its output file loads through the RL layout."""
+    import copy
+    from ao_marl_b200 import calibration
+    from ao_marl_b200.init import rtc as rtc_b
+    from ao_marl_b200.lib import Simulator
+    from ao_marl_b200.rl.layout import RLLayout, load_normalization
+    from ao_marl_b200.tools import obtain_normalization as on
+    t = copy.copy(static10)
+    t.imat = calibration.measure_imat(static10)
+    t.cmat = rtc_b.cmat_with_btt(t.imat, t.Btt, 0)
+    sim = Simulator(t, 20, rl=None)
+    try:
+        norm, zn = on.normalization_loop(sim, t, n_frames=400, first_seed=1, settle=20)
+    finally:
+        sim.close()
+    ref, zn_ref = load_normalization("production_sh_10x10_2m.py")
+    assert zn.shape == zn_ref.shape == (87,)
+    assert abs(norm["wfs"]["std"].mean() / ref["wfs"]["std"].mean() - 1) < 0.25
+    ratio = norm["dm"]["std"] / ref["dm"]["std"]
+    assert 0.5 < np.median(ratio) < 2.0, np.median(ratio)
+    assert 0.4 < np.median(zn / zn_ref) < 2.5
+    out = tmp_path / "norm.npz"
+    on.save(str(out), norm, zn)
+    z = np.load(out)
+    rl = RLLayout(87, dict(parameters_telescope="production_sh_10x10_2m.py", n_zernike_start_end=[0, 80]), None, 3,
+                  norm={k: {s: z["%s_%s" % (k, s)] for s in ("mean", "std", "max", "min")}
+                        for k in ("dm", "wfs", "dm_residual")}, zn_norm=z["zn_norm"])
+    assert rl.state_dim == 4 * 82 and np.isfinite(rl.freedom).all()
