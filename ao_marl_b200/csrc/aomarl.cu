@@ -818,6 +818,8 @@ static int fill_wfs_params(aom_ctx* ctx, WfsParams& p, int flags, float noise) {
     double px = (double)c.wfs_xoff[l] + ctx->accx[l], py = (double)c.wfs_yoff[l] + ctx->accy[l];
     L.ix = (int)floor(px); L.iy = (int)floor(py);
     L.fx = (float)(px - L.ix); L.fy = (float)(py - L.iy);
+    L.w00 = (1.f - L.fx) * (1.f - L.fy); L.w01 = L.fx * (1.f - L.fy);
+    L.w10 = (1.f - L.fx) * L.fy;         L.w11 = L.fx * L.fy;
     if (L.ix < 0 || L.iy < 0 || L.ix + c.n + 1 > L.N || L.iy + c.n + 1 > L.N)
       return fail(ctx, AOM_ERR_UNSUPPORTED, "layer %d: pupil footprint leaves the screen", l);
   }

@@ -24,6 +24,7 @@ struct WfsLayer {
   int N;
   int ix, iy;            // integer part of (offset + wind accumulator)
   float fx, fy;          // fractional part
+  float w00, w01, w10, w11;   // bilinear weights (1-fx)(1-fy), fx(1-fy), (1-fx)fy, fx fy of the four taps
 };
 
 struct WfsParams {

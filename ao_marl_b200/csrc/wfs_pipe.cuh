@@ -168,12 +168,11 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_pipe_kernel(const
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
         const float* t = reinterpret_cast<const float*>(my_tiles + (stage * NL + l) * WFT_TILE_STRIDE) + lane_off;
-        const float fx = p.layer[l].fx, fy = p.layer[l].fy;
         switch ((it.ds >> (1 + 2 * l)) & 3u) {
-          case 0: wft_layer<0>(t, fx, fy, ph); break;
-          case 1: wft_layer<1>(t, fx, fy, ph); break;
-          case 2: wft_layer<2>(t, fx, fy, ph); break;
-          default: wft_layer<3>(t, fx, fy, ph); break;
+          case 0: wft_layer<0>(t, p.layer[l], ph); break;
+          case 1: wft_layer<1>(t, p.layer[l], ph); break;
+          case 2: wft_layer<2>(t, p.layer[l], ph); break;
+          default: wft_layer<3>(t, p.layer[l], ph); break;
         }
       }
       __syncwarp();      // every lane has drained the stage before lane 0 re-arms it

@@ -318,12 +318,11 @@ __global__ void __launch_bounds__(WTC_WARPS * 32, 1) wfs_frame_tc_kernel(const _
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
           const float* t = reinterpret_cast<const float*>(my_tiles + l * WFT_TILE_STRIDE) + lane_off;
-          const float fx = p.layer[l].fx, fy = p.layer[l].fy;
           switch ((c_d >> (2 * l)) & 3u) {
-            case 0: wft_layer<0>(t, fx, fy, ph); break;
-            case 1: wft_layer<1>(t, fx, fy, ph); break;
-            case 2: wft_layer<2>(t, fx, fy, ph); break;
-            default: wft_layer<3>(t, fx, fy, ph); break;
+            case 0: wft_layer<0>(t, p.layer[l], ph); break;
+            case 1: wft_layer<1>(t, p.layer[l], ph); break;
+            case 2: wft_layer<2>(t, p.layer[l], ph); break;
+            default: wft_layer<3>(t, p.layer[l], ph); break;
           }
         }
         __syncwarp();                                   // the stage is drained: re-arm it with the next item

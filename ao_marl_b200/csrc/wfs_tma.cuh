@@ -90,26 +90,33 @@ __device__ __forceinline__ void wft_tma_load_3d(uint32_t dst, const CUtensorMap*
 // column below the tile origin (the inner coordinate of a tiled copy must be 16-byte aligned), so the wanted
 // columns begin D = origin & 3 floats into the row; D is warp-uniform and resolved by a switch around this.
 template <int D>
-__device__ __forceinline__ void wft_layer(const float* __restrict__ t, float fx, float fy, float (&ph)[2][4]) {
-  float h[3][4];
+__device__ __forceinline__ void wft_layer(const float* __restrict__ t, const WfsLayer& L, float (&ph)[2][4]) {
+  // four-tap form of the bilinear sample (weights per layer from the host): 4 FFMA per pixel and layer instead of
+  // the 5 of the separable two-pass form; same value up to float rounding
+  float v[3][8];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const float4 a = *reinterpret_cast<const float4*>(t + r * WFT_TILE_W);
-    float v[8] = {a.x, a.y, a.z, a.w, 0.f, 0.f, 0.f, 0.f};
+    v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w;
     if (D == 0) {
-      v[4] = t[r * WFT_TILE_W + 4];
+      v[r][4] = t[r * WFT_TILE_W + 4];
     } else {
       const float4 b = *reinterpret_cast<const float4*>(t + r * WFT_TILE_W + 4);
-      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      v[r][4] = b.x; v[r][5] = b.y; v[r][6] = b.z; v[r][7] = b.w;
     }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) h[r][c] = v[D + c] + fx * (v[D + c + 1] - v[D + c]);
   }
+  const float w00 = L.w00, w01 = L.w01, w10 = L.w10, w11 = L.w11;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    ph[0][c] += h[0][c] + fy * (h[1][c] - h[0][c]);
-    ph[1][c] += h[1][c] + fy * (h[2][c] - h[1][c]);
-  }
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float acc = ph[r][c];
+      acc = fmaf(w00, v[r][D + c], acc);
+      acc = fmaf(w01, v[r][D + c + 1], acc);
+      acc = fmaf(w10, v[r + 1][D + c], acc);
+      acc = fmaf(w11, v[r + 1][D + c + 1], acc);
+      ph[r][c] = acc;
+    }
 }
 
 // NW warps per CTA, NST tile stages per warp (the volt buffers are always double)
@@ -299,12 +306,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
         const float* t = reinterpret_cast<const float*>(my_tiles + (ts * NL + l) * WFT_TILE_STRIDE) + lane_off;
-        const float fx = p.layer[l].fx, fy = p.layer[l].fy;
         switch ((c_d >> (2 * l)) & 3u) {
-          case 0: wft_layer<0>(t, fx, fy, ph); break;
-          case 1: wft_layer<1>(t, fx, fy, ph); break;
-          case 2: wft_layer<2>(t, fx, fy, ph); break;
-          default: wft_layer<3>(t, fx, fy, ph); break;
+          case 0: wft_layer<0>(t, p.layer[l], ph); break;
+          case 1: wft_layer<1>(t, p.layer[l], ph); break;
+          case 2: wft_layer<2>(t, p.layer[l], ph); break;
+          default: wft_layer<3>(t, p.layer[l], ph); break;
         }
       }
       if (NST == 1 && has_next) {
