@@ -122,8 +122,10 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     return fail(nullptr, AOM_ERR_UNSUPPORTED, "actuator pitch too small for the %d-cell neighbourhood", WFS_NG_MAX);
   if (cfg->delay != 0 && cfg->delay != 1) return fail(nullptr, AOM_ERR_UNSUPPORTED, "controller delay must be 0 or 1 frame");
 
-  ctx = (aom_ctx*)calloc(1, sizeof(aom_ctx));
+  // the context embeds CUtensorMap objects (64-byte aligned)
+  ctx = (aom_ctx*)aligned_alloc(64, (sizeof(aom_ctx) + 63) / 64 * 64);
   if (!ctx) return fail(nullptr, AOM_ERR_INVALID, "out of host memory");
+  memset(ctx, 0, sizeof(aom_ctx));
   ctx->cfg = *cfg;
   ctx->gain = cfg->gain;
   ctx->closed = 1;
