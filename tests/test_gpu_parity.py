@@ -221,18 +221,25 @@ def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
 
 def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
     """Photon noise: the oracle's sampler applied to the GPU's noise-free image reproduces the GPU's
-    noisy image exactly (same Philox stream, same integer Poisson draws)."""
+    noisy image exactly (same Philox stream, same integer Poisson draws) -- for every sensor-kernel generation,
+    each of which lays the detector pixels out differently over the lanes."""
     from oracle import aoframe
     seeds = np.array([11, 12, 13, 14], dtype=np.int64)
-    sim10.reset(seeds)
-    sim10.comp_wfs_image(keep_image=True, noise=-1.0)       # frame 0
-    clean = sim10.buffer("BINCUBE").clone().view(4, -1).cpu().numpy()
-    sim10.reset(seeds)
-    sim10.comp_wfs_image(keep_image=True, noise=3.0)        # frame 0 again, same screens
-    noisy = sim10.buffer("BINCUBE").view(4, -1).cpu().numpy()
-    for e in range(4):
-        ref = aoframe.sh_noise(clean[e], 3.0, int(seeds[e]), static10.wfs_index, 0)
-        assert np.array_equal(noisy[e], ref)
+    try:
+        for path in ("tensor", "tensor_pipe", "tcgen05", "tensor_reg", "simt"):
+            sim10.set_wfs_path(path)
+            sim10.reset(seeds)
+            sim10.comp_wfs_image(keep_image=True, noise=-1.0)       # frame 0
+            clean = sim10.buffer("BINCUBE").clone().view(4, -1).cpu().numpy()
+            sim10.reset(seeds)
+            sim10.comp_wfs_image(keep_image=True, noise=3.0)        # frame 0 again, same screens
+            noisy = sim10.buffer("BINCUBE").view(4, -1).cpu().numpy()
+            sim10.check_device()
+            for e in range(4):
+                ref = aoframe.sh_noise(clean[e], 3.0, int(seeds[e]), static10.wfs_index, 0)
+                assert np.array_equal(noisy[e], ref), path
+    finally:
+        sim10.set_wfs_path("tensor")
 
 
 def test_imat_matches_oracle(static10, oracle_imat10, torch):
