@@ -41,6 +41,9 @@ struct aom_ctx {
   float *slopes_frame, *slopes, *err_v, *com, *com1, *volts, *com_before;
   float *bincube, *phase;
   const float* cube_override;
+  double* tar_mom;            // [E][3] pupil sums of the target phase (aom_comp_strehl)
+  float* tar_acc;             // [E][2] running sums for the long-exposure figures
+  int tar_n;
   int lds, lda, ldm;
   float gain;
   int closed;
@@ -172,6 +175,8 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
   CU(dalloc(&ctx->volts, E * ctx->lda));
   CU(dalloc(&ctx->com_before, E * ctx->lda));
   CU(dalloc(&ctx->strehl, E * 4));
+  CU(dalloc(&ctx->tar_mom, E * 3));
+  CU(dalloc(&ctx->tar_acc, E * 2));
   if (cfg->nmodes > 0) {
     CU(dalloc(&ctx->modes, E * ctx->ldm));
     CU(dalloc(&ctx->modes_before, E * ctx->ldm));
@@ -221,7 +226,7 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
   void* bufs[] = {ctx->k0, ctx->k1, ctx->Z, ctx->zref, ctx->newcol, ctx->slopes_frame, ctx->slopes, ctx->err_v,
                   ctx->com, ctx->com1, ctx->volts, ctx->com_before, ctx->bincube, ctx->phase, ctx->modes,
                   ctx->modes_before, ctx->modes_res, ctx->state, ctx->hist, ctx->reward, ctx->action,
-                  ctx->action_mean, ctx->strehl, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO, ctx->d_err};
+                  ctx->action_mean, ctx->strehl, ctx->tar_mom, ctx->tar_acc, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO, ctx->d_err};
   for (void* b : bufs) cudaFree(b);
   for (void* b : ctx->fast_dev) cudaFree(b);
   for (int i = 0; i < AOM_WFS_TIMERS; ++i)
@@ -458,6 +463,9 @@ static int clear_loop_state(aom_ctx* ctx, cudaStream_t st) {
   if (ctx->action) CU(cudaMemsetAsync(ctx->action, 0, E * ctx->ldact * 4, st));
   ctx->hist_head = 0;
   ctx->cube_override = nullptr;
+  ctx->tar_n = 0;
+  CU(cudaMemsetAsync(ctx->tar_acc, 0, E * 2 * sizeof(float), st));
+  CU(cudaMemsetAsync(ctx->strehl, 0, E * 4 * sizeof(float), st));
   return AOM_OK;
 }
 
@@ -946,6 +954,33 @@ extern "C" int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream) {
   dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
   wfs_phase_kernel<<<grid, blk, 0, st>>>(p, ctx->phase);
   KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int accumulate, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  if (!(lambda_um > 0.f)) return fail(ctx, AOM_ERR_INVALID, "target wavelength must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  WfsParams p;
+  int rc = fill_wfs_params(ctx, p, flags, -1.f);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->tar_mom, 0, (size_t)c.n_env * 3 * sizeof(double), st));
+  dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
+  target_moments_kernel<<<grid, blk, 0, st>>>(p, ctx->tar_mom);
+  KCHECK();
+  if (accumulate) ctx->tar_n += 1;
+  target_strehl_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(ctx->tar_mom, ctx->strehl, ctx->tar_acc, c.n_env,
+                                                             (float)(2.0 * M_PI / (double)lambda_um), accumulate ? ctx->tar_n : 0);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_reset_strehl(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  ctx->tar_n = 0;
+  CU(cudaMemsetAsync(ctx->tar_acc, 0, (size_t)ctx->cfg.n_env * 2 * sizeof(float), (cudaStream_t)stream));
+  CU(cudaMemsetAsync(ctx->strehl, 0, (size_t)ctx->cfg.n_env * 4 * sizeof(float), (cudaStream_t)stream));
   return AOM_OK;
 }
 

@@ -329,6 +329,88 @@ __global__ void wfs_phase_kernel(WfsParams p, float* phase) {
   phase[((size_t)e * p.n + y) * p.n + x] = acc;
 }
 
+// Phase statistics over the pupil for the target's Strehl (TargetCompass.comp_strehl / get_strehl,
+// targetCompass.py:139-196: get_strehl()[2] is the phase variance): the phase of wfs_phase_kernel is evaluated per
+// pixel and reduced on the fly -- sum m, sum m phi, sum m phi^2 per environment (double atomics) -- instead of
+// materialising [E][n][n].  grid (ceil(n/32), ceil(n/8), E), block (32, 8).
+__global__ void target_moments_kernel(WfsParams p, double* mom) {
+  const int e = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  float m = 0.f, acc = 0.f;
+  if (x < p.n && y < p.n) m = p.mpupil[(size_t)y * p.n + x];
+  if (m != 0.f) {
+    for (int l = 0; l < p.n_layers; ++l) {
+      const WfsLayer& L = p.layer[l];
+      const int N = L.N;
+      const float* scr = L.screen + (size_t)e * N * N;
+      const int ox = L.ox[e], oy = L.oy[e];
+      int pc0 = (x + L.ix + ox) % N, pc1 = (pc0 + 1) % N;
+      int pr0 = (y + L.iy + oy) % N, pr1 = (pr0 + 1) % N;
+      float top = wfs_layer_row(scr, N, pr0, pc0, pc1, L.fx);
+      float bot = wfs_layer_row(scr, N, pr1, pc0, pc1, L.fx);
+      acc += top + L.fy * (bot - top);
+    }
+    if (p.use_dm) {
+      const float* volts = p.volts + (size_t)e * p.ldv;
+      const int X = x + p.pzt_off, Y = y + p.pzt_off;
+      float dm = 0.f;
+      int gxh = (X - p.i1_0) >= 0 ? (X - p.i1_0) / p.pitch : -1;
+      int gyh = (Y - p.j1_0) >= 0 ? (Y - p.j1_0) / p.pitch : -1;
+      for (int gy = gyh; gy >= 0 && Y - (p.j1_0 + gy * p.pitch) < p.ss; --gy) {
+        if (gy >= p.grid_n) continue;
+        float fy = p.stamp1d[Y - (p.j1_0 + gy * p.pitch)];
+        for (int gx = gxh; gx >= 0 && X - (p.i1_0 + gx * p.pitch) < p.ss; --gx) {
+          if (gx >= p.grid_n) continue;
+          int a = p.act_map[gy * p.grid_n + gx];
+          if (a >= 0) dm = fmaf(volts[a] * fy, p.stamp1d[X - (p.i1_0 + gx * p.pitch)], dm);
+        }
+      }
+      size_t to = (size_t)(y + p.tt_off) * p.tt_dim + (x + p.tt_off);
+      dm = fmaf(volts[p.pzt_nact], p.tt_planes[to], dm);
+      dm = fmaf(volts[p.pzt_nact + 1], p.tt_planes[(size_t)p.tt_dim * p.tt_dim + to], dm);
+      acc += dm;
+    }
+  }
+  float s0 = m, s1 = m * acc, s2 = m * acc * acc;
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, sft);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, sft);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, sft);
+  }
+  __shared__ float red[8][3];
+  if (threadIdx.x == 0) { red[threadIdx.y][0] = s0; red[threadIdx.y][1] = s1; red[threadIdx.y][2] = s2; }
+  __syncthreads();
+  if (threadIdx.y == 0 && threadIdx.x < 3) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    if (t != 0.f) atomicAdd(mom + (size_t)e * 3 + threadIdx.x, (double)t);
+  }
+}
+
+// [E][4] = {short-exposure Strehl exp(-var k^2), long-exposure mean of it, phase variance, running mean variance};
+// acc [E][2] running sums of SE and var, n_le the number of accumulated frames including this one (0: no accumulation)
+__global__ void target_strehl_kernel(const double* mom, float* strehl, float* acc, int E, float k2, int n_le) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const double s0 = mom[e * 3], s1 = mom[e * 3 + 1], s2 = mom[e * 3 + 2];
+  float var = 0.f;
+  if (s0 > 0.0) {
+    const double mean = s1 / s0;
+    var = (float)fmax(s2 / s0 - mean * mean, 0.0);
+  }
+  const float se = expf(-var * k2 * k2);
+  strehl[e * 4 + 0] = se;
+  strehl[e * 4 + 2] = var;
+  if (n_le > 0) {
+    acc[e * 2 + 0] += se;
+    acc[e * 2 + 1] += var;
+    strehl[e * 4 + 1] = acc[e * 2 + 0] / (float)n_le;
+    strehl[e * 4 + 3] = acc[e * 2 + 1] / (float)n_le;
+  }
+}
+
 // Centre of gravity of an externally supplied detector cube [E][nvalid][256] (denoiser path).
 __global__ void cog_kernel(const float* cube, float* slopes, int lds, int nvalid, long long total,
                            float cog_offset, float pixsize) {

@@ -49,7 +49,7 @@ _INT_BUFFERS = {"RING_OX", "RING_OY"}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
            "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_wfs_time_ms", "aom_raytrace_wfs",
-           "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
+           "aom_comp_strehl", "aom_reset_strehl", "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
            "aom_set_gain", "aom_set_loop", "aom_reset_dm", "aom_set_dm_volts", "aom_rl_control",
            "aom_state_begin", "aom_state_end", "aom_reward", "aom_actor_forward", "aom_step", "aom_gemm_tn",
            "aom_pixel_noise"]
@@ -91,6 +91,8 @@ def load_library():
     lib.aom_wfs_time_ms.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32)]
     lib.aom_wfs_kernel.argtypes = [vp]
     lib.aom_wfs_kernel.restype = ctypes.c_char_p
+    lib.aom_comp_strehl.argtypes = [vp, i32, f32, i32, vp]
+    lib.aom_reset_strehl.argtypes = [vp, vp]
     lib.aom_set_bincube.argtypes = [vp, vp, vp]
     lib.aom_do_centroids.argtypes = [vp, vp]
     lib.aom_do_control.argtypes = [vp, vp]
@@ -363,6 +365,16 @@ class Simulator:
         flags = (1 if atmos else 0) | (2 if dms else 0)
         self._check(self.lib.aom_raytrace_wfs(self._ctx, flags, self.stream), "aom_raytrace_wfs")
         return self.buffer("PHASE").view(self.n_env, self.cfg.n, self.cfg.n)
+
+    def comp_strehl(self, lambda_um, atmos=True, dms=True, accumulate=True):
+        """Pupil phase variance -> AOM_B_STREHL [E, 4] = (SE, LE, variance, mean variance)."""
+        flags = (1 if atmos else 0) | (2 if dms else 0)
+        self._check(self.lib.aom_comp_strehl(self._ctx, flags, float(lambda_um), 1 if accumulate else 0, self.stream),
+                    "aom_comp_strehl")
+        return self.buffer("STREHL").view(self.n_env, 4)
+
+    def reset_strehl(self):
+        self._check(self.lib.aom_reset_strehl(self._ctx, self.stream), "aom_reset_strehl")
 
     def set_bincube(self, cube):
         self._cube_keepalive = cube

@@ -291,16 +291,12 @@ class RtcB200(_Base):
 class TargetB200(_Base):
     """targetCompass.py (next-row scope): Strehl from the residual phase variance over the pupil
     (Marechal, exp(-sigma^2)), which is what get_strehl()[2] reports in the reference too; the 2048^2 PSF
-    of comp_tar_image is not computed."""
+    of comp_tar_image is not computed.  One fused kernel pair (aom_comp_strehl) evaluates the on-axis phase per
+    pupil pixel and reduces it without materialising it; the short / long exposure figures live in AOM_B_STREHL."""
 
     def __init__(self, sim, config, tables):
         super().__init__(sim, config)
         self._tables = tables
-        self._n_le = 0
-        self._var = None
-        self._var_sum = None
-        self._se = None
-        self._le_sum = None
         self._flags = (False, False)
 
     def raytrace(self, index, *, tel=None, atm=None, dms=None, ncpa=True, reset=True):
@@ -312,37 +308,21 @@ class TargetB200(_Base):
         self._flags = (a, d)
 
     def comp_tar_image(self, tarNum, *, puponly=0, compLE=True):
-        import torch
-        sim, t = self._sim, self._tables
-        ph = sim.raytrace_wfs(atmos=self._flags[0], dms=self._flags[1])
-        pup = torch.as_tensor(t.mpupil, device=ph.device) > 0
-        v = ph[:, pup]
-        self._var = v.var(dim=1, unbiased=False)
         lam = float(self._config.p_targets[tarNum].Lambda)
-        self._se = torch.exp(-self._var * (2 * np.pi / lam) ** 2)
-        if compLE:
-            self._le_sum = self._se.clone() if self._le_sum is None else self._le_sum + self._se
-            self._var_sum = self._var.clone() if self._var_sum is None else self._var_sum + self._var
-            self._n_le += 1
+        self._sim.comp_strehl(lam, atmos=self._flags[0], dms=self._flags[1], accumulate=bool(compLE))
 
     def comp_strehl(self, tarNum, *, do_fit=True):
         pass
 
     def reset_strehl(self, tar_index):
-        self._n_le = 0
-        self._le_sum = self._var_sum = None
+        self._sim.reset_strehl()
 
     def get_strehl(self, tar_index, *, do_fit=True):
-        import torch
-        z = torch.zeros(self._sim.n_env, device="cuda")
-        se = self._se if self._se is not None else z
-        le = self._le_sum / self._n_le if self._n_le else z
-        var = self._var if self._var is not None else z
-        avg = self._var_sum / self._n_le if self._n_le else z
-        out = [se, le, var, avg]
+        """[SE, LE, variance, mean variance]: floats when E == 1 (targetCompass.py:139-159), else [E] device tensors."""
+        s = self._sim.buffer("STREHL").view(self._sim.n_env, 4)
         if self._sim.n_env == 1:
-            return [float(x[0]) for x in out]
-        return out
+            return [float(x) for x in s[0].cpu()]
+        return [s[:, i] for i in range(4)]
 
     def get_tar_image(self, tar_index, *, expo_type="se"):
         raise NotImplementedError("the focal-plane PSF is outside the hot-path scope (SURVEY.md 8(f) rank 1)")

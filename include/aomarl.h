@@ -201,6 +201,13 @@ int aom_wfs_time_ms(aom_ctx* ctx, float* mean_ms, int* count);
 /* Materialise the pupil-plane phase seen by the sensor (wfs.get_wfs_phase) into AOM_B_PHASE. */
 int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream);
 
+/* TargetCompass.comp_tar_image / comp_strehl / get_strehl (targetCompass.py:139-196), Marechal form: the phase
+ * of aom_raytrace_wfs is reduced over the pupil on the fly and AOM_B_STREHL = {SE, LE, variance, mean variance}
+ * with SE = exp(-var (2 pi / lambda)^2).  flags as aom_comp_wfs_image (bit0 atmosphere, bit1 mirrors);
+ * accumulate != 0 adds the frame to the long-exposure means.  The 2048^2 focal-plane PSF is not computed. */
+int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int accumulate, void* stream);
+int aom_reset_strehl(aom_ctx* ctx, void* stream);     /* TargetCompass.reset_strehl */
+
 /* Replace the detector image (RlSupervisor.autoencoder_denoising -> set_binimg, rlSupervisor.py:876-891):
  * device pointer to float [E][nvalid][npix*npix]; the next aom_do_centroids reads it. */
 int aom_set_bincube(aom_ctx* ctx, const float* dcube, void* stream);

@@ -607,3 +607,30 @@ def test_normalization_producer_against_reference_statistics(static10, oracle_im
                   norm={k: {s: z["%s_%s" % (k, s)] for s in ("mean", "std", "max", "min")}
                         for k in ("dm", "wfs", "dm_residual")}, zn_norm=z["zn_norm"])
     assert rl.state_dim == 4 * 82 and np.isfinite(rl.freedom).all()
+
+
+def test_strehl_kernel_matches_the_materialised_phase(sim10, static10, torch):
+    """aom_comp_strehl (phase evaluated and reduced on the fly) against the variance of the materialised pupil
+    phase; long-exposure means over frames; reset."""
+    seeds = np.array([41, 42, 43, 44], dtype=np.int64)
+    sim10.reset(seeds)
+    r = np.random.default_rng(4)
+    sim10.set_dm_volts(torch.as_tensor((r.standard_normal((4, static10.nactu)) * 5).astype(np.float32), device="cuda"))
+    lam = 1.65
+    pup = torch.as_tensor(static10.mpupil, device="cuda") > 0
+    se_hist, var_hist = [], []
+    for it in range(3):
+        sim10.move_atmos()
+        s = sim10.comp_strehl(lam).clone()
+        ph = sim10.raytrace_wfs()
+        var = ph[:, pup].double().var(dim=1, unbiased=False).float()
+        se = torch.exp(-var * (2 * np.pi / lam) ** 2)
+        assert float((s[:, 2] - var).abs().max()) < 2e-5 * float(var.max())
+        assert float((s[:, 0] - se).abs().max()) < 1e-5
+        se_hist.append(se)
+        var_hist.append(var)
+        assert float((s[:, 1] - torch.stack(se_hist).mean(0)).abs().max()) < 1e-5
+        assert float((s[:, 3] - torch.stack(var_hist).mean(0)).abs().max()) < 2e-5 * float(var.max())
+    sim10.reset_strehl()
+    assert float(sim10.buffer("STREHL").abs().max()) == 0.0
+    sim10.check_device()
