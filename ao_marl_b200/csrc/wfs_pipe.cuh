@@ -444,8 +444,9 @@ __global__ void __launch_bounds__(WFT_WARPS * 32, 2) wfs_frame_pipe_kernel(const
       sy += __shfl_xor_sync(0xffffffffu, sy, sft);
     }
     if (lane == 0) {
-      const float gx = (s0 > 0.f) ? sx / s0 : p.cog_offset;
-      const float gy = (s0 > 0.f) ? sy / s0 : p.cog_offset;
+      const float inv = __frcp_rn(s0);
+      const float gx = (s0 > 0.f) ? sx * inv : p.cog_offset;
+      const float gy = (s0 > 0.f) ? sy * inv : p.cog_offset;
       float* sl = p.slopes + (size_t)cur.e * p.lds;
       sl[cur.k] = (gx - p.cog_offset) * p.pixsize;
       sl[p.nvalid + cur.k] = (gy - p.cog_offset) * p.pixsize;

@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(WTC_WARPS * 32, 1) wfs_frame_tc_kernel(const _
       sy += __shfl_xor_sync(0xffffffffu, sy, sft);
     }
     if (lane == 0) {
-      const float gx = (s0 > 0.f) ? sx / s0 : p.cog_offset;
-      const float gy = (s0 > 0.f) ? sy / s0 : p.cog_offset;
+      const float inv = __frcp_rn(s0);
+      const float gx = (s0 > 0.f) ? sx * inv : p.cog_offset;
+      const float gy = (s0 > 0.f) ? sy * inv : p.cog_offset;
       float* sl = p.slopes + (size_t)ie * p.lds;
       sl[ik] = (gx - p.cog_offset) * p.pixsize;
       sl[p.nvalid + ik] = (gy - p.cog_offset) * p.pixsize;
