@@ -326,6 +326,39 @@ def test_delay_impulse(system10, torch):
         sim.set_loop(True)
 
 
+def test_delay_zero_impulse(static10, oracle_imat10, torch):
+    """Same impulse with a delay-0 controller (the *_d0_noise parameter files): it shows one frame earlier."""
+    import copy
+    from ao_marl_b200.init import rtc as rtc_b
+    from ao_marl_b200.lib import Simulator
+    from ao_marl_b200.rl.layout import RLLayout
+    t = copy.copy(static10)
+    t.delay = 0.0
+    t.imat = oracle_imat10
+    t.cmat = rtc_b.cmat_with_btt(t.imat, t.Btt, 5)
+    rl = RLLayout(t.Btt.shape[1], dict(parameters_telescope="production_sh_10x10_2m.py", n_zernike_start_end=[0, 80],
+                                       n_reverse_filtered_from_cmat=5), None, world_size=3, seed=3)
+    sim = Simulator(t, 3, rl)
+    try:
+        assert sim.cfg.delay == 0
+        sim.reset(np.array([5, 5, 5], dtype=np.int64))
+        sim.set_loop(False)
+        errs = []
+        for it in range(4):
+            a = torch.zeros((3, rl.action_dim), device="cuda")
+            if it == 1:
+                a[1, 0] = 5.0
+            sim.rows("ACTION", rl.action_dim).copy_(a)
+            sim.step(mode=1)
+            e = sim.rows("ERR", t.nactu)
+            errs.append(float((e[1] - e[0]).abs().max()))
+        assert errs[0] == 0.0
+        assert errs[1] > 0.0                 # the frame of the action step itself
+        sim.check_device()
+    finally:
+        sim.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # Full-size configuration (production_sh_40x40_8m_3layers, 1200 subapertures, 1286 actuators, 3 layers,
 # 43 windowed agents): the oracle needs minutes per frame here, so the checks are size-independent properties.
