@@ -419,13 +419,12 @@ static int extrude_once(aom_ctx* ctx, int l, int axis, int sign, cudaStream_t st
   p.N = c.screen_dim[l]; p.S = c.stencil_size[l]; p.E = c.n_env; p.layer = l; p.axis = axis; p.sign = sign;
   p.amp = c.amp[l];
   p.ldz = AOM_LD(p.S + p.N); p.Z = ctx->Z; p.zref = ctx->zref; p.ldn = AOM_LD(p.N); p.newcol = ctx->newcol;
-  dim3 g1((p.ldz + 255) / 256, c.n_env);
-  extrude_gather_kernel<<<g1, 256, 0, st>>>(p);
+  extrude_gather_kernel<<<c.n_env, 256, 0, st>>>(p);
   KCHECK();
   int rc = launch_gemm(ctx, 0, ctx->Z, p.ldz, 0, (const float*)ctx->tab[AOM_T_AB][l], p.ldz, 0, ctx->newcol, p.ldn, 0,
                        c.n_env, p.N, p.S + p.N, nullptr, 0, 0, 1, st, nullptr, 0, true);
   if (rc) return rc;
-  extrude_scatter_kernel<<<c.n_env, 256, 0, st>>>(p);
+  extrude_scatter_kernel<<<(c.n_env + 7) / 8, 256, 0, st>>>(p);
   KCHECK();
   return AOM_OK;
 }

@@ -35,11 +35,12 @@ __device__ __forceinline__ void extr_logical(int r, int c, int N, int axis, int 
 
 __device__ __forceinline__ int wrapN(int v, int N) { return v >= N ? v - N : v; }
 
-// grid: (ceil(ldz/256), E)
-__global__ void extrude_gather_kernel(ExtrudeParams p) {
-  const int e = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.ldz) return;
+// grid: E blocks of 256 threads.  One block walks the whole input vector of its environment: the per-element
+// dependent chain (stencil index -> screen pixel) is pipelined over ~5 iterations per thread instead of being paid
+// once per 256-thread block (32 k tiny blocks per launch were block-latency bound: 75 us per launch), and one
+// Philox block yields its four innovations instead of one.
+__global__ void __launch_bounds__(256) extrude_gather_kernel(ExtrudeParams p) {
+  const int e = blockIdx.x;
   const int N = p.N;
   const float* scr = p.screen + (size_t)e * N * N;
   const int ox = p.ox[e], oy = p.oy[e];
@@ -47,48 +48,57 @@ __global__ void extrude_gather_kernel(ExtrudeParams p) {
   int rr, rc;
   extr_logical(0, N - 1, N, p.axis, p.sign, rr, rc);
   const float zr = scr[(size_t)wrapN(rr + oy, N) * N + wrapN(rc + ox, N)];
-  if (k == 0) p.zref[e] = zr;
-  float v = 0.f;
-  if (k < p.S) {
-    int idx = p.stencil[k];
+  if (threadIdx.x == 0) p.zref[e] = zr;
+  float* Z = p.Z + (size_t)e * p.ldz;
+  for (int k = threadIdx.x; k < p.S; k += blockDim.x) {
+    const int idx = p.stencil[k];
     int lr, lc;
     extr_logical(idx / N, idx % N, N, p.axis, p.sign, lr, lc);
-    v = scr[(size_t)wrapN(lr + oy, N) * N + wrapN(lc + ox, N)] - zr;
-  } else if (k < p.S + N) {
-    int j = k - p.S;
-    aom_u4 w = aom_philox((uint32_t)(j >> 2), p.count[e], AOM_TAG_ATMOS, (uint32_t)p.layer, p.k0[e], p.k1[e]);
-    v = aom_mul(aom_normal_of_block(w, j & 3), p.amp);
+    Z[k] = scr[(size_t)wrapN(lr + oy, N) * N + wrapN(lc + ox, N)] - zr;
   }
-  p.Z[(size_t)e * p.ldz + k] = v;
+  const uint32_t cnt = p.count[e], k0 = p.k0[e], k1 = p.k1[e];
+  for (int b = threadIdx.x; 4 * b < N; b += blockDim.x) {
+    const aom_u4 w = aom_philox((uint32_t)b, cnt, AOM_TAG_ATMOS, (uint32_t)p.layer, k0, k1);
+    float z[4];
+    aom_normal_pair(w.x, w.y, z[0], z[1]);
+    aom_normal_pair(w.z, w.w, z[2], z[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (4 * b + i < N) Z[p.S + 4 * b + i] = aom_mul(z[i], p.amp);
+  }
+  for (int k = p.S + N + threadIdx.x; k < p.ldz; k += blockDim.x) Z[k] = 0.f;
 }
 
-// grid: E blocks of 256 threads
-__global__ void extrude_scatter_kernel(ExtrudeParams p) {
-  const int e = blockIdx.x;
+// grid: ceil(E / 8) blocks of 256 threads, one warp per environment (no block-wide barrier; 4096 one-environment
+// blocks with two barriers each were block-latency bound: 73 us per launch for 2.6 M stores).
+__global__ void __launch_bounds__(256) extrude_scatter_kernel(ExtrudeParams p) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= p.E) return;
+  const int lane = threadIdx.x & 31;
   const int N = p.N;
   float* scr = p.screen + (size_t)e * N * N;
   const int ox = p.ox[e], oy = p.oy[e];
   const float zr = p.zref[e];
-  __syncthreads();
+  __syncwarp();                                              // every lane holds the old ring origin
   int nox = ox, noy = oy;
   if (p.axis == 0) nox = (p.sign > 0) ? wrapN(ox + 1, N) : (ox == 0 ? N - 1 : ox - 1);
   else             noy = (p.sign > 0) ? wrapN(oy + 1, N) : (oy == 0 ? N - 1 : oy - 1);
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    float v = p.newcol[(size_t)e * p.ldn + j] + zr;
+  const float* col = p.newcol + (size_t)e * p.ldn;
+  for (int j = lane; j < N; j += 32) {
+    const float v = col[j] + zr;
     size_t addr;
     if (p.axis == 0) {
-      int pc = (p.sign > 0) ? ox : nox;                       // new logical column N-1 (or 0)
-      int lr = (p.sign > 0) ? j : N - 1 - j;
+      const int pc = (p.sign > 0) ? ox : nox;                 // new logical column N-1 (or 0)
+      const int lr = (p.sign > 0) ? j : N - 1 - j;
       addr = (size_t)wrapN(lr + oy, N) * N + pc;
     } else {
-      int pr = (p.sign > 0) ? oy : noy;                       // new logical row N-1 (or 0)
-      int lc = (p.sign > 0) ? j : N - 1 - j;
+      const int pr = (p.sign > 0) ? oy : noy;                 // new logical row N-1 (or 0)
+      const int lc = (p.sign > 0) ? j : N - 1 - j;
       addr = (size_t)pr * N + wrapN(lc + ox, N);
     }
     scr[addr] = v;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     p.ox[e] = nox;
     p.oy[e] = noy;
     p.count[e] += 1;
