@@ -1171,9 +1171,8 @@ extern "C" int aom_actor_forward(aom_ctx* ctx, int eval_mode, void* stream) {
   NEED(AOM_T_AGENT_IDX, 0); NEED(AOM_T_AGENT_ACT, 0); NEED(AOM_T_ACTOR_W1, 0); NEED(AOM_T_ACTOR_B1, 0);
   NEED(AOM_T_ACTOR_W2, 0); NEED(AOM_T_ACTOR_B2, 0); NEED(AOM_T_ACTOR_WH, 0); NEED(AOM_T_ACTOR_BH, 0);
   const int E = c.n_env, A = c.n_agents;
-  dim3 g((ctx->ld_ain + 127) / 128, E, A);
-  actor_gather_kernel<<<g, 128, 0, st>>>(ctx->state, ctx->ldst, (const int*)ctx->tab[AOM_T_AGENT_IDX][0], c.actor_in,
-                                         ctx->ld_ain, E, ctx->aX);
+  actor_gather_kernel<<<E, 256, 0, st>>>(ctx->state, ctx->ldst, (const int*)ctx->tab[AOM_T_AGENT_IDX][0], c.actor_in,
+                                         ctx->ld_ain, E, A, ctx->aX);
   KCHECK();
   int rc = launch_gemm(ctx, 0, ctx->aX, ctx->ld_ain, (long long)E * ctx->ld_ain, (const float*)ctx->tab[AOM_T_ACTOR_W1][0],
                        ctx->ld_ain, (long long)c.actor_hidden * ctx->ld_ain, ctx->aH1, ctx->ld_ah, (long long)E * ctx->ld_ah, E,
@@ -1187,8 +1186,7 @@ extern "C" int aom_actor_forward(aom_ctx* ctx, int eval_mode, void* stream) {
                    (long long)2 * c.actor_out * ctx->ld_ah, ctx->aHO, ctx->ld_aho, (long long)E * ctx->ld_aho, E, 2 * c.actor_out,
                    c.actor_hidden, (const float*)ctx->tab[AOM_T_ACTOR_BH][0], 2 * c.actor_out, 0, A, st);
   if (rc) return rc;
-  dim3 g2((c.actor_out + 63) / 64, E, A);
-  actor_sample_kernel<<<g2, 64, 0, st>>>(ctx->aHO, ctx->ld_aho, c.actor_out, (const int*)ctx->tab[AOM_T_AGENT_ACT][0], E, A,
+  actor_sample_kernel<<<E, 256, 0, st>>>(ctx->aHO, ctx->ld_aho, c.actor_out, (const int*)ctx->tab[AOM_T_AGENT_ACT][0], E, A,
                                          c.log_sig_min, c.log_sig_max, c.pol_act_scale, c.pol_act_bias, eval_mode, ctx->step,
                                          ctx->k0, ctx->k1, ctx->action, ctx->action_mean, ctx->ldact);
   KCHECK();

@@ -72,39 +72,51 @@ __global__ void reward_kernel(const float* modes_res, int ldm, const int* ranges
 }
 
 // TrainerRPC.divide_states_for_agents (train_rpc.py:418-427): X[a][e][i] = state[e][idx[a][i]]
-__global__ void actor_gather_kernel(const float* state, int lds, const int* idx, int actor_in, int ldx,
-                                    int E, float* X) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int e = blockIdx.y, a = blockIdx.z;
-  if (i >= ldx) return;
-  float v = 0.f;
-  if (i < actor_in) {
-    int s = idx[(size_t)a * actor_in + i];
-    if (s >= 0) v = state[(size_t)e * lds + s];
+// grid: E blocks of 256 threads; one block serves all agents of its environment (the state row stays in L1, the
+// per-agent rows are written as contiguous runs) -- half a million 128-thread blocks were block-latency bound.
+__global__ void __launch_bounds__(256) actor_gather_kernel(const float* __restrict__ state, int lds,
+                                                           const int* __restrict__ idx, int actor_in, int ldx, int E,
+                                                           int n_agents, float* __restrict__ X) {
+  const int e = blockIdx.x;
+  const float* srow = state + (size_t)e * lds;
+  const int total = n_agents * ldx;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int a = t / ldx, i = t - a * ldx;
+    float v = 0.f;
+    if (i < actor_in) {
+      const int s = __ldg(idx + (size_t)a * actor_in + i);
+      if (s >= 0) v = srow[s];
+    }
+    X[((size_t)a * E + e) * ldx + i] = v;
   }
-  X[((size_t)a * E + e) * ldx + i] = v;
 }
 
 // GaussianPolicy.sample(only_choosing_action=True) + TrainerRPC.report_action
 // (model_rpc.py:131-144, train_rpc.py:667-675).  heads[a][e][0:out] = mean, [out:2 out] = log std.
-__global__ void actor_sample_kernel(const float* heads, int ldh, int actor_out, const int* act_slot, int E,
-                                    int n_agents, float log_sig_min, float log_sig_max, float act_scale,
-                                    float act_bias, int eval_mode, uint32_t step, const uint32_t* k0,
-                                    const uint32_t* k1, float* action, float* action_mean, int lda) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  int e = blockIdx.y, a = blockIdx.z;
-  if (j >= actor_out) return;
-  int slot = act_slot[(size_t)a * actor_out + j];
-  if (slot < 0) return;
-  const float* h = heads + ((size_t)a * E + e) * ldh;
-  float mu = h[j];
-  float ls = fminf(fmaxf(h[actor_out + j], log_sig_min), log_sig_max);
-  aom_u4 w = aom_philox((uint32_t)(j >> 2), step, AOM_TAG_ACTOR, (uint32_t)a, k0[e], k1[e]);
-  float eps = aom_normal_of_block(w, j & 3);
-  float act = tanhf(mu + expf(ls) * eps) * act_scale + act_bias;
-  float mean = tanhf(mu) * act_scale + act_bias;
-  action[(size_t)e * lda + slot] = eval_mode ? mean : act;
-  action_mean[(size_t)e * lda + slot] = mean;
+// grid: E blocks of 256 threads, every block loops over (agent, output).
+__global__ void __launch_bounds__(256) actor_sample_kernel(const float* __restrict__ heads, int ldh, int actor_out,
+                                                           const int* __restrict__ act_slot, int E, int n_agents,
+                                                           float log_sig_min, float log_sig_max, float act_scale,
+                                                           float act_bias, int eval_mode, uint32_t step,
+                                                           const uint32_t* k0, const uint32_t* k1, float* action,
+                                                           float* action_mean, int lda) {
+  const int e = blockIdx.x;
+  const uint32_t key0 = k0[e], key1 = k1[e];
+  const int total = n_agents * actor_out;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int a = t / actor_out, j = t - a * actor_out;
+    const int slot = __ldg(act_slot + (size_t)a * actor_out + j);
+    if (slot < 0) continue;
+    const float* h = heads + ((size_t)a * E + e) * ldh;
+    const float mu = h[j];
+    const float ls = fminf(fmaxf(h[actor_out + j], log_sig_min), log_sig_max);
+    const aom_u4 w = aom_philox((uint32_t)(j >> 2), step, AOM_TAG_ACTOR, (uint32_t)a, key0, key1);
+    const float eps = aom_normal_of_block(w, j & 3);
+    const float act = tanhf(mu + expf(ls) * eps) * act_scale + act_bias;
+    const float mean = tanhf(mu) * act_scale + act_bias;
+    action[(size_t)e * lda + slot] = eval_mode ? mean : act;
+    action_mean[(size_t)e * lda + slot] = mean;
+  }
 }
 
 __global__ void pixel_noise_kernel(const float* lam, float* out, long long n, float noise, uint32_t k0,
