@@ -16,6 +16,8 @@
 #include "wfs_tma.cuh"
 #include "wfs_pipe.cuh"
 #include "wfs_tc.cuh"
+#include "geo_kernels.cuh"
+#include "pupil_sweep.cuh"
 
 static char g_create_error[512] = "";
 
@@ -44,6 +46,16 @@ struct aom_ctx {
   double* tar_mom;            // [E][3] pupil sums of the target phase (aom_comp_strehl)
   float* tar_acc;             // [E][2] running sums for the long-exposure figures
   int tar_n;
+  // geometric controller (geo_kernels.cuh), allocated on first use
+  float *geo_com, *geo_volts, *geo_b, *geo_T, *strehl_geo, *geo_acc;
+  double* geo_mom;            // [E][4] pupil sums of m phi, m phi tt_x, m phi tt_y
+  int geo_gp, geo_tar_n;
+  cudaEvent_t ev_geo;
+  // pupil sweep (pupil_sweep.cuh): mask / tip-tilt planes repacked in the lattice frame
+  int sweep_state;            // 0 = not prepared, 1 = eligible, -1 = not eligible
+  uint32_t* sweep_mask;
+  float* sweep_ttp;
+  int sweep_nb;               // 128-pixel column blocks per pupil row
   int lds, lda, ldm;
   float gain;
   int closed;
@@ -226,7 +238,9 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
   void* bufs[] = {ctx->k0, ctx->k1, ctx->Z, ctx->zref, ctx->newcol, ctx->slopes_frame, ctx->slopes, ctx->err_v,
                   ctx->com, ctx->com1, ctx->volts, ctx->com_before, ctx->bincube, ctx->phase, ctx->modes,
                   ctx->modes_before, ctx->modes_res, ctx->state, ctx->hist, ctx->reward, ctx->action,
-                  ctx->action_mean, ctx->strehl, ctx->tar_mom, ctx->tar_acc, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO, ctx->d_err};
+                  ctx->action_mean, ctx->strehl, ctx->tar_mom, ctx->tar_acc, ctx->aX, ctx->aH1, ctx->aH2, ctx->aHO, ctx->d_err,
+                  ctx->geo_com, ctx->geo_volts, ctx->geo_b, ctx->geo_T, ctx->strehl_geo, ctx->geo_acc, ctx->geo_mom,
+                  ctx->sweep_mask, ctx->sweep_ttp};
   for (void* b : bufs) cudaFree(b);
   for (void* b : ctx->fast_dev) cudaFree(b);
   for (int i = 0; i < AOM_WFS_TIMERS; ++i)
@@ -235,6 +249,7 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_geo) cudaEventDestroy(ctx->ev_geo);
   for (int t = 0; t < AOM_T_COUNT; ++t) free(ctx->htab[t]);
   free(ctx);
 }
@@ -266,6 +281,8 @@ static size_t table_expected_bytes(const aom_ctx* ctx, int t, int index) {
     case AOM_T_ACTOR_W2: return A * c.actor_hidden * AOM_LD(c.actor_hidden) * 4;
     case AOM_T_ACTOR_WH: return A * 2 * c.actor_out * AOM_LD(c.actor_hidden) * 4;
     case AOM_T_ACTOR_BH: return A * 2 * c.actor_out * 4;
+    case AOM_T_GEO_PROJ: return (size_t)c.nactu * AOM_LD(c.nactu) * 4;
+    case AOM_T_GEO_SIFN: return (size_t)c.nactu * 4;
   }
   return 0;
 }
@@ -290,6 +307,7 @@ extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* hos
     ctx->htab_bytes[table] = nbytes;
     ctx->fast_state = 0;     // derived tables of the TMA-staged sensor kernel are rebuilt on the next frame
   }
+  if (table == AOM_T_MPUPIL || table == AOM_T_TT_PLANES) ctx->sweep_state = 0;
   return AOM_OK;
 }
 
@@ -301,6 +319,88 @@ extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* hos
 extern "C" int aom_device_count_launches(const aom_ctx* ctx, uint64_t* n) {
   if (!ctx || !n) return AOM_ERR_INVALID;
   *n = ctx->launches;
+  return AOM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pupil sweep: eligibility, repacked tables, launch
+static int fill_wfs_params(aom_ctx* ctx, WfsParams& p, int flags, float noise);
+
+static int sweep_prepare(aom_ctx* ctx, cudaStream_t st) {
+  if (ctx->sweep_state) return AOM_OK;
+  const aom_config& c = ctx->cfg;
+  ctx->sweep_state = -1;
+  const int xs0 = c.pzt_i1_0 - c.pzt_off, ys0 = c.pzt_j1_0 - c.pzt_off;
+  if (c.pzt_pitch != 16 || c.stamp_size > 64 || xs0 > 0 || ys0 > 0 || c.n_layers > 4 || !ctx->tab[AOM_T_TT_PLANES][0] ||
+      !ctx->tab[AOM_T_STAMP1D][0] || !ctx->tab[AOM_T_ACT_MAP][0])
+    return AOM_OK;
+  for (int l = 0; l < c.n_layers; ++l)
+    if ((c.screen_dim[l] & 3) || c.screen_dim[l] < PSW_BW) return AOM_OK;
+  const int nb = (c.n - xs0 + 127) / 128;
+  ctx->sweep_nb = nb;
+  cudaFree(ctx->sweep_mask); cudaFree(ctx->sweep_ttp);
+  ctx->sweep_mask = nullptr; ctx->sweep_ttp = nullptr;
+  CU(cudaMalloc((void**)&ctx->sweep_mask, (size_t)c.n * 32 * nb * sizeof(uint32_t)));
+  CU(cudaMalloc((void**)&ctx->sweep_ttp, (size_t)2 * c.n * 128 * nb * sizeof(float)));
+  WfsParams p;
+  int rc = fill_wfs_params(ctx, p, 2, -1.f);
+  if (rc) return rc;
+  sweep_tables_kernel<<<c.n, 128, 0, st>>>(p, ctx->sweep_mask, ctx->sweep_ttp, nb);
+  KCHECK();
+  CU(cudaStreamSynchronize(st));     // one-time: later sweeps may run on another stream (aom_step's second stream)
+  ctx->sweep_state = 1;
+  return AOM_OK;
+}
+
+template <int NL, int MODE>
+static int sweep_launch_t(aom_ctx* ctx, const SweepParams& P, cudaStream_t st) {
+  const size_t smem = psw_smem_bytes(NL);
+  CU(cudaFuncSetAttribute(pupil_sweep_kernel<NL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((P.n_strips * P.nb + PSW_WARPS - 1) / PSW_WARPS, P.w.E);
+  pupil_sweep_kernel<NL, MODE><<<grid, PSW_WARPS * 32, smem, st>>>(P);
+  KCHECK();
+  return AOM_OK;
+}
+
+// MODE 0: Tp / mom = geometric projection ; MODE 1: mom = pupil sums of m, m phi, m phi^2
+template <int MODE>
+static int sweep_launch(aom_ctx* ctx, const WfsParams& w, float* Tp, double* mom, cudaStream_t st) {
+  const aom_config& c = ctx->cfg;
+  SweepParams P;
+  memset(&P, 0, sizeof(P));
+  P.w = w;
+  P.maskw = ctx->sweep_mask; P.ttp = ctx->sweep_ttp;
+  P.Tp = Tp; P.mom = mom;
+  P.nb = ctx->sweep_nb;
+  P.n_strips = (c.n + PSW_STRIP - 1) / PSW_STRIP;
+  P.err = ctx->d_err;
+  switch (w.n_layers) {
+    case 0: case 1: return sweep_launch_t<1, MODE>(ctx, P, st);
+    case 2: return sweep_launch_t<2, MODE>(ctx, P, st);
+    case 3: return sweep_launch_t<3, MODE>(ctx, P, st);
+    default: return sweep_launch_t<4, MODE>(ctx, P, st);
+  }
+}
+
+// buffers of the geometric controller (only configurations that use it pay for them)
+static int geo_prepare(aom_ctx* ctx) {
+  if (ctx->geo_com) return AOM_OK;
+  const aom_config& c = ctx->cfg;
+  const size_t E = c.n_env;
+  if (c.pzt_grid_n < 1 || c.pzt_pitch < 1) return fail(ctx, AOM_ERR_UNSUPPORTED, "geometric controller needs the actuator lattice");
+  ctx->geo_gp = AOM_LD(c.pzt_grid_n);
+  CU(dalloc(&ctx->geo_volts, E * ctx->lda));
+  CU(dalloc(&ctx->geo_b, E * ctx->lda));
+  {
+    // lattice-column sums of every pupil row: [E][n][gp], or the sweep's per-block partials [E][n][nb][PSW_TP]
+    const size_t per_row = (size_t)ctx->geo_gp > (size_t)((c.n + 64 + 127) / 128 + 1) * PSW_TP ? (size_t)ctx->geo_gp : (size_t)((c.n + 64 + 127) / 128 + 1) * PSW_TP;
+    CU(dalloc(&ctx->geo_T, E * c.n * per_row));
+  }
+  CU(dalloc(&ctx->geo_mom, E * 4));
+  CU(dalloc(&ctx->strehl_geo, E * 4));
+  CU(dalloc(&ctx->geo_acc, E * 2));
+  CU(cudaEventCreateWithFlags(&ctx->ev_geo, cudaEventDisableTiming));
+  CU(dalloc(&ctx->geo_com, E * ctx->lda));
   return AOM_OK;
 }
 
@@ -337,6 +437,13 @@ extern "C" int aom_get_buffer(aom_ctx* ctx, int buffer, int index, void** dptr, 
     case AOM_B_ACTION: p = ctx->action; n = E * ctx->ldact; break;
     case AOM_B_ACTION_MEAN: p = ctx->action_mean; n = E * ctx->ldact; break;
     case AOM_B_STREHL: p = ctx->strehl; n = E * 4; break;
+    case AOM_B_GEO_COM: case AOM_B_GEO_VOLTS: case AOM_B_STREHL_GEO: case AOM_B_GEO_PROJ: {
+      int rc = geo_prepare(ctx);
+      if (rc) return rc;
+      if (buffer == AOM_B_STREHL_GEO) { p = ctx->strehl_geo; n = E * 4; }
+      else { p = buffer == AOM_B_GEO_COM ? ctx->geo_com : buffer == AOM_B_GEO_VOLTS ? ctx->geo_volts : ctx->geo_b; n = E * ctx->lda; }
+      break;
+    }
     default: return fail(ctx, AOM_ERR_INVALID, "unknown buffer id %d", buffer);
   }
   if (!p) return fail(ctx, AOM_ERR_STATE, "buffer %d is not allocated for this configuration", buffer);
@@ -465,6 +572,13 @@ static int clear_loop_state(aom_ctx* ctx, cudaStream_t st) {
   ctx->tar_n = 0;
   CU(cudaMemsetAsync(ctx->tar_acc, 0, E * 2 * sizeof(float), st));
   CU(cudaMemsetAsync(ctx->strehl, 0, E * 4 * sizeof(float), st));
+  if (ctx->geo_com) {
+    ctx->geo_tar_n = 0;
+    CU(cudaMemsetAsync(ctx->geo_com, 0, E * ctx->lda * 4, st));
+    CU(cudaMemsetAsync(ctx->geo_volts, 0, E * ctx->lda * 4, st));
+    CU(cudaMemsetAsync(ctx->geo_acc, 0, E * 2 * sizeof(float), st));
+    CU(cudaMemsetAsync(ctx->strehl_geo, 0, E * 4 * sizeof(float), st));
+  }
   return AOM_OK;
 }
 
@@ -964,14 +1078,72 @@ extern "C" int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int acc
   WfsParams p;
   int rc = fill_wfs_params(ctx, p, flags, -1.f);
   if (rc) return rc;
+  const bool geo = (flags & AOM_TAR_GEO) != 0;
+  if (geo) {
+    rc = geo_prepare(ctx);
+    if (rc) return rc;
+    p.volts = ctx->geo_volts;
+  }
+  int& n_le = geo ? ctx->geo_tar_n : ctx->tar_n;
   CU(cudaMemsetAsync(ctx->tar_mom, 0, (size_t)c.n_env * 3 * sizeof(double), st));
-  dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
-  target_moments_kernel<<<grid, blk, 0, st>>>(p, ctx->tar_mom);
+  rc = sweep_prepare(ctx, st);
+  if (rc) return rc;
+  if (ctx->sweep_state == 1 && ctx->opt[AOM_OPT_PUPIL_PATH] == AOM_PUPIL_SWEEP) {
+    rc = sweep_launch<1>(ctx, p, nullptr, ctx->tar_mom, st);
+    if (rc) return rc;
+  } else {
+    dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
+    target_moments_kernel<<<grid, blk, 0, st>>>(p, ctx->tar_mom);
+    KCHECK();
+  }
+  if (accumulate) n_le += 1;
+  target_strehl_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(ctx->tar_mom, geo ? ctx->strehl_geo : ctx->strehl,
+                                                             geo ? ctx->geo_acc : ctx->tar_acc, c.n_env,
+                                                             (float)(2.0 * M_PI / (double)lambda_um), accumulate ? n_le : 0);
   KCHECK();
-  if (accumulate) ctx->tar_n += 1;
-  target_strehl_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(ctx->tar_mom, ctx->strehl, ctx->tar_acc, c.n_env,
-                                                             (float)(2.0 * M_PI / (double)lambda_um), accumulate ? ctx->tar_n : 0);
+  return AOM_OK;
+}
+
+extern "C" int aom_do_control_geo(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const aom_config& c = ctx->cfg;
+  NEED(AOM_T_GEO_PROJ, 0); NEED(AOM_T_GEO_SIFN, 0);
+  int rc = geo_prepare(ctx);
+  if (rc) return rc;
+  WfsParams p;
+  rc = fill_wfs_params(ctx, p, 1 | 2, -1.f);      // the mirrors' tables are needed, their voltages are not read
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->geo_mom, 0, (size_t)c.n_env * 4 * sizeof(double), st));
+  rc = sweep_prepare(ctx, st);
+  if (rc) return rc;
+  int nb = 0;
+  if (ctx->sweep_state == 1 && ctx->opt[AOM_OPT_PUPIL_PATH] == AOM_PUPIL_SWEEP) {
+    rc = sweep_launch<0>(ctx, p, ctx->geo_T, ctx->geo_mom, st);
+    if (rc) return rc;
+    nb = ctx->sweep_nb;
+  } else {
+    const size_t smem = (size_t)GEO_ROW_WARPS * (c.n + (c.n >> 4) + 2) * sizeof(float);
+    dim3 grid((c.n + GEO_ROW_WARPS - 1) / GEO_ROW_WARPS, c.n_env);
+    geo_rows_kernel<<<grid, GEO_ROW_WARPS * 32, smem, st>>>(p, ctx->geo_T, ctx->geo_gp, ctx->geo_mom);
+    KCHECK();
+  }
+  geo_cols_kernel<<<c.n_env, 256, 0, st>>>(p, ctx->geo_T, ctx->geo_gp, nb, ctx->geo_mom,
+                                           (const float*)ctx->tab[AOM_T_GEO_SIFN][0], ctx->geo_b, ctx->lda);
   KCHECK();
+  // exact float32 FFMA accumulation: the tip-tilt entries of b are 100x the piezo ones and the product cancels to
+  // ~1e-3 of its largest terms; the tensor core's truncated accumulator left 3 % errors in the commands (measured,
+  // profiles/dev/geo_probe.py).  The reference inverts and multiplies in double (sutra_controller_geo).
+  return launch_gemm(ctx, 0, ctx->geo_b, ctx->lda, 0, (const float*)ctx->tab[AOM_T_GEO_PROJ][0], ctx->lda, 0, ctx->geo_com,
+                     ctx->lda, 0, c.n_env, c.nactu, c.nactu, nullptr, 0, 0, 1, st, nullptr, 0, true);
+}
+
+extern "C" int aom_apply_control_geo(aom_ctx* ctx, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  int rc = geo_prepare(ctx);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->geo_volts, ctx->geo_com, (size_t)ctx->cfg.n_env * ctx->lda * sizeof(float),
+                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return AOM_OK;
 }
 
@@ -980,6 +1152,11 @@ extern "C" int aom_reset_strehl(aom_ctx* ctx, void* stream) {
   ctx->tar_n = 0;
   CU(cudaMemsetAsync(ctx->tar_acc, 0, (size_t)ctx->cfg.n_env * 2 * sizeof(float), (cudaStream_t)stream));
   CU(cudaMemsetAsync(ctx->strehl, 0, (size_t)ctx->cfg.n_env * 4 * sizeof(float), (cudaStream_t)stream));
+  if (ctx->geo_com) {
+    ctx->geo_tar_n = 0;
+    CU(cudaMemsetAsync(ctx->geo_acc, 0, (size_t)ctx->cfg.n_env * 2 * sizeof(float), (cudaStream_t)stream));
+    CU(cudaMemsetAsync(ctx->strehl_geo, 0, (size_t)ctx->cfg.n_env * 4 * sizeof(float), (cudaStream_t)stream));
+  }
   return AOM_OK;
 }
 
@@ -1217,10 +1394,20 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   rc = aom_state_begin(ctx, stream); if (rc) return rc;
   if (fork) CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
   else { rc = aom_move_atmos(ctx, stream); if (rc) return rc; }
+  // second controller of the production parameter files (next_part_one loops over p_controllers,
+  // rlSupervisor.py:1036-1046): it reads only the moved screens, so it runs beside the sensor frame
+  const bool geo = ctx->opt[AOM_OPT_GEO] != 0;
+  if (geo) {
+    cudaStream_t gs = fork ? ctx->side_stream : st;
+    rc = aom_do_control_geo(ctx, gs); if (rc) return rc;
+    rc = aom_apply_control_geo(ctx, gs); if (rc) return rc;
+    if (fork) CU(cudaEventRecord(ctx->ev_geo, gs));
+  }
   rc = aom_comp_wfs_image(ctx, 3, ctx->cfg.noise, stream); if (rc) return rc;
   rc = aom_do_centroids(ctx, stream); if (rc) return rc;
   rc = aom_do_control(ctx, stream); if (rc) return rc;
   if (ctx->state) { rc = aom_state_end(ctx, stream); if (rc) return rc; }
+  if (geo && fork) CU(cudaStreamWaitEvent(st, ctx->ev_geo, 0));
   return AOM_OK;
 }
 

@@ -1,0 +1,328 @@
+// pupil_sweep.cuh -- one pass over the pupil-plane phase of every environment without materialising it.
+//
+// Two consumers share the sweep:
+//   MODE 0  geometric controller (RlSupervisor.next_part_one_geo, shesha/supervisor/rlSupervisor.py:989-1013; sutra
+//           comp_dphi + the sparse IF product of comp_com): target phase through the atmosphere, masked by the pupil,
+//           projected on the lattice columns (T[e][y][gx], see geo_kernels.cuh) + the pupil sums of the piston /
+//           tip-tilt rows;
+//   MODE 1  target Strehl (TargetCompass.comp_tar_image / comp_strehl, shesha/supervisor/components/targetCompass.py:139-196,
+//           Marechal form): atmosphere + mirrors, pupil sums of m, m phi, m phi^2.
+//
+// Layout of the work.  A warp owns a 128-pixel column block of a strip of consecutive pupil rows of one environment:
+// one lane = four pixels of the current row.  Pupil row y needs the screen rows r(y), r(y)+1 of every layer, and
+// r(y)+1 = r(y+1): the warp keeps a three-slot ring of staged screen-row segments (136 floats per layer) in shared
+// memory, filled two rows ahead by 1-D bulk copies (cp.async.bulk, completion on a per-slot mbarrier), so each screen
+// row is fetched once per strip with no address arithmetic in the lanes, and 6 KB of shared memory per warp leave 32
+// warps per SM.  (A first version staged whole 656-float rows per warp: 28 KB per warp, 8 warps per SM, issue slots
+// 20 % busy -- profiles/r01_pupil_sweep_v1_*.)  Copies start at the 16-byte aligned column below the wanted one (bulk
+// copies need 16-byte alignment; a segment wraps around the torus in at most two pieces); the residual offset
+// D = column & 3 is warp-uniform and resolved by a switch, so the lanes read the staged rows with aligned LDS.128:
+// 4 vector loads + 16 FFMA per layer for four pixels (four-tap bilinear weights from the host).
+// Pixels are addressed in the lattice frame x' = x - (i1_0 - pzt_off) (>= 0): a column block is eight 16-pixel lattice
+// chunks, and the pupil mask / tip-tilt planes are repacked once into that frame (sweep_tables_kernel).
+// MODE 0 row pass: Q[j][u] = sum_k f[16u+k] row[16j+k] is one FFMA chain per lane (32 = 8 chunks x 4 offsets); the
+// lattice sums T[g] = Q[g][0] + Q[g+1][1] + Q[g+2][2] + Q[g+3][3] reach three chunks to the right, so every block
+// writes its 11 partial sums (g = 8 cb - 3 .. 8 cb + 7) to Tp[e][y][cb][12] and geo_cols_kernel adds the two
+// blocks that can contribute to a lattice column -- no atomics, deterministic.
+#pragma once
+#include "wfs_kernels.cuh"
+#include "wfs_tma.cuh"
+
+#define PSW_WARPS 8
+#define PSW_SLOTS 3
+#define PSW_STRIP 46        // pupil rows per warp: 644 = 14 x 46 on the 40x40 grid
+#define PSW_BW 136          // staged floats per layer and screen row: 128 pixels + 1, rounded to 16 bytes, + alignment slack
+#define PSW_TP 12           // partial lattice sums per block and row (11 used)
+
+struct SweepParams {
+  WfsParams w;
+  const uint32_t* maskw;    // [n][32 nb]     pupil mask, one byte per pixel, four per word (lattice frame, 0 outside)
+  const float* ttp;         // [2][n][128 nb] tip-tilt planes in the lattice frame, zero outside the pupil frame
+  float* Tp;                // MODE 0: [E][n][nb][PSW_TP]
+  double* mom;              // MODE 0: [E][4] sums of m phi, m phi tt_x, m phi tt_y ; MODE 1: [E][3] sums of m, m phi, m phi^2
+  int nb;                   // column blocks per row
+  int n_strips;
+  int* err;
+};
+
+__host__ __device__ inline size_t psw_warp_floats(int NL) {
+  return (size_t)PSW_SLOTS * NL * PSW_BW + 160 + 32 + 48 + 16 + 8;   // ring, out row, Q, volt window, R row, barriers
+}
+__host__ __device__ inline size_t psw_smem_bytes(int NL) { return (PSW_WARPS * psw_warp_floats(NL) + 64) * sizeof(float); }
+
+// mask / tip-tilt planes in the lattice frame; grid (n), block 128
+__global__ void sweep_tables_kernel(WfsParams p, uint32_t* maskw, float* ttp, int nb) {
+  const int y = blockIdx.x;
+  const int xs0 = p.i1_0 - p.pzt_off;
+  for (int m = threadIdx.x; m < 32 * nb; m += blockDim.x) {
+    uint32_t word = 0;
+    for (int c = 0; c < 4; ++c) {
+      const int x = 4 * m + c + xs0;
+      const bool in = x >= 0 && x < p.n;
+      const bool lit = in && p.mpupil[(size_t)y * p.n + x] != 0.f;
+      word |= (lit ? 1u : 0u) << (8 * c);
+      for (int j = 0; j < 2; ++j) {
+        float v = 0.f;
+        if (in && p.tt_planes)
+          v = p.tt_planes[(size_t)j * p.tt_dim * p.tt_dim + (size_t)(y + p.tt_off) * p.tt_dim + x + p.tt_off];
+        ttp[((size_t)j * p.n + y) * 128 * nb + 4 * m + c] = v;
+      }
+    }
+    maskw[(size_t)y * 32 * nb + m] = word;
+  }
+}
+
+__device__ __forceinline__ void psw_bulk(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// four pixels of one layer from the staged upper / lower screen rows (16-byte aligned pointers, wanted columns start
+// D floats in)
+template <int D>
+__device__ __forceinline__ void psw_layer(const float* __restrict__ up, const float* __restrict__ lo, const WfsLayer& L,
+                                          float (&ph)[4]) {
+  float a[8], b[8];
+  const float4 a0 = *reinterpret_cast<const float4*>(up), b0 = *reinterpret_cast<const float4*>(lo);
+  a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+  b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+  if (D == 0) {
+    a[4] = up[4]; b[4] = lo[4];
+  } else {
+    const float4 a1 = *reinterpret_cast<const float4*>(up + 4), b1 = *reinterpret_cast<const float4*>(lo + 4);
+    a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+  const float w00 = L.w00, w01 = L.w01, w10 = L.w10, w11 = L.w11;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float acc = ph[c];
+    acc = fmaf(w00, a[D + c], acc);
+    acc = fmaf(w01, a[D + c + 1], acc);
+    acc = fmaf(w10, b[D + c], acc);
+    acc = fmaf(w11, b[D + c + 1], acc);
+    ph[c] = acc;
+  }
+}
+
+template <int NL, int MODE>
+__global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __grid_constant__ SweepParams P) {
+  extern __shared__ __align__(128) float psw_smem[];
+  const WfsParams& p = P.w;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.y;
+  const int nl = p.n_layers < NL ? p.n_layers : NL;
+
+  float* s_f = psw_smem;                                    // [64] stamp taps, zero beyond ss
+  float* ring = psw_smem + 64 + (size_t)warp * psw_warp_floats(NL);   // [PSW_SLOTS][NL][PSW_BW]
+  float* s_out = ring + PSW_SLOTS * NL * PSW_BW;            // [8][20]   MODE 0: masked phase of the row, lattice chunks
+  float* s_q = s_out + 160;                                 // [8][4]    MODE 0: chunk partial sums
+  float* s_v = s_q + 32;                                    // [4][12]   MODE 1: volts of the four lattice rows in reach
+  float* s_r = s_v + 48;                                    // [16]      MODE 1: R_y[g], g = 8 cb - 3 + index
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_r + 16);   // [PSW_SLOTS]
+
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_f[i] = i < p.ss ? p.stamp1d[i] : 0.f;
+  if (lane < 16) s_r[lane] = 0.f;
+  if (lane < PSW_SLOTS)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wft_smem_u32(s_bar + lane)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const int item = blockIdx.x * PSW_WARPS + warp;
+  if (item >= P.n_strips * P.nb) return;
+  const int strip = item / P.nb, cb = item - strip * P.nb;
+  const int yb = strip * PSW_STRIP;
+  const int rows = min(PSW_STRIP, p.n - yb);
+  const int xs0 = p.i1_0 - p.pzt_off, ys0 = p.j1_0 - p.pzt_off;
+
+  // per layer: first screen row of the strip, aligned start column of the staged segment, residual offset
+  int row0[NL], ca[NL], dd[NL];
+  const float* scr[NL];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    row0[l] = ca[l] = dd[l] = 0; scr[l] = nullptr;
+    if (l < nl) {
+      const WfsLayer& L = p.layer[l];
+      const int N = L.N;
+      scr[l] = L.screen + (size_t)e * N * N;
+      int r = yb + L.iy + L.oy[e]; r -= (r >= N) ? N : 0;
+      row0[l] = r;
+      int c = (128 * cb + xs0 + L.ix + L.ox[e]) % N;      // column of the block's first pixel (x may lie outside the frame)
+      c += (c < 0) ? N : 0;
+      ca[l] = c & ~3; dd[l] = c & 3;
+    }
+  }
+  const uint32_t ring_u32 = wft_smem_u32(ring), bar_u32 = wft_smem_u32(s_bar);
+
+  auto issue = [&](int i) {           // screen rows of strip row i -> slot i % 3   (lane 0)
+    const int slot = i % PSW_SLOTS;
+    const uint32_t bar = bar_u32 + 8 * slot;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nl * PSW_BW * 4) : "memory");
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      if (l < nl) {
+        const int N = p.layer[l].N;
+        int r = row0[l] + i; r -= (r >= N) ? N : 0;
+        const float* src = scr[l] + (size_t)r * N;
+        const uint32_t dst = ring_u32 + (uint32_t)((slot * NL + l) * PSW_BW) * 4u;
+        const int len = min(PSW_BW, N - ca[l]);
+        psw_bulk(dst, src + ca[l], (uint32_t)len * 4u, bar);
+        if (len < PSW_BW) psw_bulk(dst + (uint32_t)len * 4u, src, (uint32_t)(PSW_BW - len) * 4u, bar);
+      }
+    }
+  };
+
+  if (nl > 0 && lane == 0) {
+    for (int i = 0; i < 3 && i <= rows; ++i) issue(i);
+  }
+
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // MODE 0: s1 = sum v, s2 = sum v ttx, s3 = sum v tty ; MODE 1: s0 = count, s1 = sum v, s2 = sum v^2
+  float tt0 = 0.f, tt1 = 0.f;
+  const float* volts = nullptr;
+  const bool dm = MODE == 1 && p.use_dm;
+  if (dm) {
+    volts = p.volts + (size_t)e * p.ldv;
+    tt0 = __ldg(volts + p.pzt_nact); tt1 = __ldg(volts + p.pzt_nact + 1);
+  }
+  float fq[16];                                    // MODE 0: the 16 taps of this lane's lattice offset u = lane & 3
+  if (MODE == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) fq[k] = s_f[16 * (lane & 3) + k];
+  }
+  const int ngw = 32 * P.nb, ga = 32 * cb + lane;   // groups per row of the tables, this lane's group
+  const int jl = lane >> 2, k0 = 4 * (lane & 3);    // lattice chunk inside the block, first pixel inside the chunk
+  int jy_have = -1000;
+
+  for (int i = 0; i < rows; ++i) {
+    const int y = yb + i;
+    const uint32_t mask = __ldg(P.maskw + (size_t)y * ngw + ga);
+    float4 tx = make_float4(0.f, 0.f, 0.f, 0.f), ty = tx;
+    if (mask != 0u && (MODE == 0 || dm)) {
+      tx = __ldg(reinterpret_cast<const float4*>(P.ttp + (size_t)y * 4 * ngw + 4 * ga));
+      ty = __ldg(reinterpret_cast<const float4*>(P.ttp + ((size_t)p.n + y) * 4 * ngw + 4 * ga));
+    }
+    if (dm) {
+      // R_y[g] = sum_u f[16 u + ky] v[jy - u][g] over the at most four lattice rows whose stamp covers this pupil row
+      const int yp = y - ys0, jy = yp >> 4, ky = yp & 15;
+      if (jy != jy_have) {
+        jy_have = jy;
+        if (lane < 11) {
+          const int g = 8 * cb - 3 + lane;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int gy = jy - u;
+            float v = 0.f;
+            if (g >= 0 && g < p.grid_n && gy >= 0 && gy < p.grid_n) {
+              const int a = __ldg(p.act_map + gy * p.grid_n + g);
+              if (a >= 0) v = __ldg(volts + a);
+            }
+            s_v[12 * u + lane] = v;
+          }
+        }
+        __syncwarp();
+      }
+      if (lane < 11) {
+        float r = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r = fmaf(s_f[16 * u + ky], s_v[12 * u + lane], r);
+        s_r[lane] = r;
+      }
+      __syncwarp();
+    }
+    if (nl > 0) {
+      if (i == 0 && !wft_mbar_wait(bar_u32, 0, P.err)) return;
+      const int s = (i + 1) % PSW_SLOTS;
+      if (!wft_mbar_wait(bar_u32 + 8 * s, (uint32_t)(((i + 1) / PSW_SLOTS) & 1), P.err)) return;
+    }
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mask != 0u) {
+      const float* up = ring + ((i % PSW_SLOTS) * NL) * PSW_BW + 4 * lane;
+      const float* lo = ring + (((i + 1) % PSW_SLOTS) * NL) * PSW_BW + 4 * lane;
+      float ph[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        if (l < nl) {
+          switch (dd[l]) {
+            case 0: psw_layer<0>(up + l * PSW_BW, lo + l * PSW_BW, p.layer[l], ph); break;
+            case 1: psw_layer<1>(up + l * PSW_BW, lo + l * PSW_BW, p.layer[l], ph); break;
+            case 2: psw_layer<2>(up + l * PSW_BW, lo + l * PSW_BW, p.layer[l], ph); break;
+            default: psw_layer<3>(up + l * PSW_BW, lo + l * PSW_BW, p.layer[l], ph); break;
+          }
+        }
+      }
+      if (dm) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float r = s_r[jl - u + 3];
+          const float4 f4 = *reinterpret_cast<const float4*>(s_f + 16 * u + k0);
+          ph[0] = fmaf(r, f4.x, ph[0]); ph[1] = fmaf(r, f4.y, ph[1]);
+          ph[2] = fmaf(r, f4.z, ph[2]); ph[3] = fmaf(r, f4.w, ph[3]);
+        }
+        ph[0] = fmaf(tt0, tx.x, ph[0]); ph[1] = fmaf(tt0, tx.y, ph[1]);
+        ph[2] = fmaf(tt0, tx.z, ph[2]); ph[3] = fmaf(tt0, tx.w, ph[3]);
+        ph[0] = fmaf(tt1, ty.x, ph[0]); ph[1] = fmaf(tt1, ty.y, ph[1]);
+        ph[2] = fmaf(tt1, ty.z, ph[2]); ph[3] = fmaf(tt1, ty.w, ph[3]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = ((mask >> (8 * c)) & 1u) ? ph[c] : 0.f;
+      s1 += (v[0] + v[1]) + (v[2] + v[3]);
+      if (MODE == 0) {
+        s2 = fmaf(v[0], tx.x, s2); s2 = fmaf(v[1], tx.y, s2); s2 = fmaf(v[2], tx.z, s2); s2 = fmaf(v[3], tx.w, s2);
+        s3 = fmaf(v[0], ty.x, s3); s3 = fmaf(v[1], ty.y, s3); s3 = fmaf(v[2], ty.z, s3); s3 = fmaf(v[3], ty.w, s3);
+      } else {
+        s0 += (float)__popc(mask);
+        s2 = fmaf(v[0], v[0], s2); s2 = fmaf(v[1], v[1], s2); s2 = fmaf(v[2], v[2], s2); s2 = fmaf(v[3], v[3], s2);
+      }
+    }
+    if (MODE == 0) *reinterpret_cast<float4*>(s_out + 20 * jl + k0) = make_float4(v[0], v[1], v[2], v[3]);
+    __syncwarp();
+    // the upper slot is free: fetch the screen rows of strip row i + 3 into it
+    if (nl > 0 && lane == 0 && i + 3 <= rows) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(i + 3);
+    }
+    if (MODE == 0) {
+      // lattice pass: Q[j][u] = sum_k f[16u + k] row[16j + k], one (chunk j, offset u) per lane
+      const float4* q4 = reinterpret_cast<const float4*>(s_out + 20 * jl);
+      float acc = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 q = q4[k4];
+        acc = fmaf(fq[4 * k4 + 0], q.x, acc); acc = fmaf(fq[4 * k4 + 1], q.y, acc);
+        acc = fmaf(fq[4 * k4 + 2], q.z, acc); acc = fmaf(fq[4 * k4 + 3], q.w, acc);
+      }
+      s_q[lane] = acc;
+      __syncwarp();
+      if (lane < 11) {
+        // partial T[g], g = 8 cb - 3 + lane: the chunks g + u that belong to this block
+        float t = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = lane - 3 + u;
+          if (j >= 0 && j < 8) t += s_q[4 * j + u];
+        }
+        P.Tp[(((size_t)e * p.n + y) * P.nb + cb) * PSW_TP + lane] = t;
+      }
+      __syncwarp();
+    }
+  }
+
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, sft);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, sft);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, sft);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, sft);
+  }
+  if (lane == 0) {
+    if (MODE == 0) {
+      if (s1 != 0.f) atomicAdd(P.mom + (size_t)e * 4 + 0, (double)s1);
+      if (s2 != 0.f) atomicAdd(P.mom + (size_t)e * 4 + 1, (double)s2);
+      if (s3 != 0.f) atomicAdd(P.mom + (size_t)e * 4 + 2, (double)s3);
+    } else {
+      if (s0 != 0.f) atomicAdd(P.mom + (size_t)e * 3 + 0, (double)s0);
+      if (s1 != 0.f) atomicAdd(P.mom + (size_t)e * 3 + 1, (double)s1);
+      if (s2 != 0.f) atomicAdd(P.mom + (size_t)e * 3 + 2, (double)s2);
+    }
+  }
+}

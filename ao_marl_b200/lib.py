@@ -40,16 +40,16 @@ class AomConfig(ctypes.Structure):
 TABLES = ["AB", "STENCIL", "MPUPIL", "HALFXY", "SUB_X0", "SUB_Y0", "FLUX", "STAMP1D", "ACT_MAP", "TT_PLANES",
           "CMAT", "V2M", "M2V", "FREEDOM", "ACTION_MAP", "STATE_MAP", "NORM_DM_MEAN", "NORM_DM_STD",
           "NORM_RES_MEAN", "NORM_RES_STD", "AGENT_IDX", "AGENT_ACT", "AGENT_REWARD", "ACTOR_W1", "ACTOR_B1",
-          "ACTOR_W2", "ACTOR_B2", "ACTOR_WH", "ACTOR_BH"]
+          "ACTOR_W2", "ACTOR_B2", "ACTOR_WH", "ACTOR_BH", "GEO_PROJ", "GEO_SIFN"]
 T = {name: i for i, name in enumerate(TABLES)}
 BUFFERS = ["SCREEN", "RING_OX", "RING_OY", "SLOPES", "ERR", "COM", "VOLTS", "BINCUBE", "PHASE", "MODES",
-           "RES_MODES", "STATE", "REWARD", "ACTION", "ACTION_MEAN", "STREHL"]
+           "RES_MODES", "STATE", "REWARD", "ACTION", "ACTION_MEAN", "STREHL", "GEO_COM", "GEO_VOLTS", "STREHL_GEO", "GEO_PROJ"]
 B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
            "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_wfs_time_ms", "aom_raytrace_wfs",
-           "aom_comp_strehl", "aom_reset_strehl", "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
+           "aom_comp_strehl", "aom_reset_strehl", "aom_do_control_geo", "aom_apply_control_geo", "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
            "aom_set_gain", "aom_set_loop", "aom_reset_dm", "aom_set_dm_volts", "aom_rl_control",
            "aom_state_begin", "aom_state_end", "aom_reward", "aom_actor_forward", "aom_step", "aom_gemm_tn",
            "aom_pixel_noise"]
@@ -225,6 +225,8 @@ class Simulator:
             self.set_basis(t.Btt, t.P)
         if getattr(t, "cmat", None) is not None:
             self.set_command_matrix(t.cmat)
+        if getattr(t, "geo_proj", None) is not None:
+            self.set_geo(t.geo_proj, t.geo_sifn)
         if rl is not None:
             rl.upload(self)
 
@@ -366,12 +368,37 @@ class Simulator:
         self._check(self.lib.aom_raytrace_wfs(self._ctx, flags, self.stream), "aom_raytrace_wfs")
         return self.buffer("PHASE").view(self.n_env, self.cfg.n, self.cfg.n)
 
-    def comp_strehl(self, lambda_um, atmos=True, dms=True, accumulate=True):
-        """Pupil phase variance -> AOM_B_STREHL [E, 4] = (SE, LE, variance, mean variance)."""
-        flags = (1 if atmos else 0) | (2 if dms else 0)
+    def comp_strehl(self, lambda_um, atmos=True, dms=True, accumulate=True, geo=False):
+        """Pupil phase variance -> AOM_B_STREHL [E, 4] = (SE, LE, variance, mean variance); geo=True: the target
+        behind the geometric controller's mirrors (AOM_B_STREHL_GEO)."""
+        flags = (1 if atmos else 0) | (2 if dms else 0) | (0x100 if geo else 0)
         self._check(self.lib.aom_comp_strehl(self._ctx, flags, float(lambda_um), 1 if accumulate else 0, self.stream),
                     "aom_comp_strehl")
-        return self.buffer("STREHL").view(self.n_env, 4)
+        return self.buffer("STREHL_GEO" if geo else "STREHL").view(self.n_env, 4)
+
+    def set_geo(self, proj, sifn):
+        """Upload the geometric controller's tables (ao_marl_b200.init.geo.build_geo)."""
+        proj = np.asarray(proj, dtype=np.float32)
+        if proj.shape != (self.cfg.nactu, self.cfg.nactu) or np.shape(sifn) != (self.cfg.nactu,):
+            raise ValueError("Dimension mismatch")
+        self.set_table("GEO_PROJ", pad_rows(proj))
+        self.set_table("GEO_SIFN", np.asarray(sifn, dtype=np.float32))
+
+    def do_control_geo(self):
+        """rtc.do_control(geo controller, sources=target): AOM_B_GEO_COM = least-squares mirror fit of the turbulence."""
+        self._check(self.lib.aom_do_control_geo(self._ctx, self.stream), "aom_do_control_geo")
+        return self.rows("GEO_COM", self.cfg.nactu)
+
+    def apply_control_geo(self):
+        self._check(self.lib.aom_apply_control_geo(self._ctx, self.stream), "aom_apply_control_geo")
+
+    def set_pupil_path(self, name):
+        """Kernels behind comp_strehl / do_control_geo: 'sweep' (default) or 'pixel' (cross-check path)."""
+        self._check(self.lib.aom_set_option(self._ctx, 4, {"sweep": 0, "pixel": 1}[name]), "aom_set_option")
+
+    def step_with_geo(self, on=True):
+        """aom_step also runs the geometric controller every frame (AOM_OPT_GEO)."""
+        self._check(self.lib.aom_set_option(self._ctx, 3, 1 if on else 0), "aom_set_option")
 
     def reset_strehl(self):
         self._check(self.lib.aom_reset_strehl(self._ctx, self.stream), "aom_reset_strehl")

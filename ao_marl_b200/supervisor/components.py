@@ -210,27 +210,43 @@ class _RtcHandle:
 
 
 class RtcB200(_Base):
-    """rtcCompass.py:55-630 (controller 0 = least-squares integrator)."""
+    """rtcCompass.py:55-630: controller 0 = least-squares integrator; when the parameter file lists a geometric
+    controller (type "geo"), do_control / apply_control / get_command / get_voltages also accept its index."""
 
     def __init__(self, sim, config, tables):
         super().__init__(sim, config)
         self._tables = tables
-        self._rtc = _RtcHandle([_Controller(sim, "ls")])
+        self._geo = next((i for i, c in enumerate(config.p_controllers) if getattr(c, "type", "") == "geo"), None)
+        controls = [_Controller(sim, "ls")]
+        if self._geo is not None:
+            while len(controls) < self._geo:
+                controls.append(None)
+            controls.append(_Controller(sim, "geo"))
+        self._rtc = _RtcHandle(controls)
         self.d_control = self._rtc.d_control
+
+    def _is_geo(self, i):
+        return i != 0 and i == self._geo and getattr(self._tables, "geo_proj", None) is not None
 
     def _chk(self, i):
         if i != 0:
-            raise NotImplementedError("only controller 0 (LS integrator) is on the hot path")
+            raise NotImplementedError("controller %d: only the LS integrator (0) serves this call" % i)
 
     def do_centroids(self, controller_index):
         self._chk(controller_index)
         self._sim.do_centroids()
 
     def do_control(self, controller_index, **kw):
+        if self._is_geo(controller_index):
+            self._sim.do_control_geo()
+            return
         self._chk(controller_index)
         self._sim.do_control()
 
     def apply_control(self, controller_index, *, comp_voltage=True):
+        if self._is_geo(controller_index):
+            self._sim.apply_control_geo()
+            return
         self._chk(controller_index)
         self._sim.apply_control(comp_voltage)
 
@@ -246,10 +262,14 @@ class RtcB200(_Base):
         return self._out(self._sim.rows("ERR", self._sim.cfg.nactu))
 
     def get_command(self, controller_index):
+        if self._is_geo(controller_index):
+            return self._out(self._sim.rows("GEO_COM", self._sim.cfg.nactu))
         self._chk(controller_index)
         return self._out(self._sim.rows("COM", self._sim.cfg.nactu))
 
     def get_voltages(self, controller_index):
+        if self._is_geo(controller_index):
+            return self._out(self._sim.rows("GEO_VOLTS", self._sim.cfg.nactu))
         self._chk(controller_index)
         return self._out(self._sim.rows("VOLTS", self._sim.cfg.nactu))
 
@@ -297,19 +317,29 @@ class TargetB200(_Base):
     def __init__(self, sim, config, tables):
         super().__init__(sim, config)
         self._tables = tables
-        self._flags = (False, False)
+        self._flags = {}
+        # target i looks through the mirrors of the geometric controller when its dms are that controller's
+        # (parameter layout "geo": target 1 <-> DMs [1, 3] <-> controller 1)
+        geo = next((c for c in config.p_controllers if getattr(c, "type", "") == "geo"), None)
+        gd = sorted(int(d) for d in geo.ndm) if geo is not None else None
+        self._geo_targets = {i for i, tg in enumerate(config.p_targets)
+                             if gd is not None and sorted(int(d) for d in tg.dms_seen) == gd}
+
+    def _is_geo(self, index):
+        return index in self._geo_targets and getattr(self._tables, "geo_proj", None) is not None
 
     def raytrace(self, index, *, tel=None, atm=None, dms=None, ncpa=True, reset=True):
-        a, d = (False, False) if reset else self._flags
+        a, d = (False, False) if reset else self._flags.get(index, (False, False))
         if atm is not None and getattr(atm, "is_enable", True):
             a = True
         if dms is not None:
             d = True
-        self._flags = (a, d)
+        self._flags[index] = (a, d)
 
     def comp_tar_image(self, tarNum, *, puponly=0, compLE=True):
         lam = float(self._config.p_targets[tarNum].Lambda)
-        self._sim.comp_strehl(lam, atmos=self._flags[0], dms=self._flags[1], accumulate=bool(compLE))
+        a, d = self._flags.get(tarNum, (False, False))
+        self._sim.comp_strehl(lam, atmos=a, dms=d, accumulate=bool(compLE), geo=self._is_geo(tarNum))
 
     def comp_strehl(self, tarNum, *, do_fit=True):
         pass
@@ -319,7 +349,7 @@ class TargetB200(_Base):
 
     def get_strehl(self, tar_index, *, do_fit=True):
         """[SE, LE, variance, mean variance]: floats when E == 1 (targetCompass.py:139-159), else [E] device tensors."""
-        s = self._sim.buffer("STREHL").view(self._sim.n_env, 4)
+        s = self._sim.buffer("STREHL_GEO" if self._is_geo(tar_index) else "STREHL").view(self._sim.n_env, 4)
         if self._sim.n_env == 1:
             return [float(x) for x in s[0].cpu()]
         return [s[:, i] for i in range(4)]
@@ -328,4 +358,5 @@ class TargetB200(_Base):
         raise NotImplementedError("the focal-plane PSF is outside the hot-path scope (SURVEY.md 8(f) rank 1)")
 
     def get_tar_phase(self, tar_index, *, pupil=False):
-        return self._out(self._sim.raytrace_wfs(atmos=self._flags[0], dms=self._flags[1]))
+        a, d = self._flags.get(tar_index, (False, False))
+        return self._out(self._sim.raytrace_wfs(atmos=a, dms=d))

@@ -12,6 +12,7 @@ batched over E environments and executed by libaomarl.so.
 import numpy as np
 
 from .. import calibration, tables as tables_mod
+from ..init import geo as geo_b
 from ..init import rtc as rtc_b
 from ..lib import Simulator
 from ..rl.layout import RLLayout
@@ -64,6 +65,10 @@ class RlSupervisor:
         if getattr(t, "cmat", None) is None or getattr(t, "nfilt", None) != max(nfilt, 0):
             t.nfilt = max(nfilt, 0)
             t.cmat = rtc_b.cmat_with_btt(t.imat, t.Btt, t.nfilt)
+        # second controller of the "geo" parameter layouts: least-squares fit of the mirrors to the target phase
+        self.geo_index = next((i for i, c in enumerate(config.p_controllers) if getattr(c, "type", "") == "geo"), None)
+        if self.geo_index is not None and getattr(t, "geo_proj", None) is None:
+            geo_b.build_geo(t)
         self.tables = t
         self.modes2volts, self.volts2modes = t.Btt, t.P
         sac = getattr(config_rl, "sac", None)
@@ -177,11 +182,30 @@ class RlSupervisor:
             self.rtc.do_centroids(ncontrol)
             self.rtc.do_control(ncontrol)
 
+    def next_part_one_geo(self, *, ncontrol=1, do_control=True, geometric_apply_control=True):
+        """rlSupervisor.py:989-1013: target trace through the atmosphere, projection, apply, trace through the mirrors."""
+        t = ncontrol
+        if self.atmos.is_enable:
+            self.target.raytrace(t, tel=self.tel, atm=self.atmos, ncpa=False)
+        else:
+            self.target.raytrace(t, tel=self.tel, ncpa=False)
+        if do_control and self.rtc is not None:
+            self.rtc.do_control(ncontrol, sources=None, source_index=t)
+            if geometric_apply_control:
+                self.rtc.apply_control(ncontrol)
+            self.target.raytrace(t, dms=self.dms, ncpa=True, reset=False)
+
     def next_part_one(self, *, move_atmos=True, tar_trace=None, wfs_trace=None, do_control=True,
-                      geometric_apply_control=True):
+                      geometric_apply_control=True, geo=False):
+        """rlSupervisor.py:1015-1051.  The reference runs every controller of the parameter file each frame; the
+        geometric one only feeds the "fitting error" curves, so here it is opt-in (geo=True, or
+        ``sim.step_with_geo()`` for the fused step)."""
         if move_atmos and self.atmos is not None:
             self.atmos.move_atmos()
         self.next_part_one_integrator(ncontrol=0, do_control=do_control)
+        if geo and self.geo_index is not None:
+            self.next_part_one_geo(ncontrol=self.geo_index, do_control=do_control,
+                                   geometric_apply_control=geometric_apply_control)
         self.iter += 1
 
     def next(self, *, move_atmos=True, nControl=0, tar_trace=None, wfs_trace=None, do_control=True,

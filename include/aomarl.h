@@ -113,6 +113,8 @@ typedef enum aom_table {
   AOM_T_ACTOR_B2,
   AOM_T_ACTOR_WH,      /* float [n_agents][2*actor_out][ld(hidden)]  mean rows then log-std rows */
   AOM_T_ACTOR_BH,      /* float [n_agents][2*actor_out] */
+  AOM_T_GEO_PROJ,      /* float [nactu][ld(nactu)]    -(IF IF^T)^+ of the geometric controller (rtc_init.py:418-448) */
+  AOM_T_GEO_SIFN,      /* float [nactu]        pupil sum of each influence row / number of pupil points           */
   AOM_T_COUNT
 } aom_table;
 
@@ -134,6 +136,10 @@ typedef enum aom_buffer {
   AOM_B_ACTION,        /* float [E][ld(action_dim)]                                       */
   AOM_B_ACTION_MEAN,   /* float [E][ld(action_dim)]                                       */
   AOM_B_STREHL,        /* float [E][4]  SE, LE, phase variance, running mean variance     */
+  AOM_B_GEO_COM,       /* float [E][ld(nactu)]     command of the geometric controller    */
+  AOM_B_GEO_VOLTS,     /* float [E][ld(nactu)]     voltages on the mirrors it drives      */
+  AOM_B_STREHL_GEO,    /* float [E][4]  as AOM_B_STREHL, for the target behind those mirrors */
+  AOM_B_GEO_PROJ,      /* float [E][ld(nactu)]     IF (phi - <phi>): the phase projected on the influence functions */
   AOM_B_COUNT
 } aom_buffer;
 
@@ -142,8 +148,16 @@ typedef enum aom_option {
   AOM_OPT_WFS_PATH = 0, /* which Shack-Hartmann frame kernel serves the Nfft = 64 geometry */
   AOM_OPT_GEMM_PATH,    /* which GEMM kernel serves the env-batched contractions */
   AOM_OPT_TIME_WFS,     /* != 0: bracket every sensor-kernel launch with CUDA events (read with aom_wfs_time_ms) */
+  AOM_OPT_GEO,          /* != 0: aom_step also runs the geometric controller every frame, as next_part_one does when
+                           the parameter file lists one (rlSupervisor.py:1036-1046); needs the AOM_T_GEO_* tables */
+  AOM_OPT_PUPIL_PATH,   /* which kernels sweep the pupil-plane phase for aom_comp_strehl / aom_do_control_geo */
   AOM_OPT_COUNT
 } aom_option;
+enum {
+  AOM_PUPIL_SWEEP = 0,     /* staged screen rows, one warp per strip of pupil rows (pitch-16 lattices; default; other
+                              geometries fall back to AOM_PUPIL_PIXEL) */
+  AOM_PUPIL_PIXEL = 1      /* one thread per pixel / one warp per row with plain global loads (cross-check path) */
+};
 enum {
   AOM_WFS_TENSOR = 0,      /* TMA-staged tiles + tensor-pipe DFT, three fp16 MMAs per product in both stages (fp32-grade;
                               default; geometries the staged kernel does not cover fall back to AOM_WFS_TENSOR_REG) */
@@ -205,8 +219,18 @@ int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream);
  * of aom_raytrace_wfs is reduced over the pupil on the fly and AOM_B_STREHL = {SE, LE, variance, mean variance}
  * with SE = exp(-var (2 pi / lambda)^2).  flags as aom_comp_wfs_image (bit0 atmosphere, bit1 mirrors);
  * accumulate != 0 adds the frame to the long-exposure means.  The 2048^2 focal-plane PSF is not computed. */
+#define AOM_TAR_GEO 0x100   /* flags bit: the target behind the geometric controller's mirrors (reads AOM_B_GEO_VOLTS,
+                               writes AOM_B_STREHL_GEO) instead of the main ones */
 int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int accumulate, void* stream);
 int aom_reset_strehl(aom_ctx* ctx, void* stream);     /* TargetCompass.reset_strehl */
+
+/* Geometric controller (RlSupervisor.next_part_one_geo, rlSupervisor.py:989-1013; init_controller_geo,
+ * rtc_init.py:418-448): aom_do_control_geo traces the target through the atmosphere and leaves
+ * AOM_B_GEO_COM = -(IF IF^T)^+ IF (phi - <phi>), the least-squares mirror fit of the turbulent phase;
+ * aom_apply_control_geo copies it to AOM_B_GEO_VOLTS (no latency: "geo pure delay 0").  The Strehl behind those
+ * mirrors is aom_comp_strehl(flags | AOM_TAR_GEO). */
+int aom_do_control_geo(aom_ctx* ctx, void* stream);
+int aom_apply_control_geo(aom_ctx* ctx, void* stream);
 
 /* Replace the detector image (RlSupervisor.autoencoder_denoising -> set_binimg, rlSupervisor.py:876-891):
  * device pointer to float [E][nvalid][npix*npix]; the next aom_do_centroids reads it. */
