@@ -109,7 +109,9 @@ template <int NL, int MODE>
 __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __grid_constant__ SweepParams P) {
   extern __shared__ __align__(128) float psw_smem[];
   const WfsParams& p = P.w;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: the compiler then keeps everything derived from it (strip, column block, the
+  // source pointers of the bulk copies) in uniform registers instead of broadcasting it per copy
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int e = blockIdx.y;
   const int nl = p.n_layers < NL ? p.n_layers : NL;
 
@@ -135,46 +137,53 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
   const int rows = min(PSW_STRIP, p.n - yb);
   const int xs0 = p.i1_0 - p.pzt_off, ys0 = p.j1_0 - p.pzt_off;
 
-  // per layer: first screen row of the strip, aligned start column of the staged segment, residual offset
-  int row0[NL], ca[NL], dd[NL];
-  const float* scr[NL];
+  // per layer: source of the next screen row to fetch (segment start, 16-byte aligned), rows left before the torus
+  // wraps, length of the first piece, residual column offset
+  const float* src[NL];
+  int left[NL], len0[NL], dd[NL];
 #pragma unroll
   for (int l = 0; l < NL; ++l) {
-    row0[l] = ca[l] = dd[l] = 0; scr[l] = nullptr;
+    src[l] = nullptr; left[l] = len0[l] = dd[l] = 0;
     if (l < nl) {
       const WfsLayer& L = p.layer[l];
       const int N = L.N;
-      scr[l] = L.screen + (size_t)e * N * N;
-      int r = yb + L.iy + L.oy[e]; r -= (r >= N) ? N : 0;
-      row0[l] = r;
-      int c = (128 * cb + xs0 + L.ix + L.ox[e]) % N;      // column of the block's first pixel (x may lie outside the frame)
+      const int oy = __shfl_sync(0xffffffffu, __ldg(L.oy + e), 0), ox = __shfl_sync(0xffffffffu, __ldg(L.ox + e), 0);
+      int r = yb + L.iy + oy; r -= (r >= N) ? N : 0;
+      int c = (128 * cb + xs0 + L.ix + ox) % N;           // column of the block's first pixel (x may lie outside the frame)
       c += (c < 0) ? N : 0;
-      ca[l] = c & ~3; dd[l] = c & 3;
+      dd[l] = c & 3; c &= ~3;
+      src[l] = L.screen + (size_t)e * N * N + c + (size_t)r * N;
+      left[l] = N - r;
+      len0[l] = min(PSW_BW, N - c) * 4;
     }
   }
   const uint32_t ring_u32 = wft_smem_u32(ring), bar_u32 = wft_smem_u32(s_bar);
 
-  auto issue = [&](int i) {           // screen rows of strip row i -> slot i % 3   (lane 0)
-    const int slot = i % PSW_SLOTS;
+  // every lane keeps the (warp-uniform) copy state, lane 0 alone issues: the state then lives in uniform registers
+  auto issue = [&](int slot) {        // next screen row of every layer -> ring slot
     const uint32_t bar = bar_u32 + 8 * slot;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nl * PSW_BW * 4) : "memory");
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nl * PSW_BW * 4) : "memory");
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       if (l < nl) {
-        const int N = p.layer[l].N;
-        int r = row0[l] + i; r -= (r >= N) ? N : 0;
-        const float* src = scr[l] + (size_t)r * N;
         const uint32_t dst = ring_u32 + (uint32_t)((slot * NL + l) * PSW_BW) * 4u;
-        const int len = min(PSW_BW, N - ca[l]);
-        psw_bulk(dst, src + ca[l], (uint32_t)len * 4u, bar);
-        if (len < PSW_BW) psw_bulk(dst + (uint32_t)len * 4u, src, (uint32_t)(PSW_BW - len) * 4u, bar);
+        if (lane == 0) {
+          psw_bulk(dst, src[l], (uint32_t)len0[l], bar);
+          if (len0[l] < PSW_BW * 4)    // the segment wraps: the rest starts at column 0 of the same screen row
+            psw_bulk(dst + (uint32_t)len0[l], src[l] - (p.layer[l].N - len0[l] / 4), (uint32_t)(PSW_BW * 4 - len0[l]), bar);
+        }
+        src[l] += p.layer[l].N;
+        if (--left[l] == 0) { src[l] -= (size_t)p.layer[l].N * p.layer[l].N; left[l] = p.layer[l].N; }
       }
     }
   };
 
-  if (nl > 0 && lane == 0) {
+  if (nl > 0) {
     for (int i = 0; i < 3 && i <= rows; ++i) issue(i);
   }
+  int s_up = 0, s_lo = 1;                           // ring slots of the upper / lower screen rows of the current pupil row
+  uint32_t par_lo = 0;                              // phase parity the lower slot completes next
 
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // MODE 0: s1 = sum v, s2 = sum v ttx, s3 = sum v tty ; MODE 1: s0 = count, s1 = sum v, s2 = sum v^2
   float tt0 = 0.f, tt1 = 0.f;
@@ -191,21 +200,22 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
   }
   const int ngw = 32 * P.nb, ga = 32 * cb + lane;   // groups per row of the tables, this lane's group
   const int jl = lane >> 2, k0 = 4 * (lane & 3);    // lattice chunk inside the block, first pixel inside the chunk
-  int jy_have = -1000;
+  int ro = yb * ngw + ga;                           // this lane's group in the mask / tip-tilt tables, current row
+  const float4* ttp4 = reinterpret_cast<const float4*>(P.ttp);
+  const int ty_off = p.n * ngw;
+  float* tp = MODE == 0 ? P.Tp + (((size_t)e * p.n + yb) * P.nb + cb) * PSW_TP + lane : nullptr;
+  int jy = (yb - ys0) >> 4, ky = (yb - ys0) & 15;
+  bool new_jy = true;
 
   for (int i = 0; i < rows; ++i) {
-    const int y = yb + i;
-    const uint32_t mask = __ldg(P.maskw + (size_t)y * ngw + ga);
+    const uint32_t mask = __ldg(P.maskw + ro);
     float4 tx = make_float4(0.f, 0.f, 0.f, 0.f), ty = tx;
-    if (mask != 0u && (MODE == 0 || dm)) {
-      tx = __ldg(reinterpret_cast<const float4*>(P.ttp + (size_t)y * 4 * ngw + 4 * ga));
-      ty = __ldg(reinterpret_cast<const float4*>(P.ttp + ((size_t)p.n + y) * 4 * ngw + 4 * ga));
-    }
+    if (mask != 0u && (MODE == 0 || dm)) { tx = __ldg(ttp4 + ro); ty = __ldg(ttp4 + ro + ty_off); }
+    ro += ngw;
     if (dm) {
       // R_y[g] = sum_u f[16 u + ky] v[jy - u][g] over the at most four lattice rows whose stamp covers this pupil row
-      const int yp = y - ys0, jy = yp >> 4, ky = yp & 15;
-      if (jy != jy_have) {
-        jy_have = jy;
+      if (new_jy) {
+        new_jy = false;
         if (lane < 11) {
           const int g = 8 * cb - 3 + lane;
 #pragma unroll
@@ -228,16 +238,16 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
         s_r[lane] = r;
       }
       __syncwarp();
+      if (++ky == 16) { ky = 0; ++jy; new_jy = true; }
     }
     if (nl > 0) {
       if (i == 0 && !wft_mbar_wait(bar_u32, 0, P.err)) return;
-      const int s = (i + 1) % PSW_SLOTS;
-      if (!wft_mbar_wait(bar_u32 + 8 * s, (uint32_t)(((i + 1) / PSW_SLOTS) & 1), P.err)) return;
+      if (!wft_mbar_wait(bar_u32 + 8 * s_lo, par_lo, P.err)) return;
     }
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (mask != 0u) {
-      const float* up = ring + ((i % PSW_SLOTS) * NL) * PSW_BW + 4 * lane;
-      const float* lo = ring + (((i + 1) % PSW_SLOTS) * NL) * PSW_BW + 4 * lane;
+      const float* up = ring + (s_up * NL) * PSW_BW + 4 * lane;
+      const float* lo = ring + (s_lo * NL) * PSW_BW + 4 * lane;
       float ph[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -277,10 +287,12 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
     if (MODE == 0) *reinterpret_cast<float4*>(s_out + 20 * jl + k0) = make_float4(v[0], v[1], v[2], v[3]);
     __syncwarp();
     // the upper slot is free: fetch the screen rows of strip row i + 3 into it
-    if (nl > 0 && lane == 0 && i + 3 <= rows) {
+    if (nl > 0 && i + 3 <= rows) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(i + 3);
+      issue(s_up);
     }
+    s_up = s_lo;
+    if (++s_lo == PSW_SLOTS) { s_lo = 0; par_lo ^= 1u; }
     if (MODE == 0) {
       // lattice pass: Q[j][u] = sum_k f[16u + k] row[16j + k], one (chunk j, offset u) per lane
       const float4* q4 = reinterpret_cast<const float4*>(s_out + 20 * jl);
@@ -301,8 +313,9 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
           const int j = lane - 3 + u;
           if (j >= 0 && j < 8) t += s_q[4 * j + u];
         }
-        P.Tp[(((size_t)e * p.n + y) * P.nb + cb) * PSW_TP + lane] = t;
+        *tp = t;
       }
+      tp += P.nb * PSW_TP;
       __syncwarp();
     }
   }
