@@ -18,6 +18,7 @@
 #include "wfs_tc.cuh"
 #include "geo_kernels.cuh"
 #include "pupil_sweep.cuh"
+#include "denoise_kernels.cuh"
 
 static char g_create_error[512] = "";
 
@@ -283,6 +284,7 @@ static size_t table_expected_bytes(const aom_ctx* ctx, int t, int index) {
     case AOM_T_ACTOR_BH: return A * 2 * c.actor_out * 4;
     case AOM_T_GEO_PROJ: return (size_t)c.nactu * AOM_LD(c.nactu) * 4;
     case AOM_T_GEO_SIFN: return (size_t)c.nactu * 4;
+    case AOM_T_DENOISER: return (size_t)DN_PARAM_FLOATS * 4;
   }
   return 0;
 }
@@ -1164,6 +1166,33 @@ extern "C" int aom_set_bincube(aom_ctx* ctx, const float* dcube, void* stream) {
   if (!ctx || !dcube) return fail(ctx, AOM_ERR_INVALID, "null argument");
   (void)stream;
   ctx->cube_override = dcube;
+  return AOM_OK;
+}
+
+extern "C" int aom_denoise(aom_ctx* ctx, const float* din, float* dout, long long n_spots, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  NEED(AOM_T_DENOISER, 0);
+  const aom_config& c = ctx->cfg;
+  if (!din) {
+    if (!ctx->bincube) return fail(ctx, AOM_ERR_STATE, "no detector cube: run aom_comp_wfs_image with the keep-image flag first");
+    din = ctx->bincube;
+    n_spots = (long long)c.n_env * c.nvalid;
+  }
+  if (n_spots < 0) return fail(ctx, AOM_ERR_INVALID, "negative spot count");
+  const bool in_place = dout == nullptr;
+  if (in_place) {
+    if (din != ctx->bincube) return fail(ctx, AOM_ERR_INVALID, "in-place denoising needs the context's detector cube as input");
+    dout = ctx->bincube;
+  }
+  if (n_spots > 0) {
+    CU(cudaFuncSetAttribute(denoise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_SMEM_BYTES));
+    const long long batches = (n_spots + DN_G - 1) / DN_G;
+    const int grid = (int)(batches < ctx->num_sms ? batches : ctx->num_sms);
+    denoise_kernel<<<grid, DN_THREADS, DN_SMEM_BYTES, (cudaStream_t)stream>>>(din, dout, n_spots,
+                                                                              (const float*)ctx->tab[AOM_T_DENOISER][0]);
+    KCHECK();
+  }
+  if (in_place) ctx->cube_override = ctx->bincube;
   return AOM_OK;
 }
 

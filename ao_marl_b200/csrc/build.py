@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libaomarl.so")
 SOURCES = ["aomarl.cu"]
-HEADERS = ["atmos_kernels.cuh", "gemm_kernels.cuh", "gemm_tc.cuh", "rtc_kernels.cuh", "wfs_kernels.cuh", "wfs_mma.cuh", "wfs_tma.cuh", "wfs_pipe.cuh", "wfs_tc.cuh", "geo_kernels.cuh", "pupil_sweep.cuh", "fft16.cuh", "twiddles.cuh",
+HEADERS = ["atmos_kernels.cuh", "gemm_kernels.cuh", "gemm_tc.cuh", "rtc_kernels.cuh", "wfs_kernels.cuh", "wfs_mma.cuh", "wfs_tma.cuh", "wfs_pipe.cuh", "wfs_tc.cuh", "geo_kernels.cuh", "pupil_sweep.cuh", "denoise_kernels.cuh", "fft16.cuh", "twiddles.cuh",
            "rng.cuh", "../../include/aomarl.h"]
 
 

@@ -7,8 +7,13 @@ unchanged; `Autoencoder` mirrors the reference wrapper (autoencoder_models.py:19
 (rlSupervisor.py:857-891), here the whole [E * nvalid, 1, 16, 16] cube of a frame goes through the network in
 chunks and the result feeds aom_set_bincube / aom_do_centroids without leaving the device.
 
-The network itself runs on cuDNN through PyTorch (library code; a hand-written tcgen05 implicit-GEMM kernel is
-the next step for this row): 3.42 MFLOP per subaperture, 4.1 GFLOP per 40x40 frame.
+On the product path the network is ONE hand-written fused CUDA kernel (csrc/denoise_kernels.cuh, `aom_denoise`):
+`Autoencoder(config, sim=simulator)` packs the checkpoint into the kernel's layout and every `predict` of a CUDA tensor
+goes through the library.  The torch module below is the holder of the reference's parameter names (checkpoint
+loading, the golden-vector test against the reference's own module on the CPU) and what `predict` uses when no
+simulator is attached (host-side tooling); measured on B200 it needs 3.5 ms per environment through cuDNN in float32
+(0.36 ms with TF32 allowed) against the fused kernel's figure in DESIGN.md section 4.
+3.42 MFLOP per subaperture, 4.1 GFLOP per 40x40 frame and environment.
 """
 import os
 
@@ -43,6 +48,27 @@ class DenoisingAutoencoderCNN2DSingleSubapeture(nn.Module):
         return torch.sigmoid(x) if self.criterion == "BCE" else x
 
 
+def pack_weights(state_dict):
+    """Parameters in the fused kernel's order and layout (csrc/denoise_kernels.cuh: DN_E1W ... DN_D3B): convolution
+    weights as [input channel][tap][output channel], biases after each, padded to a multiple of four floats."""
+    sd = {k: np.asarray(v.detach().cpu() if hasattr(v, "detach") else v, dtype=np.float32) for k, v in state_dict.items()}
+    parts = []
+    for name in ("encoder1", "encoder2", "encoder3"):            # Conv2d weight [co][ci][ky][kx]
+        w = sd[name + ".weight"]
+        parts += [w.transpose(1, 2, 3, 0).reshape(-1), sd[name + ".bias"]]
+    for name in ("decoder1", "decoder2"):                        # ConvTranspose2d weight [ci][co][ky][kx]
+        w = sd[name + ".weight"]
+        parts += [w.transpose(0, 2, 3, 1).reshape(-1), sd[name + ".bias"]]
+    parts += [sd["decoder3.weight"].reshape(-1), sd["decoder3.bias"]]      # [16][1][3][3] -> [ci][tap]
+    flat = np.concatenate(parts).astype(np.float32)
+    expect = 144 + 16 + 4608 + 32 + 18432 + 64 + 32768 + 32 + 8192 + 16 + 144 + 1
+    if flat.size != expect:
+        raise ValueError("Dimension mismatch: the checkpoint is not the per-subaperture CNN (%d parameters)" % flat.size)
+    out = np.zeros((flat.size + 3) & ~3, dtype=np.float32)
+    out[:flat.size] = flat
+    return out
+
+
 def load_weights(name_or_path):
     """state_dict from a reference checkpoint (torch.save of model.state_dict()) or a shipped .npz export."""
     path = name_or_path
@@ -57,7 +83,7 @@ def load_weights(name_or_path):
 class Autoencoder:
     """Reference-shaped wrapper: `Autoencoder(config)` with config.autoencoder = {'type', 'path'}."""
 
-    def __init__(self, config, device=None, chunk=65536):
+    def __init__(self, config, device=None, chunk=65536, sim=None):
         ae = config.autoencoder if hasattr(config, "autoencoder") else dict(config)
         self.type = str(ae.get("type", "cnn_single_subaperture")).lower()
         if self.type != "cnn_single_subaperture":
@@ -68,10 +94,21 @@ class Autoencoder:
             self.model.load_state_dict(load_weights(ae["path"]))
         self.model.to(self.device).eval()
         self.chunk = int(chunk)
+        self.sim = None
+        if sim is not None:
+            self.attach(sim)
+
+    def attach(self, sim):
+        """Route `predict` through the fused CUDA kernel of this simulator context (uploads the packed parameters)."""
+        sim.set_denoiser(pack_weights(self.model.state_dict()))
+        self.sim = sim
 
     @torch.no_grad()
     def predict(self, noisy_tensor, only_inference_time=False):
         """[..., 16, 16] (or [..., 256]) spots -> denoised spots of the same shape, on the input's device."""
+        if self.sim is not None:
+            x = torch.as_tensor(noisy_tensor, dtype=torch.float32, device="cuda")
+            return self.sim.denoise(x.contiguous())
         x = torch.as_tensor(noisy_tensor, dtype=torch.float32, device=self.device)
         shape = x.shape
         x = x.reshape(-1, 1, 16, 16)

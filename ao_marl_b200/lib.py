@@ -40,7 +40,7 @@ class AomConfig(ctypes.Structure):
 TABLES = ["AB", "STENCIL", "MPUPIL", "HALFXY", "SUB_X0", "SUB_Y0", "FLUX", "STAMP1D", "ACT_MAP", "TT_PLANES",
           "CMAT", "V2M", "M2V", "FREEDOM", "ACTION_MAP", "STATE_MAP", "NORM_DM_MEAN", "NORM_DM_STD",
           "NORM_RES_MEAN", "NORM_RES_STD", "AGENT_IDX", "AGENT_ACT", "AGENT_REWARD", "ACTOR_W1", "ACTOR_B1",
-          "ACTOR_W2", "ACTOR_B2", "ACTOR_WH", "ACTOR_BH", "GEO_PROJ", "GEO_SIFN"]
+          "ACTOR_W2", "ACTOR_B2", "ACTOR_WH", "ACTOR_BH", "GEO_PROJ", "GEO_SIFN", "DENOISER"]
 T = {name: i for i, name in enumerate(TABLES)}
 BUFFERS = ["SCREEN", "RING_OX", "RING_OY", "SLOPES", "ERR", "COM", "VOLTS", "BINCUBE", "PHASE", "MODES",
            "RES_MODES", "STATE", "REWARD", "ACTION", "ACTION_MEAN", "STREHL", "GEO_COM", "GEO_VOLTS", "STREHL_GEO", "GEO_PROJ"]
@@ -49,7 +49,7 @@ _INT_BUFFERS = {"RING_OX", "RING_OY"}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
            "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_wfs_time_ms", "aom_raytrace_wfs",
-           "aom_comp_strehl", "aom_reset_strehl", "aom_do_control_geo", "aom_apply_control_geo", "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
+           "aom_comp_strehl", "aom_reset_strehl", "aom_do_control_geo", "aom_apply_control_geo", "aom_denoise", "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
            "aom_set_gain", "aom_set_loop", "aom_reset_dm", "aom_set_dm_volts", "aom_rl_control",
            "aom_state_begin", "aom_state_end", "aom_reward", "aom_actor_forward", "aom_step", "aom_gemm_tn",
            "aom_pixel_noise"]
@@ -93,6 +93,9 @@ def load_library():
     lib.aom_wfs_kernel.restype = ctypes.c_char_p
     lib.aom_comp_strehl.argtypes = [vp, i32, f32, i32, vp]
     lib.aom_reset_strehl.argtypes = [vp, vp]
+    lib.aom_do_control_geo.argtypes = [vp, vp]
+    lib.aom_apply_control_geo.argtypes = [vp, vp]
+    lib.aom_denoise.argtypes = [vp, vp, vp, i64, vp]
     lib.aom_set_bincube.argtypes = [vp, vp, vp]
     lib.aom_do_centroids.argtypes = [vp, vp]
     lib.aom_do_control.argtypes = [vp, vp]
@@ -402,6 +405,26 @@ class Simulator:
 
     def reset_strehl(self):
         self._check(self.lib.aom_reset_strehl(self._ctx, self.stream), "aom_reset_strehl")
+
+    def set_denoiser(self, packed):
+        """Upload the denoiser's parameters (ao_marl_b200.denoiser.pack_weights)."""
+        self.set_table("DENOISER", np.asarray(packed, dtype=np.float32))
+
+    def denoise(self, cube=None, out=None):
+        """Fused CNN denoiser.  cube None: the last frame's detector cube, in place, feeding the next do_centroids;
+        otherwise a CUDA float32 tensor [..., 256] (or [..., 16, 16]), returns the denoised tensor of the same shape."""
+        if cube is None:
+            self._check(self.lib.aom_denoise(self._ctx, None, None, 0, self.stream), "aom_denoise")
+            return self.buffer("BINCUBE").view(self.n_env, self.cfg.nvalid, 256)
+        torch = self.torch
+        x = cube if (cube.is_cuda and cube.dtype == torch.float32 and cube.is_contiguous()) else \
+            cube.to(device="cuda", dtype=torch.float32).contiguous()
+        if x.numel() % 256:
+            raise ValueError("Dimension mismatch")
+        y = torch.empty_like(x) if out is None else out
+        self._check(self.lib.aom_denoise(self._ctx, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()),
+                                         x.numel() // 256, self.stream), "aom_denoise")
+        return y
 
     def set_bincube(self, cube):
         self._cube_keepalive = cube

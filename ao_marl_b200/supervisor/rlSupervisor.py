@@ -76,6 +76,8 @@ class RlSupervisor:
         self.freedom_vector = self.rl.freedom
         self.sim = Simulator(t, n_env, self.rl)
         self.n_env = int(n_env)
+        if autoencoder is not None and hasattr(autoencoder, "attach"):
+            autoencoder.attach(self.sim)  # per-subaperture CNN on the fused kernel (aom_denoise)
 
         ctrl = config.p_controllers[0]
         self.tel = TelescopeB200(self.sim, config)
@@ -149,6 +151,9 @@ class RlSupervisor:
     def autoencoder_denoising(self):
         """bincube -> denoiser -> back into the centroider input, all on the device (rlSupervisor.py:876-891
         does a host round trip and a python loop over subapertures)."""
+        if getattr(self.autoencoder, "sim", None) is self.sim:
+            self.sim.denoise()            # fused kernel, in place, feeds the next do_centroids
+            return
         cube = self.wfs.get_bincube()
         E, nv = cube.shape[0], cube.shape[1]
         den = self.autoencoder.predict(cube.reshape(E * nv, 16, 16))

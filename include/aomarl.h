@@ -115,6 +115,8 @@ typedef enum aom_table {
   AOM_T_ACTOR_BH,      /* float [n_agents][2*actor_out] */
   AOM_T_GEO_PROJ,      /* float [nactu][ld(nactu)]    -(IF IF^T)^+ of the geometric controller (rtc_init.py:418-448) */
   AOM_T_GEO_SIFN,      /* float [nactu]        pupil sum of each influence row / number of pupil points           */
+  AOM_T_DENOISER,      /* float [64452]        parameters of the per-subaperture denoiser, packed per layer as
+                                               [input channel][tap][output channel] + bias (autoencoder_models.py:130-197) */
   AOM_T_COUNT
 } aom_table;
 
@@ -235,6 +237,13 @@ int aom_apply_control_geo(aom_ctx* ctx, void* stream);
 /* Replace the detector image (RlSupervisor.autoencoder_denoising -> set_binimg, rlSupervisor.py:876-891):
  * device pointer to float [E][nvalid][npix*npix]; the next aom_do_centroids reads it. */
 int aom_set_bincube(aom_ctx* ctx, const float* dcube, void* stream);
+
+/* RlSupervisor.autoencoder_denoising (rlSupervisor.py:876-891) -> Autoencoder.predict (src/autoencoder/
+ * autoencoder_models.py:199-240) for the per-subaperture CNN: every 16x16 spot of din [n_spots][256] through the six
+ * layers in one fused kernel, result to dout.  din == NULL: the detector cube of the last frame (AOM_B_BINCUBE, needs
+ * flag bit2 of aom_comp_wfs_image); dout == NULL: in place, and the next aom_do_centroids reads the denoised cube
+ * (what set_binimg does in the reference).  n_spots is ignored when din == NULL. */
+int aom_denoise(aom_ctx* ctx, const float* din, float* dout, long long n_spots, void* stream);
 
 /* RtcCompass.do_centroids / do_control / set_command / apply_control (rtcCompass.py:557-563, 527-547, 463-473, 573-582) */
 int aom_do_centroids(aom_ctx* ctx, void* stream);
