@@ -6,12 +6,13 @@
 //   convT4x4s2(64->32) relu | convT4x4s2(32->16) relu | convT3x3(16->1)
 // 1.71 M multiply-adds per spot, 64 449 parameters shared by all spots.
 //
-// One fused kernel: a CTA of 256 threads carries DN_G = 4 spots through all six layers with the activations in shared
+// One fused kernel: a CTA of 384 threads carries DN_G = 6 spots through all six layers with the activations in shared
 // memory (two ping-pong buffers per spot, zero borders instead of bounds checks); nothing but the 1 KB spot and the
-// 1 KB result touches HBM.  Arithmetic is plain float32 FFMA -- the result has to match the reference's float32 module
+// 1 KB result touches HBM.  (Measured on B200: 4 spots / 256 threads / 233 registers 34.3 TFLOP/s, 6 / 384 / 167
+// 37.8 TFLOP/s, 7 / 448 / 128 with spills 34.2 TFLOP/s.)  Arithmetic is plain float32 FFMA -- the result has to match the reference's float32 module
 // (tests/golden/ref_autoencoder.npz), and the spots are raw photo-electron counts, so no reduced-precision operand
 // format is safe without a per-spot scale.  Every thread owns a register tile (2 rows x 4 columns x CB channels); the
-// 256 threads of a layer are indexed (tile position, spot, channel group) with the channel group slowest, so the
+// threads of a layer are indexed (tile position, spot, channel group) with the channel group slowest, so the
 // lanes of a warp read the same weights: weight loads are warp-uniform broadcasts from L1/L2 in the prepacked layout
 // [input channel][tap][output channel] (aom_table AOM_T_DENOISER, packed by ao_marl_b200/denoiser.py::pack_weights).
 // A stride-2 transposed 4x4 convolution is four independent 2x2 convolutions, one per output parity class:
@@ -19,8 +20,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#define DN_G 4
-#define DN_THREADS 256
+#define DN_G 6
+#define DN_THREADS 384
 // Activation layouts [channel][row][pitch] and the distance between the spots of a batch, chosen so that the 32 lanes
 // of a warp (tile positions x spots) hit 32 different banks when they read their input windows (model of the address
 // patterns: profiles/dev/denoise_banks.py; the first version with pitch = side + 2 and strides that were multiples of
