@@ -1432,7 +1432,9 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
     rc = aom_apply_control_geo(ctx, gs); if (rc) return rc;
     if (fork) CU(cudaEventRecord(ctx->ev_geo, gs));
   }
-  rc = aom_comp_wfs_image(ctx, 3, ctx->cfg.noise, stream); if (rc) return rc;
+  const bool denoise = ctx->opt[AOM_OPT_DENOISE] != 0;
+  rc = aom_comp_wfs_image(ctx, denoise ? 7 : 3, ctx->cfg.noise, stream); if (rc) return rc;
+  if (denoise) { rc = aom_denoise(ctx, nullptr, nullptr, 0, stream); if (rc) return rc; }
   rc = aom_do_centroids(ctx, stream); if (rc) return rc;
   rc = aom_do_control(ctx, stream); if (rc) return rc;
   if (ctx->state) { rc = aom_state_end(ctx, stream); if (rc) return rc; }

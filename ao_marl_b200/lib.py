@@ -397,7 +397,11 @@ class Simulator:
 
     def set_pupil_path(self, name):
         """Kernels behind comp_strehl / do_control_geo: 'sweep' (default) or 'pixel' (cross-check path)."""
-        self._check(self.lib.aom_set_option(self._ctx, 4, {"sweep": 0, "pixel": 1}[name]), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, 5, {"sweep": 0, "pixel": 1}[name]), "aom_set_option")
+
+    def step_with_denoiser(self, on=True):
+        """aom_step runs the fused denoiser between the sensor frame and the centroider (AOM_OPT_DENOISE)."""
+        self._check(self.lib.aom_set_option(self._ctx, 4, 1 if on else 0), "aom_set_option")
 
     def step_with_geo(self, on=True):
         """aom_step also runs the geometric controller every frame (AOM_OPT_GEO)."""

@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 4096 / 1024)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--denoise", action="store_true",
+                    help="run the fused per-subaperture denoiser inside every step (row a-6; the *_d0_noise files use it)")
     ap.add_argument("--geo", action="store_true",
                     help="also run the parameter file's geometric controller every step (SURVEY 8(f) rank 4; off by default)")
     ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt", "tensor_reg", "tensor_pipe", "tcgen05"],
@@ -245,6 +247,10 @@ def run_ours(args):
     t_build = time.perf_counter()
     sim, t, rl = build_system(wl["par"], E, env_rl=dict(wl["env_rl"]), world_size=wl["world_size"], seed=0)
     sim.set_wfs_path(args.wfs_path)
+    if args.denoise:
+        from ao_marl_b200.denoiser import Autoencoder
+        Autoencoder(dict(type="cnn_single_subaperture", path="autoencoder_M9_rms_3"), device="cuda", sim=sim)
+        sim.step_with_denoiser(True)
     if args.geo:
         from ao_marl_b200.init import geo as geo_b
         sim.set_geo(*geo_b.build_geo(t))
@@ -359,7 +365,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "envs_per_gpu": E, "total_envs": E * world,
                        "parallelism": "env-sharded x%d, no collective on the step path" % world, "wfs_path": args.wfs_path,
-                       "geo_controller": bool(args.geo),
+                       "geo_controller": bool(args.geo), "denoiser": bool(args.denoise),
                        "l2": "inputs larger than L2 (%.1f GB of screens per GPU)" % (
                            sum(int(n) ** 2 for n in t.dim_screens) * 4 * E / 1e9),
                        "us_per_frame": ms / args.steps / E * 1e3, "build_s": t_build},

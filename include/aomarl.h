@@ -152,6 +152,9 @@ typedef enum aom_option {
   AOM_OPT_TIME_WFS,     /* != 0: bracket every sensor-kernel launch with CUDA events (read with aom_wfs_time_ms) */
   AOM_OPT_GEO,          /* != 0: aom_step also runs the geometric controller every frame, as next_part_one does when
                            the parameter file lists one (rlSupervisor.py:1036-1046); needs the AOM_T_GEO_* tables */
+  AOM_OPT_DENOISE,      /* != 0: aom_step keeps the detector cube and runs aom_denoise between the sensor frame and the
+                           centroider, as next_part_one_integrator does when an autoencoder is configured
+                           (rlSupervisor.py:968-979); needs AOM_T_DENOISER */
   AOM_OPT_PUPIL_PATH,   /* which kernels sweep the pupil-plane phase for aom_comp_strehl / aom_do_control_geo */
   AOM_OPT_COUNT
 } aom_option;

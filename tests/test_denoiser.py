@@ -100,3 +100,44 @@ def test_in_place_denoising_feeds_the_centroider(static10):
         sim.check_device()
     finally:
         sim.close()
+
+
+@pytest.mark.gpu
+def test_step_with_denoiser_equals_the_manual_sequence(static10, oracle_imat10):
+    """AOM_OPT_DENOISE: aom_step = apply_control, move_atmos, frame (image kept), denoise, centroids, control --
+    bit-identical to the calls RlSupervisor.next_part_one_integrator makes one by one (rlSupervisor.py:949-987)."""
+    import copy
+    from ao_marl_b200.init import rtc as rtc_b
+    from ao_marl_b200.lib import Simulator
+    t = copy.copy(static10)
+    t.imat = oracle_imat10
+    t.cmat = rtc_b.cmat_with_btt(t.imat, t.Btt, 5)
+    seeds = np.array([21, 22], dtype=np.int64)
+    sims = [Simulator(t, 2, rl=None) for _ in range(2)]
+    try:
+        for sim in sims:
+            Autoencoder(dict(type="cnn_single_subaperture", path="autoencoder_M9_rms_3"), device="cuda", sim=sim)
+            sim.reset(seeds)
+        sims[0].step_with_denoiser(True)
+        for _ in range(3):
+            sims[0].step(mode=2)
+            m = sims[1]
+            m.apply_control()
+            m.move_atmos()
+            m.comp_wfs_image(keep_image=True)
+            m.denoise()
+            m.do_centroids()
+            m.do_control()
+        for name, n in (("SLOPES", t.nslopes), ("COM", t.nactu)):
+            assert torch.equal(sims[0].rows(name, n), sims[1].rows(name, n)), name
+        raw = Simulator(t, 2, rl=None)
+        raw.reset(seeds)
+        for _ in range(3):
+            raw.step(mode=2)
+        assert not torch.equal(raw.rows("SLOPES", t.nslopes), sims[0].rows("SLOPES", t.nslopes))
+        raw.close()
+        for sim in sims:
+            sim.check_device()
+    finally:
+        for sim in sims:
+            sim.close()
