@@ -395,7 +395,9 @@ static int geo_prepare(aom_ctx* ctx) {
   CU(dalloc(&ctx->geo_b, E * ctx->lda));
   {
     // lattice-column sums of every pupil row: [E][n][gp], or the sweep's per-block partials [E][n][nb][PSW_TP]
-    const size_t per_row = (size_t)ctx->geo_gp > (size_t)((c.n + 64 + 127) / 128 + 1) * PSW_TP ? (size_t)ctx->geo_gp : (size_t)((c.n + 64 + 127) / 128 + 1) * PSW_TP;
+    const int xs0 = c.pzt_i1_0 - c.pzt_off;
+    const size_t nb = xs0 <= 0 ? (size_t)(c.n - xs0 + 127) / 128 : 0;
+    const size_t per_row = nb * PSW_TP > (size_t)ctx->geo_gp ? nb * PSW_TP : (size_t)ctx->geo_gp;
     CU(dalloc(&ctx->geo_T, E * c.n * per_row));
   }
   CU(dalloc(&ctx->geo_mom, E * 4));
@@ -1407,7 +1409,9 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   // The turbulence update (exact-fp32 extrusion GEMMs on the FP32 pipe) touches only the screens, the rl
   // half-step (tensor-core GEMMs of the actors and the modal projections) only the controller state: they run
   // side by side on two streams and join before the sensor frame.
-  const bool fork = ctx->cfg.n_layers > 0 && ctx->seeded;
+  const bool atmos_done = (mode & AOM_STEP_ATMOS_DONE) != 0;
+  mode &= ~AOM_STEP_ATMOS_DONE;
+  const bool fork = ctx->cfg.n_layers > 0 && ctx->seeded && !atmos_done;
   if (fork) {
     CU(cudaEventRecord(ctx->ev_fork, st));
     CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
@@ -1422,7 +1426,7 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   // linear half-step: AoEnv.linear_step -> RlSupervisor.next_part_one (rlSupervisor.py:1015-1051)
   rc = aom_state_begin(ctx, stream); if (rc) return rc;
   if (fork) CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-  else { rc = aom_move_atmos(ctx, stream); if (rc) return rc; }
+  else if (!atmos_done) { rc = aom_move_atmos(ctx, stream); if (rc) return rc; }
   // second controller of the production parameter files (next_part_one loops over p_controllers,
   // rlSupervisor.py:1036-1046): it reads only the moved screens, so it runs beside the sensor frame
   const bool geo = ctx->opt[AOM_OPT_GEO] != 0;

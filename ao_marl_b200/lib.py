@@ -495,8 +495,11 @@ class Simulator:
     def actor_forward(self, eval_mode=False):
         self._check(self.lib.aom_actor_forward(self._ctx, int(bool(eval_mode)), self.stream), "aom_actor_forward")
 
-    def step(self, mode=0, eval_mode=False):
-        self._check(self.lib.aom_step(self._ctx, int(mode), int(bool(eval_mode)), self.stream), "aom_step")
+    def step(self, mode=0, eval_mode=False, atmos_done=False):
+        """One env-step of the whole batch.  atmos_done: the caller already ran move_atmos for this step (for example
+        on a second stream while the actions were on their way from the host)."""
+        self._check(self.lib.aom_step(self._ctx, int(mode) | (8 if atmos_done else 0), int(bool(eval_mode)), self.stream),
+                    "aom_step")
 
     def gemm_tn(self, A, Bm, bias=None, relu=False):
         """C = A . Bm^T on padded device tensors [M, ld] / [N, ld]; returns [M, LD(N)] (test entry point)."""

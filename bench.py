@@ -319,10 +319,20 @@ def run_ours(args):
     barrier()
     f0, f1 = ev(enable_timing=True), ev(enable_timing=True)
     f0.record()
+    atmos_stream = torch.cuda.Stream()
+    frame_done = ev()
     for i in range(k_e2e):
         b = i & 1
         act_d.copy_(act_h, non_blocking=True)       # H2D: this step's actions
-        sim.step(mode=1)                            # rl half-step + reward + linear half-step
+        main.wait_stream(atmos_stream)              # the turbulence of this step was advanced during the last round trip
+        sim.step(mode=1, atmos_done=i > 0)          # rl half-step + reward + linear half-step
+        if i + 1 < k_e2e:
+            # the next step's turbulence does not depend on the actions: it runs on a second stream while the
+            # actions make their round trip through the host (the GPU would idle on PCIe and the host sync)
+            frame_done.record(main)
+            atmos_stream.wait_event(frame_done)
+            with torch.cuda.stream(atmos_stream):
+                sim.move_atmos()
         sim.actor_forward(False)                    # next actions from the new state
         act_h.copy_(act_d, non_blocking=True)       # D2H: next actions
         if i >= 2:
@@ -386,7 +396,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(E * rl.action_dim * 4),
                     "d2h_bytes_per_step": int(E * (rl.action_dim + rl.state_dim + rl.n_agents) * 4), "steps": k_e2e,
                     "note": "actions H2D + D2H synchronously every step (host in the loop); state and rewards D2H from a "
-                            "device snapshot on a copy stream, overlapped with the next step"},
+                            "device snapshot on a copy stream, overlapped with the next step; the next step's turbulence "
+                            "update (independent of the actions) runs on a second stream during the round trip"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -276,7 +276,10 @@ int aom_actor_forward(aom_ctx* ctx, int eval_mode, void* stream);
 
 /* One whole env-step: rl half-step (rl_control + apply_control + reward) and linear half-step
  * (move_atmos + WFS frame + centroids + control + state) -- TrainerRPC.env_step (train_rpc.py:633-648).
- * mode 0: actions from aom_actor_forward on the current state; 1: actions from AOM_B_ACTION; 2: integrator only. */
+ * mode 0: actions from aom_actor_forward on the current state; 1: actions from AOM_B_ACTION; 2: integrator only.
+ * mode | AOM_STEP_ATMOS_DONE: the caller has already advanced the turbulence for this step with aom_move_atmos (it
+ * does not depend on the actions, so a host-in-the-loop caller can run it while the actions travel over PCIe). */
+#define AOM_STEP_ATMOS_DONE 8
 int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream);
 
 /* Generic device GEMM used by the path, exposed for the parity tests:

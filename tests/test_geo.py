@@ -222,3 +222,35 @@ def test_40x40_geo_fit():
             assert abs(s_geo[e, 2] - res.var()) < 2e-3 * res.var()
     finally:
         sim.close()
+
+
+@pytest.mark.gpu
+def test_step_with_the_turbulence_advanced_by_the_caller(static10, oracle_imat10):
+    """aom_step(mode | AOM_STEP_ATMOS_DONE) after an explicit aom_move_atmos == plain aom_step, bit for bit."""
+    import copy
+    import torch
+    from ao_marl_b200.init import rtc as rtc_b
+    from ao_marl_b200.lib import Simulator
+    t = copy.copy(static10)
+    t.imat = oracle_imat10
+    t.cmat = rtc_b.cmat_with_btt(t.imat, t.Btt, 5)
+    seeds = np.array([31, 32, 33], dtype=np.int64)
+    a, b = Simulator(t, 3, rl=None), Simulator(t, 3, rl=None)
+    try:
+        a.reset(seeds)
+        b.reset(seeds)
+        side = torch.cuda.Stream()
+        for _ in range(4):
+            a.step(mode=2)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                b.move_atmos()
+            torch.cuda.current_stream().wait_stream(side)
+            b.step(mode=2, atmos_done=True)
+        for name, n in (("SLOPES", t.nslopes), ("COM", t.nactu), ("VOLTS", t.nactu)):
+            assert torch.equal(a.rows(name, n), b.rows(name, n)), name
+        a.check_device()
+        b.check_device()
+    finally:
+        a.close()
+        b.close()
