@@ -30,6 +30,7 @@
 #define GTC_BN 128
 #define GTC_BK 16
 #define GTC_STAGES 3
+#define GTC_INFLIGHT 3                                        // slabs of global loads in flight per loader thread (register sets)
 #define GTC_TILE_BYTES (GTC_BM * GTC_BK * 4)                 // 8 KB: one hi or lo slab of the A operand
 #define GTC_BTILE_BYTES(BN) ((BN) * GTC_BK * 4)               // one hi or lo slab of the B operand
 #define GTC_STAGE_BYTES_T(BN) (2 * GTC_TILE_BYTES + 2 * GTC_BTILE_BYTES(BN))   // A hi, A lo, B hi, B lo
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
     const int r0 = tid >> 2;                     // rows r0, r0 + 32, r0 + 64, r0 + 96
     // two slabs of global loads stay in flight (register sets 0 / 1): one slab alone left every stage waiting
     // for HBM/L2 latency longer than its three MMAs take
-    float4 va[2][4], vb[2][B_ITERS];
+    float4 va[GTC_INFLIGHT][4], vb[GTC_INFLIGHT][B_ITERS];
     auto load_regs = [&](int kb, float4 (&xa)[4], float4 (&xb)[B_ITERS]) {
       const int k = kb * GTC_BK + c * 4;
       const bool kin = k < p.K;
@@ -190,16 +191,18 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
           *reinterpret_cast<float4*>(st + B_OFF + GTC_BTILE_BYTES(BN) + off) = lo;
         }
       }
-      if (kb + 2 < nkb) load_regs(kb + 2, xa, xb);   // refill this register set two slabs ahead
+      if (kb + GTC_INFLIGHT < nkb) load_regs(kb + GTC_INFLIGHT, xa, xb);   // refill this register set GTC_INFLIGHT slabs ahead
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) gtc_mbar_arrive(full0 + 8 * s);
     };
-    if (nkb > 0) load_regs(0, va[0], vb[0]);
-    if (nkb > 1) load_regs(1, va[1], vb[1]);
-    for (int kb = 0; kb < nkb; kb += 2) {
-      stage_out(kb, va[0], vb[0]);
-      if (kb + 1 < nkb) stage_out(kb + 1, va[1], vb[1]);
+#pragma unroll
+    for (int j = 0; j < GTC_INFLIGHT; ++j)
+      if (j < nkb) load_regs(j, va[j], vb[j]);
+    for (int kb = 0; kb < nkb; kb += GTC_INFLIGHT) {
+#pragma unroll
+      for (int j = 0; j < GTC_INFLIGHT; ++j)
+        if (kb + j < nkb) stage_out(kb + j, va[j], vb[j]);
     }
 
     // ===== epilogue: TMEM lanes 32 warp .. 32 warp + 31 are rows m0 + 32 warp + lane =====

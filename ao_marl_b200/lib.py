@@ -46,6 +46,8 @@ BUFFERS = ["SCREEN", "RING_OX", "RING_OY", "SLOPES", "ERR", "COM", "VOLTS", "BIN
            "RES_MODES", "STATE", "REWARD", "ACTION", "ACTION_MEAN", "STREHL", "GEO_COM", "GEO_VOLTS", "STREHL_GEO", "GEO_PROJ"]
 B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
+OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH"]
+O = {name: i for i, name in enumerate(OPTIONS)}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
            "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_wfs_time_ms", "aom_raytrace_wfs",
@@ -274,7 +276,7 @@ class Simulator:
 
     def set_wfs_path(self, name):
         """Select the Shack-Hartmann frame kernel: 'tensor' (default), 'tensor_fast', 'tensor_reg' or 'simt'."""
-        self._check(self.lib.aom_set_option(self._ctx, 0, self.WFS_PATHS[name]), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, O["WFS_PATH"], self.WFS_PATHS[name]), "aom_set_option")
 
     def wfs_kernel(self):
         """Name of the kernel the next frame launches (and, via last_error, why the staged one is not used)."""
@@ -282,7 +284,7 @@ class Simulator:
 
     def time_wfs(self, on=True):
         """Bracket every sensor-kernel launch with CUDA events (read the mean with wfs_time_ms)."""
-        self._check(self.lib.aom_set_option(self._ctx, 2, 1 if on else 0), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, O["TIME_WFS"], 1 if on else 0), "aom_set_option")
 
     def wfs_time_ms(self):
         """(mean device time in ms, number of launches) of the sensor kernel since the last call."""
@@ -294,7 +296,7 @@ class Simulator:
 
     def set_gemm_path(self, name):
         """Select the GEMM kernel of the env-batched contractions: 'tcgen05' (default) or 'simt'."""
-        self._check(self.lib.aom_set_option(self._ctx, 1, self.GEMM_PATHS[name]), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, O["GEMM_PATH"], self.GEMM_PATHS[name]), "aom_set_option")
 
     def check_device(self):
         """Synchronise and raise if a kernel reported an asynchronous error."""
@@ -397,15 +399,15 @@ class Simulator:
 
     def set_pupil_path(self, name):
         """Kernels behind comp_strehl / do_control_geo: 'sweep' (default) or 'pixel' (cross-check path)."""
-        self._check(self.lib.aom_set_option(self._ctx, 5, {"sweep": 0, "pixel": 1}[name]), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, O["PUPIL_PATH"], {"sweep": 0, "pixel": 1}[name]), "aom_set_option")
 
     def step_with_denoiser(self, on=True):
         """aom_step runs the fused denoiser between the sensor frame and the centroider (AOM_OPT_DENOISE)."""
-        self._check(self.lib.aom_set_option(self._ctx, 4, 1 if on else 0), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, O["DENOISE"], 1 if on else 0), "aom_set_option")
 
     def step_with_geo(self, on=True):
         """aom_step also runs the geometric controller every frame (AOM_OPT_GEO)."""
-        self._check(self.lib.aom_set_option(self._ctx, 3, 1 if on else 0), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, O["GEO"], 1 if on else 0), "aom_set_option")
 
     def reset_strehl(self):
         self._check(self.lib.aom_reset_strehl(self._ctx, self.stream), "aom_reset_strehl")

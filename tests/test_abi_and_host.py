@@ -30,6 +30,8 @@ def test_table_and_buffer_enums_match_header():
     bufs = re.findall(r"^\s*AOM_B_([A-Z0-9_]+)", header, flags=re.M)
     assert [t for t in tabs if t != "COUNT"] == binding.TABLES
     assert [b for b in bufs if b != "COUNT"] == binding.BUFFERS
+    opts = re.findall(r"^\s*AOM_OPT_([A-Z0-9_]+)", header, flags=re.M)
+    assert [o for o in opts if o != "COUNT"] == binding.OPTIONS
 
 
 def test_no_cpu_path():
