@@ -428,6 +428,8 @@ class Simulator:
         if x.numel() % 256:
             raise ValueError("Dimension mismatch")
         y = torch.empty_like(x) if out is None else out
+        if x.numel() == 0:
+            return y                                         # an empty tensor has no device pointer to hand over
         self._check(self.lib.aom_denoise(self._ctx, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()),
                                          x.numel() // 256, self.stream), "aom_denoise")
         return y

@@ -667,3 +667,49 @@ def test_strehl_kernel_matches_the_materialised_phase(sim10, static10, torch):
     sim10.reset_strehl()
     assert float(sim10.buffer("STREHL").abs().max()) == 0.0
     sim10.check_device()
+
+
+def test_error_behaviour_and_edge_sizes(static10, torch):
+    """Edge cases of the C ABI: rejected sizes raise (ValueError for dimension problems, as the reference's
+    set_command does, rtcCompass.py:471-472), empty work is a no-op, calls before their prerequisites report
+    AOM_ERR_STATE instead of reading unset tables."""
+    import ctypes
+    from ao_marl_b200.denoiser import Autoencoder
+    from ao_marl_b200.lib import Simulator
+    with pytest.raises(ValueError):
+        Simulator(static10, 0, rl=None)
+    with pytest.raises(ValueError):
+        Simulator(static10, 65536, rl=None)
+    import copy
+    t = copy.copy(static10)
+    t.geo_proj = None                                        # another module may have built the projector tables
+    sim = Simulator(t, 1, rl=None, atmosphere=False)
+    try:
+        with pytest.raises(ValueError):
+            sim.set_table("MPUPIL", np.zeros(7, np.float32))
+        with pytest.raises(ValueError):
+            sim.set_command(torch.zeros((1, static10.nactu + 1), device="cuda"))
+        with pytest.raises(RuntimeError):
+            sim.denoise()                                    # no denoiser parameters uploaded
+        Autoencoder(dict(type="cnn_single_subaperture", path="autoencoder_M9_rms_3"), device="cuda", sim=sim)
+        with pytest.raises(RuntimeError):
+            sim.denoise()                                    # no detector cube kept yet
+        empty = torch.empty((0, 256), device="cuda")
+        assert sim.denoise(empty).shape == (0, 256)
+        with pytest.raises(ValueError):
+            sim.denoise(torch.zeros(100, device="cuda"))
+        with pytest.raises(RuntimeError):
+            sim.do_control_geo()                             # projector tables not uploaded
+        # no atmosphere: flat wavefront, zero slopes, unit Strehl, zero geometric command
+        sim.reset(np.array([1], dtype=np.int64))
+        sim.comp_wfs_image(noise=-1.0)
+        sim.do_centroids()
+        assert float(sim.rows("SLOPES", static10.nslopes).abs().max()) < 2e-6
+        s = sim.comp_strehl(1.65)
+        assert abs(float(s[0, 0]) - 1.0) < 1e-6 and float(s[0, 2]) == 0.0
+        from ao_marl_b200.init import geo
+        sim.set_geo(*geo.build_geo(static10))
+        assert float(sim.do_control_geo().abs().max()) == 0.0
+        sim.check_device()
+    finally:
+        sim.close()
