@@ -44,7 +44,7 @@ struct aom_ctx {
   float *slopes_frame, *slopes, *err_v, *com, *com1, *volts, *com_before;
   float *bincube, *phase;
   const float* cube_override;
-  double* tar_mom;            // [E][3] pupil sums of the target phase (aom_comp_strehl)
+  double* tar_mom;            // [E][5] pupil sums of the target phase (aom_comp_strehl)
   float* tar_acc;             // [E][2] running sums for the long-exposure figures
   int tar_n;
   // geometric controller (geo_kernels.cuh), allocated on first use
@@ -188,7 +188,7 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
   CU(dalloc(&ctx->volts, E * ctx->lda));
   CU(dalloc(&ctx->com_before, E * ctx->lda));
   CU(dalloc(&ctx->strehl, E * 4));
-  CU(dalloc(&ctx->tar_mom, E * 3));
+  CU(dalloc(&ctx->tar_mom, E * 5));
   CU(dalloc(&ctx->tar_acc, E * 2));
   if (cfg->nmodes > 0) {
     CU(dalloc(&ctx->modes, E * ctx->ldm));
@@ -366,13 +366,13 @@ static int sweep_launch_t(aom_ctx* ctx, const SweepParams& P, cudaStream_t st) {
 
 // MODE 0: Tp / mom = geometric projection ; MODE 1: mom = pupil sums of m, m phi, m phi^2
 template <int MODE>
-static int sweep_launch(aom_ctx* ctx, const WfsParams& w, float* Tp, double* mom, cudaStream_t st) {
+static int sweep_launch(aom_ctx* ctx, const WfsParams& w, float* Tp, double* mom, cudaStream_t st, float k2t = 0.f) {
   const aom_config& c = ctx->cfg;
   SweepParams P;
   memset(&P, 0, sizeof(P));
   P.w = w;
   P.maskw = ctx->sweep_mask; P.ttp = ctx->sweep_ttp;
-  P.Tp = Tp; P.mom = mom;
+  P.Tp = Tp; P.mom = mom; P.k2t = k2t;
   P.nb = ctx->sweep_nb;
   P.n_strips = (c.n + PSW_STRIP - 1) / PSW_STRIP;
   P.err = ctx->d_err;
@@ -1089,21 +1089,21 @@ extern "C" int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int acc
     p.volts = ctx->geo_volts;
   }
   int& n_le = geo ? ctx->geo_tar_n : ctx->tar_n;
-  CU(cudaMemsetAsync(ctx->tar_mom, 0, (size_t)c.n_env * 3 * sizeof(double), st));
+  CU(cudaMemsetAsync(ctx->tar_mom, 0, (size_t)c.n_env * 5 * sizeof(double), st));
   rc = sweep_prepare(ctx, st);
   if (rc) return rc;
   if (ctx->sweep_state == 1 && ctx->opt[AOM_OPT_PUPIL_PATH] == AOM_PUPIL_SWEEP) {
-    rc = sweep_launch<1>(ctx, p, nullptr, ctx->tar_mom, st);
+    rc = sweep_launch<1>(ctx, p, nullptr, ctx->tar_mom, st, (float)(2.0 * M_PI / (double)lambda_um));
     if (rc) return rc;
   } else {
     dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
-    target_moments_kernel<<<grid, blk, 0, st>>>(p, ctx->tar_mom);
+    target_moments_kernel<<<grid, blk, 0, st>>>(p, ctx->tar_mom, (float)(2.0 * M_PI / (double)lambda_um));
     KCHECK();
   }
   if (accumulate) n_le += 1;
   target_strehl_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(ctx->tar_mom, geo ? ctx->strehl_geo : ctx->strehl,
                                                              geo ? ctx->geo_acc : ctx->tar_acc, c.n_env,
-                                                             (float)(2.0 * M_PI / (double)lambda_um), accumulate ? n_le : 0);
+                                                             accumulate ? n_le : 0);
   KCHECK();
   return AOM_OK;
 }

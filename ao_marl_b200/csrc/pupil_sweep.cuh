@@ -6,7 +6,8 @@
 //           projected on the lattice columns (T[e][y][gx], see geo_kernels.cuh) + the pupil sums of the piston /
 //           tip-tilt rows;
 //   MODE 1  target Strehl (TargetCompass.comp_tar_image / comp_strehl, shesha/supervisor/components/targetCompass.py:139-196,
-//           Marechal form): atmosphere + mirrors, pupil sums of m, m phi, m phi^2.
+//           atmosphere + mirrors, pupil sums of m, m phi, m phi^2 (variance) and of m exp(i k phi): the on-axis
+//           intensity |<exp(i k phi)>|^2 is the peak of the PSF the reference's FFT would give for a tilt-free residual.
 //
 // Layout of the work.  A warp owns a 128-pixel column block of a strip of consecutive pupil rows of one environment:
 // one lane = four pixels of the current row.  Pupil row y needs the screen rows r(y), r(y)+1 of every layer, and
@@ -39,7 +40,9 @@ struct SweepParams {
   const uint32_t* maskw;    // [n][32 nb]     pupil mask, one byte per pixel, four per word (lattice frame, 0 outside)
   const float* ttp;         // [2][n][128 nb] tip-tilt planes in the lattice frame, zero outside the pupil frame
   float* Tp;                // MODE 0: [E][n][nb][PSW_TP]
-  double* mom;              // MODE 0: [E][4] sums of m phi, m phi tt_x, m phi tt_y ; MODE 1: [E][3] sums of m, m phi, m phi^2
+  double* mom;              // MODE 0: [E][4] sums of m phi, m phi tt_x, m phi tt_y
+                            // MODE 1: [E][5] sums of m, m phi, m phi^2, m cos(k phi), m sin(k phi)
+  float k2t;                // MODE 1: 2 pi / target wavelength
   int nb;                   // column blocks per row
   int n_strips;
   int* err;
@@ -185,7 +188,8 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
   int s_up = 0, s_lo = 1;                           // ring slots of the upper / lower screen rows of the current pupil row
   uint32_t par_lo = 0;                              // phase parity the lower slot completes next
 
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // MODE 0: s1 = sum v, s2 = sum v ttx, s3 = sum v tty ; MODE 1: s0 = count, s1 = sum v, s2 = sum v^2
+  // MODE 0: s1 = sum v, s2 = sum v ttx, s3 = sum v tty ; MODE 1: s0 = count, s1 = sum v, s2 = sum v^2, s3 / s4 = sum cos / sin (k v)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
   float tt0 = 0.f, tt1 = 0.f;
   const float* volts = nullptr;
   const bool dm = MODE == 1 && p.use_dm;
@@ -282,6 +286,14 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
       } else {
         s0 += (float)__popc(mask);
         s2 = fmaf(v[0], v[0], s2); s2 = fmaf(v[1], v[1], s2); s2 = fmaf(v[2], v[2], s2); s2 = fmaf(v[3], v[3], s2);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if ((mask >> (8 * c)) & 1u) {
+            float sn, cs;
+            wfm_sincos(P.k2t * v[c], sn, cs);
+            s3 += cs; s4 += sn;
+          }
+        }
       }
     }
     if (MODE == 0) *reinterpret_cast<float4*>(s_out + 20 * jl + k0) = make_float4(v[0], v[1], v[2], v[3]);
@@ -326,6 +338,7 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
     s1 += __shfl_xor_sync(0xffffffffu, s1, sft);
     s2 += __shfl_xor_sync(0xffffffffu, s2, sft);
     s3 += __shfl_xor_sync(0xffffffffu, s3, sft);
+    s4 += __shfl_xor_sync(0xffffffffu, s4, sft);
   }
   if (lane == 0) {
     if (MODE == 0) {
@@ -333,9 +346,11 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
       if (s2 != 0.f) atomicAdd(P.mom + (size_t)e * 4 + 1, (double)s2);
       if (s3 != 0.f) atomicAdd(P.mom + (size_t)e * 4 + 2, (double)s3);
     } else {
-      if (s0 != 0.f) atomicAdd(P.mom + (size_t)e * 3 + 0, (double)s0);
-      if (s1 != 0.f) atomicAdd(P.mom + (size_t)e * 3 + 1, (double)s1);
-      if (s2 != 0.f) atomicAdd(P.mom + (size_t)e * 3 + 2, (double)s2);
+      if (s0 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 0, (double)s0);
+      if (s1 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 1, (double)s1);
+      if (s2 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 2, (double)s2);
+      if (s3 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 3, (double)s3);
+      if (s4 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 4, (double)s4);
     }
   }
 }

@@ -330,10 +330,11 @@ __global__ void wfs_phase_kernel(WfsParams p, float* phase) {
 }
 
 // Phase statistics over the pupil for the target's Strehl (TargetCompass.comp_strehl / get_strehl,
-// targetCompass.py:139-196: get_strehl()[2] is the phase variance): the phase of wfs_phase_kernel is evaluated per
-// pixel and reduced on the fly -- sum m, sum m phi, sum m phi^2 per environment (double atomics) -- instead of
-// materialising [E][n][n].  grid (ceil(n/32), ceil(n/8), E), block (32, 8).
-__global__ void target_moments_kernel(WfsParams p, double* mom) {
+// targetCompass.py:139-196: get_strehl()[2] is the phase variance, [0] the peak of the PSF): the phase of
+// wfs_phase_kernel is evaluated per pixel and reduced on the fly -- sum m, sum m phi, sum m phi^2, sum m cos(k phi),
+// sum m sin(k phi) per environment (double atomics) -- instead of materialising [E][n][n].
+// grid (ceil(n/32), ceil(n/8), E), block (32, 8).  (Per-pixel cross-check form of pupil_sweep.cuh MODE 1.)
+__global__ void target_moments_kernel(WfsParams p, double* mom, float k2t) {
   const int e = blockIdx.z;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -372,35 +373,48 @@ __global__ void target_moments_kernel(WfsParams p, double* mom) {
       acc += dm;
     }
   }
-  float s0 = m, s1 = m * acc, s2 = m * acc * acc;
+  float s0 = m, s1 = m * acc, s2 = m * acc * acc, s3 = 0.f, s4 = 0.f;
+  if (m != 0.f) {
+    sincosf(k2t * acc, &s4, &s3);
+    s3 *= m; s4 *= m;
+  }
 #pragma unroll
   for (int sft = 16; sft > 0; sft >>= 1) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, sft);
     s1 += __shfl_xor_sync(0xffffffffu, s1, sft);
     s2 += __shfl_xor_sync(0xffffffffu, s2, sft);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, sft);
+    s4 += __shfl_xor_sync(0xffffffffu, s4, sft);
   }
-  __shared__ float red[8][3];
-  if (threadIdx.x == 0) { red[threadIdx.y][0] = s0; red[threadIdx.y][1] = s1; red[threadIdx.y][2] = s2; }
+  __shared__ float red[8][5];
+  if (threadIdx.x == 0) {
+    red[threadIdx.y][0] = s0; red[threadIdx.y][1] = s1; red[threadIdx.y][2] = s2;
+    red[threadIdx.y][3] = s3; red[threadIdx.y][4] = s4;
+  }
   __syncthreads();
-  if (threadIdx.y == 0 && threadIdx.x < 3) {
+  if (threadIdx.y == 0 && threadIdx.x < 5) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    if (t != 0.f) atomicAdd(mom + (size_t)e * 3 + threadIdx.x, (double)t);
+    if (t != 0.f) atomicAdd(mom + (size_t)e * 5 + threadIdx.x, (double)t);
   }
 }
 
-// [E][4] = {short-exposure Strehl exp(-var k^2), long-exposure mean of it, phase variance, running mean variance};
-// acc [E][2] running sums of SE and var, n_le the number of accumulated frames including this one (0: no accumulation)
-__global__ void target_strehl_kernel(const double* mom, float* strehl, float* acc, int E, float k2, int n_le) {
+// [E][4] = {short-exposure Strehl, long-exposure mean of it, phase variance, running mean variance}.  The short-exposure
+// figure is the on-axis intensity ratio |<exp(i k phi)>|^2 over the pupil -- the peak of the PSF of a tilt-free
+// residual, what the reference reads off its FFT image; it equals the Marechal value exp(-var k^2) for small residuals
+// and stays meaningful in open loop where that underflows.  The long-exposure PSF is the mean of the short ones, so
+// its peak is the running mean.  acc [E][2] running sums of SE and var, n_le the number of accumulated frames
+// including this one (0: no accumulation).
+__global__ void target_strehl_kernel(const double* mom, float* strehl, float* acc, int E, int n_le) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  const double s0 = mom[e * 3], s1 = mom[e * 3 + 1], s2 = mom[e * 3 + 2];
-  float var = 0.f;
+  const double s0 = mom[e * 5], s1 = mom[e * 5 + 1], s2 = mom[e * 5 + 2], sc = mom[e * 5 + 3], ss = mom[e * 5 + 4];
+  float var = 0.f, se = 1.f;
   if (s0 > 0.0) {
     const double mean = s1 / s0;
     var = (float)fmax(s2 / s0 - mean * mean, 0.0);
+    se = (float)((sc * sc + ss * ss) / (s0 * s0));
   }
-  const float se = expf(-var * k2 * k2);
   strehl[e * 4 + 0] = se;
   strehl[e * 4 + 2] = var;
   if (n_le > 0) {

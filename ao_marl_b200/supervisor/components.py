@@ -309,10 +309,11 @@ class RtcB200(_Base):
 
 
 class TargetB200(_Base):
-    """targetCompass.py (next-row scope): Strehl from the residual phase variance over the pupil
-    (Marechal, exp(-sigma^2)), which is what get_strehl()[2] reports in the reference too; the 2048^2 PSF
-    of comp_tar_image is not computed.  One fused kernel pair (aom_comp_strehl) evaluates the on-axis phase per
-    pupil pixel and reduces it without materialising it; the short / long exposure figures live in AOM_B_STREHL."""
+    """targetCompass.py (next-row scope) without the focal-plane image: get_strehl() = [SE, LE, phase variance, mean
+    variance] with SE = |<exp(i k phi)>|^2 over the pupil -- the on-axis intensity ratio, i.e. the peak of the PSF the
+    reference's FFT gives for a tilt-free residual (Marechal's exp(-sigma^2) for small ones) -- and LE its mean over the
+    frames; the 2048^2 image of comp_tar_image is not computed.  One sweep kernel (aom_comp_strehl) evaluates the on-axis
+    phase per pupil pixel and reduces it without materialising it; the figures live in AOM_B_STREHL."""
 
     def __init__(self, sim, config, tables):
         super().__init__(sim, config)

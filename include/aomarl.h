@@ -220,10 +220,12 @@ int aom_wfs_time_ms(aom_ctx* ctx, float* mean_ms, int* count);
 /* Materialise the pupil-plane phase seen by the sensor (wfs.get_wfs_phase) into AOM_B_PHASE. */
 int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream);
 
-/* TargetCompass.comp_tar_image / comp_strehl / get_strehl (targetCompass.py:139-196), Marechal form: the phase
- * of aom_raytrace_wfs is reduced over the pupil on the fly and AOM_B_STREHL = {SE, LE, variance, mean variance}
- * with SE = exp(-var (2 pi / lambda)^2).  flags as aom_comp_wfs_image (bit0 atmosphere, bit1 mirrors);
- * accumulate != 0 adds the frame to the long-exposure means.  The 2048^2 focal-plane PSF is not computed. */
+/* TargetCompass.comp_tar_image / comp_strehl / get_strehl (targetCompass.py:139-196) without the focal-plane image: the
+ * phase of aom_raytrace_wfs is reduced over the pupil on the fly and AOM_B_STREHL = {SE, LE, variance, mean variance},
+ * SE = |<exp(2 pi i phi / lambda)>|^2, the on-axis intensity ratio (the PSF peak of a tilt-free residual; equals the
+ * Marechal value exp(-var (2 pi / lambda)^2) for small residuals), LE its mean over the accumulated frames.  flags as
+ * aom_comp_wfs_image (bit0 atmosphere, bit1 mirrors); accumulate != 0 adds the frame to the long-exposure means.
+ * The 2048^2 focal-plane PSF is not computed. */
 #define AOM_TAR_GEO 0x100   /* flags bit: the target behind the geometric controller's mirrors (reads AOM_B_GEO_VOLTS,
                                writes AOM_B_STREHL_GEO) instead of the main ones */
 int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int accumulate, void* stream);
