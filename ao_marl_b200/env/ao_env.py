@@ -63,15 +63,16 @@ class AoEnv:
         self.supervisor.iter = 0
         if normalization_loop:
             return None
-        return self.linear_step(return_dict)
+        return self.linear_step(return_dict, geometric_do_control, geometric_apply_control)
 
     def state(self):
         return self.sim.rows("STATE", self.state_size)
 
     def linear_step(self, return_dict=False, geometric_do_control=False, geometric_apply_control=True):
-        """raytrace + WFS frame + centroids + integrator, then the normalised state."""
+        """raytrace + WFS frame + centroids + integrator, then the normalised state.  geometric_do_control also runs the
+        parameter file's geometric controller (the reference runs it every frame, ao_env.py:885; opt-in here)."""
         self.sim.state_begin()                         # s_dm_before_linear = rtc.get_command(0)
-        self.supervisor.next_part_one(geometric_apply_control=geometric_apply_control)
+        self.supervisor.next_part_one(geometric_apply_control=geometric_apply_control, geo=geometric_do_control)
         self.sim.state_end()
         s = self.state()
         if return_dict:
@@ -80,7 +81,12 @@ class AoEnv:
         return self._out(s)
 
     def calculate_reward(self, target=0, reward_type=None):
-        """Global reward: -factor * mean over the action range of (v2m . d_err)^2 (ao_env.py:845-853)."""
+        """Global reward: -factor * mean over the action range of (v2m . d_err)^2 (ao_env.py:845-853);
+        reward_type "strehl_ratio_se" / "strehl_ratio_le": the Strehl figures of `target` (ao_env.py:587-602)."""
+        if reward_type in ("strehl_ratio_se", "strehl_ratio_le"):
+            self.supervisor.target.raytrace(target, atm=self.supervisor.atmos, dms=self.supervisor.dms)
+            self.supervisor.target.comp_tar_image(target)
+            return self.supervisor.target.get_strehl(target)[0 if reward_type.endswith("_se") else 1]
         rl = self.supervisor.rl
         import torch
         res = self.sim.rows("RES_MODES", rl.nmodes)
@@ -101,7 +107,11 @@ class AoEnv:
         self.supervisor.next_part_two(action=action, linear_control=linear_control,
                                       evaluation_rl_full_action=evaluation_rl_full_action,
                                       apply_control=apply_control, compute_tar_psf=compute_tar_psf)
-        return self.calculate_reward(), False, ""
+        r = self.calculate_reward()
+        if geometric_do_control and self.supervisor.geo_index is not None:
+            # fitting-only Strehl of the target behind the geometric controller's mirrors (ao_env.py:928-937)
+            return r, False, "", self.calculate_reward(target=1, reward_type="strehl_ratio_se")   # target 1, as the reference
+        return r, False, ""
 
     def normalization_step(self, linear_control_through_modal=False):
         return self.supervisor.next_normalization(linear_control_through_modal)

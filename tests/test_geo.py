@@ -186,6 +186,11 @@ def test_geo_supervisor_surface():
         se0, le0, var0, _ = sup.target.get_strehl(0)
         assert 0.0 < var1 < var0            # the fitting-only residual bounds the closed loop from below
         assert se1 > se0
+        # the reference's env surface: linear_step / rl_step with geometric_do_control (ao_env.py:873-937)
+        env.linear_step(geometric_do_control=True)
+        r, done, info, r_geo = env.rl_step(np.zeros(env.action_size, np.float32), geometric_do_control=True)
+        assert isinstance(r, float) and isinstance(r_geo, float) and 0.0 < r_geo <= 1.0
+        assert len(env.rl_step(np.zeros(env.action_size, np.float32))) == 3
     finally:
         sup.sim.close()
 
