@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
   short* s_amap = (short*)(s_vall + NW * 2 * 32);
   uint2* s_sub = (uint2*)((unsigned char*)s_amap + ((f.GW * f.GW * 2 + 15) & ~15));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: marks it (and the work-item index, tile coordinates, TMA operands derived from it)
+  // warp-uniform for the compiler
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
 
   for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) s_c1[i] = f.c1[i];
@@ -199,7 +201,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
   float n_v = 0.f;
   bool n_seam = false;
   auto prefetch = [&](int pe, int pk, int stage, bool tiles, bool aux) {
-    const uint2 sb = sub[pk];
+    uint2 sb = sub[pk];
+    sb.x = __shfl_sync(0xffffffffu, sb.x, 0); sb.y = __shfl_sync(0xffffffffu, sb.y, 0);
     n_xy = sb.x;
     if (NL > 0 && tiles) {
       if (pe != ring_e) {
