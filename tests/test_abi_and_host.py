@@ -134,3 +134,23 @@ def test_env_sharding_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)], env=env,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_rl_layout_40x40_agent_counts():
+    """SURVEY note N1: the benchmarked layout is 43 agents (42 x 30 modes + tip-tilt, window 20 -> 280 / 168 inputs);
+    the literal reading of the config name is 14 x 90 modes + tip-tilt (520 / 168 inputs).  Both are parameters of the
+    same tables."""
+    from ao_marl_b200.rl.layout import RLLayout
+    env = dict(parameters_telescope="production_sh_40x40_8m_3layers.py", n_zernike_start_end=[0, 1260],
+               window_n_zernike=20, include_tip_tilt_windowed=True, n_reverse_filtered_from_cmat=5)
+    rl = RLLayout(1283, env, None, world_size=44)
+    assert rl.n_agents == 43 and rl.action_dim == 1262 and rl.state_modes == 1283
+    assert rl.actor_in == 280 and rl.actor_out == 30
+    widths = (rl.agent_idx >= 0).sum(axis=1)
+    assert sorted(set(widths.tolist())) == [168, 280] or int(widths.max()) == 280
+    assert int((rl.agent_act >= 0).sum()) == rl.action_dim                       # every action slot owned once
+    assert sorted(rl.agent_act[rl.agent_act >= 0].tolist()) == list(range(rl.action_dim))
+    rl14 = RLLayout(1283, env, None, world_size=16)                             # 14 mode agents + tip-tilt + the trainer rank
+    assert rl14.n_agents == 15 and rl14.actor_out == 90
+    assert int((rl14.agent_idx >= 0).sum(axis=1).max()) == 520
+    assert sorted(rl14.agent_act[rl14.agent_act >= 0].tolist()) == list(range(rl14.action_dim))
