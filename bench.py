@@ -388,8 +388,9 @@ def run_ours(args):
                          "peak_source": "measured" if peaks else "fallback",
                          "ms_per_launch": wfs_ms, "share_of_step": wfs_ms / (ms / args.steps),
                          "fp32_tflops_algorithmic": flops_per_frame * E / (wfs_ms * 1e-3) / 1e12,
-                         "note": "latency bound at 4 warps per scheduler (~1180 warp instructions per subaperture at ~0.5 "
-                                 "IPC; HMMA pipe 50 %, DRAM 19 %): neither HBM nor tensor bound, see DESIGN.md section 4"
+                         "note": "bound by its instruction count (~1110 warp instructions per subaperture, 144 of them "
+                                 "mma.sync, at ~0.53 IPC per scheduler; HMMA pipe 50 %, DRAM 19 %): neither HBM nor "
+                                 "tensor bound, see DESIGN.md section 4"
                                  if args.wfs_path != "simt" else
                                  "issue-bound on the FP32 pipe (SIMT pruned FFT), not on HBM: see DESIGN.md"},
             "e2e": {"value": k_e2e * E * world / (ms_e2e * 1e-3), "unit": "env-steps/s",
