@@ -1411,7 +1411,12 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   // side by side on two streams and join before the sensor frame.
   const bool atmos_done = (mode & AOM_STEP_ATMOS_DONE) != 0;
   mode &= ~AOM_STEP_ATMOS_DONE;
-  const bool fork = ctx->cfg.n_layers > 0 && ctx->seeded && !atmos_done;
+  // with the per-frame Strehl the target sweep reads the screens of the previous frame after apply_control, so the
+  // turbulence update cannot run ahead of it: no fork, no caller-side update
+  const bool strehl = ctx->opt[AOM_OPT_STREHL] != 0;
+  if (strehl && atmos_done)
+    return fail(ctx, AOM_ERR_STATE, "AOM_OPT_STREHL needs the screens of the previous frame: do not combine with AOM_STEP_ATMOS_DONE");
+  const bool fork = ctx->cfg.n_layers > 0 && ctx->seeded && !atmos_done && !strehl;
   if (fork) {
     CU(cudaEventRecord(ctx->ev_fork, st));
     CU(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
@@ -1422,7 +1427,13 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   if (mode == 0) { rc = aom_actor_forward(ctx, eval_mode, stream); if (rc) return rc; }
   if (mode != 2) { rc = aom_rl_control(ctx, nullptr, stream); if (rc) return rc; }
   rc = aom_apply_control(ctx, 1, stream); if (rc) return rc;
-  if (ctx->reward) { rc = aom_reward(ctx, 1000.f, stream); if (rc) return rc; }
+  if (strehl) {
+    // next_part_two: target.comp_tar_image + comp_strehl right after apply_control (rlSupervisor.py:936-947): the
+    // mirrors carry the new voltages, the atmosphere is still the one of the previous frame
+    const int nm = ctx->opt[AOM_OPT_STREHL_LAMBDA_NM] > 0 ? ctx->opt[AOM_OPT_STREHL_LAMBDA_NM] : 1650;
+    rc = aom_comp_strehl(ctx, 3, (float)nm * 1e-3f, 1, stream); if (rc) return rc;
+  }
+  if (ctx->reward) { rc = aom_reward(ctx, ctx->cfg.reward_factor, stream); if (rc) return rc; }
   // linear half-step: AoEnv.linear_step -> RlSupervisor.next_part_one (rlSupervisor.py:1015-1051)
   rc = aom_state_begin(ctx, stream); if (rc) return rc;
   if (fork) CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
@@ -1437,7 +1448,8 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
     if (fork) CU(cudaEventRecord(ctx->ev_geo, gs));
   }
   const bool denoise = ctx->opt[AOM_OPT_DENOISE] != 0;
-  rc = aom_comp_wfs_image(ctx, denoise ? 7 : 3, ctx->cfg.noise, stream); if (rc) return rc;
+  const bool keep = denoise || ctx->opt[AOM_OPT_KEEP_IMAGE] != 0;
+  rc = aom_comp_wfs_image(ctx, keep ? 7 : 3, ctx->cfg.noise, stream); if (rc) return rc;
   if (denoise) { rc = aom_denoise(ctx, nullptr, nullptr, 0, stream); if (rc) return rc; }
   rc = aom_do_centroids(ctx, stream); if (rc) return rc;
   rc = aom_do_control(ctx, stream); if (rc) return rc;

@@ -153,17 +153,26 @@ AOM_HD float aom_normal_of_block(const aom_u4& w, int j) {
   return (j & 1) ? z1 : z0;
 }
 
+// uniform for the CDF inversion: ((x >> 9) + 0.5) * 2^-23, exact in float32 and strictly inside (0, 1)
+// (aom_u01's (x >> 8) + 0.5 rounds to 2^24 for the largest words, i.e. u == 1.0, which no float32 CDF reaches)
+AOM_HD float aom_u01_open(uint32_t x) {
+  return aom_mul(aom_add((float)(x >> 9), 0.5f), 1.1920928955078125e-07f);  // 2^-23
+}
+
 AOM_HD int32_t aom_poisson(float lam, uint32_t x0, uint32_t x1) {
   if (!(lam > 0.0f)) return 0;
   if (lam < AOM_POISSON_SWITCH) {
-    float u = aom_u01(x0);
+    float u = aom_u01_open(x0);
     float p = aom_det_exp(-lam);
     float F = p;
     int k = 0;
     while (u > F && k < AOM_POISSON_MAXK) {
       k += 1;
       p = aom_div(aom_mul(p, lam), (float)k);
-      F = aom_add(F, p);
+      const float Fn = aom_add(F, p);
+      // the float32 CDF has stopped growing beyond the mode: this k is the tail sample (never the loop cap)
+      if (Fn == F && (float)k > lam) break;
+      F = Fn;
     }
     return k;
   }

@@ -34,7 +34,8 @@ class AomConfig(ctypes.Structure):
            ("state_modes", ctypes.c_int32), ("state_dim", ctypes.c_int32)]
         + [(k, ctypes.c_float) for k in ("env_act_scale", "env_act_bias", "pol_act_scale", "pol_act_bias",
                                          "log_sig_min", "log_sig_max")]
-        + [(k, ctypes.c_int32) for k in ("n_agents", "actor_in", "actor_hidden", "actor_out", "action_dim")])
+        + [(k, ctypes.c_int32) for k in ("n_agents", "actor_in", "actor_hidden", "actor_out", "action_dim")]
+        + [("reward_factor", ctypes.c_float)])
 
 
 TABLES = ["AB", "STENCIL", "MPUPIL", "HALFXY", "SUB_X0", "SUB_Y0", "FLUX", "STAMP1D", "ACT_MAP", "TT_PLANES",
@@ -46,7 +47,7 @@ BUFFERS = ["SCREEN", "RING_OX", "RING_OY", "SLOPES", "ERR", "COM", "VOLTS", "BIN
            "RES_MODES", "STATE", "REWARD", "ACTION", "ACTION_MEAN", "STREHL", "GEO_COM", "GEO_VOLTS", "STREHL_GEO", "GEO_PROJ"]
 B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
-OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH"]
+OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH", "KEEP_IMAGE", "STREHL", "STREHL_LAMBDA_NM"]
 O = {name: i for i, name in enumerate(OPTIONS)}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
@@ -210,6 +211,7 @@ class Simulator:
         cfg.nactu, cfg.nslopes = t.nactu, t.nslopes
         cfg.nmodes = int(t.Btt.shape[1]) if getattr(t, "Btt", None) is not None else 0
         cfg.gain, cfg.delay = t.gain, int(round(t.delay))
+        cfg.reward_factor = 1000.0
         if float(t.delay) not in (0.0, 1.0):
             raise NotImplementedError("controller delay must be 0 or 1 frame")
         if rl is not None:
@@ -404,6 +406,16 @@ class Simulator:
     def step_with_denoiser(self, on=True):
         """aom_step runs the fused denoiser between the sensor frame and the centroider (AOM_OPT_DENOISE)."""
         self._check(self.lib.aom_set_option(self._ctx, O["DENOISE"], 1 if on else 0), "aom_set_option")
+
+    def step_keeps_image(self, on=True):
+        """aom_step keeps every frame's detector cube in AOM_B_BINCUBE (AOM_OPT_KEEP_IMAGE)."""
+        self._check(self.lib.aom_set_option(self._ctx, O["KEEP_IMAGE"], 1 if on else 0), "aom_set_option")
+
+    def step_with_strehl(self, on=True, lambda_um=1.65):
+        """aom_step evaluates the target Strehl every frame, as the reference's next_part_two does by default
+        (compute_tar_psf=True, rlSupervisor.py:944-947)."""
+        self._check(self.lib.aom_set_option(self._ctx, O["STREHL_LAMBDA_NM"], int(round(lambda_um * 1000))), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, O["STREHL"], 1 if on else 0), "aom_set_option")
 
     def step_with_geo(self, on=True):
         """aom_step also runs the geometric controller every frame (AOM_OPT_GEO)."""

@@ -145,6 +145,7 @@ class RLLayout:
         cfg.n_agents, cfg.actor_in, cfg.actor_hidden, cfg.actor_out = (self.n_agents, self.actor_in, self.hidden,
                                                                       self.actor_out)
         cfg.action_dim = self.action_dim
+        cfg.reward_factor = float(self.reward_factor)
 
     def upload(self, sim):
         sim.set_table("FREEDOM", self.freedom)

@@ -40,7 +40,7 @@ class AtmosB200(_Base):
         self._sim.move_atmos()
 
     def reset_turbu(self, seed):
-        """Reseed and regenerate every layer.  `seed` may be a scalar (environment e gets seed + e * 1000003,
+        """Reseed and regenerate every layer.  `seed` may be a scalar (environment e gets seed + e, Simulator.env_seeds,
         so that E == 1 reproduces the reference's single stream) or an int64 array [E]."""
         self._sim.reset(self._sim.env_seeds(seed))
 

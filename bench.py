@@ -19,6 +19,13 @@ import tempfile
 import threading
 import time
 
+# CPU-baseline worker processes (spawned by cpu_baseline with AOM_BENCH_CPU_WORKER=1) re-import this file first: the
+# BLAS / OpenMP pools must be limited BEFORE numpy / torch are imported, otherwise every "one core" worker runs a
+# multi-threaded BLAS and N workers oversubscribe the box N times (round-1 finding).
+if os.environ.get("AOM_BENCH_CPU_WORKER") == "1":
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "VECLIB_MAXIMUM_THREADS"):
+        os.environ[_v] = "1"
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -145,13 +152,33 @@ def cpu_env_factory(workload_key, cmat_cache=None):
     return lambda seed: loop.OracleEnv(tab, cmat, t.Btt, t.P, rl, seed=seed), t, rl
 
 
+def _host_cores():
+    try:
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return list(range(os.cpu_count() or 1))
+
+
 def _cpu_worker(args):
-    blob_path, seed, seconds, min_steps = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    """One oracle environment on ONE pinned host core with single-threaded BLAS / torch."""
+    blob_path, seed, seconds, min_steps, core = args
     import pickle
+    if core is not None:
+        try:
+            os.sched_setaffinity(0, {core})
+        except Exception:
+            pass
+    threads = {"omp_env": os.environ.get("OMP_NUM_THREADS")}
     try:
         import torch
         torch.set_num_threads(1)
+        threads["torch"] = torch.get_num_threads()
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(1)
+        threads["blas"] = max([int(x.get("num_threads", 1)) for x in threadpool_info()] or [1])
     except Exception:
         pass
     from oracle import loop
@@ -172,36 +199,50 @@ def _cpu_worker(args):
         el = time.perf_counter() - t0
         if (el >= seconds and n >= min_steps) or n >= 100000:
             break
-    return n, el
+    return n, el, threads
+
+
+_BLOBS = {}
 
 
 def cpu_baseline(workload_key, seconds, procs=1):
-    """env-steps/s of the oracle on `procs` host processes (one environment each), bounded sample.  The static
-    tables are built once in this process and handed to the workers through a pickle."""
+    """env-steps/s of the oracle on `procs` host processes (one environment, one pinned core, one BLAS thread each),
+    bounded sample.  The static tables are built once in this process and handed to the workers through a pickle;
+    the workers are always spawned so that their thread pools are limited before numpy / torch load."""
     import multiprocessing as mp
     import pickle
     t0 = time.perf_counter()
-    make, t, rl = cpu_env_factory(workload_key)
-    cells = dict(zip(make.__code__.co_freevars, (c.cell_contents for c in make.__closure__)))
-    blob = dict(tab=cells["tab"], cmat=cells["cmat"], Btt=cells["t"].Btt, P=cells["t"].P, rl=cells["rl"])
+    if workload_key not in _BLOBS:
+        make, t, rl = cpu_env_factory(workload_key)
+        cells = dict(zip(make.__code__.co_freevars, (c.cell_contents for c in make.__closure__)))
+        _BLOBS[workload_key] = dict(tab=cells["tab"], cmat=cells["cmat"], Btt=cells["t"].Btt, P=cells["t"].P, rl=cells["rl"])
+    blob = _BLOBS[workload_key]
     with tempfile.NamedTemporaryFile("wb", suffix=".pkl", delete=False) as f:
         pickle.dump(blob, f, protocol=pickle.HIGHEST_PROTOCOL)
         path = f.name
+    cores = _host_cores()
+    procs = max(1, min(int(procs), len(cores)))
+    saved = {k: os.environ.get(k) for k in ("AOM_BENCH_CPU_WORKER",)}
+    os.environ["AOM_BENCH_CPU_WORKER"] = "1"
     try:
-        if procs == 1:
-            res = [_cpu_worker((path, 1234, seconds, 2))]
-        else:
-            ctx = mp.get_context("spawn")
-            with ctx.Pool(procs) as pool:
-                res = pool.map(_cpu_worker, [(path, 1234 + i, seconds, 2) for i in range(procs)])
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_cpu_worker, [(path, 1234 + i, seconds, 2, cores[i % len(cores)]) for i in range(procs)])
     finally:
         os.unlink(path)
-    rate = sum(n / el for n, el in res)
-    steps = sum(n for n, _ in res)
-    return dict(value=rate, unit="env-steps/s", cores=procs, kind="port",
-                sample="%d env-steps of 1 environment per process on %d process(es), %.1f s of stepping "
-                       "(oracle/loop.py: numpy frame + CPU torch actors), start-up %.0f s excluded"
-                       % (steps, procs, max(el for _, el in res), time.perf_counter() - t0 - max(el for _, el in res)))
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    rate = sum(n / el for n, el, _ in res)
+    steps = sum(n for n, _, _ in res)
+    el_max = max(el for _, el, _ in res)
+    return dict(value=rate, unit="env-steps/s", cores=procs, per_core=rate / procs, host_cores=len(cores),
+                os_cpu_count=os.cpu_count(), threads_per_process=res[0][2], kind="port",
+                sample="%d env-steps of 1 environment per process on %d pinned single-thread process(es), %.1f s of "
+                       "stepping (oracle/loop.py: numpy frame + CPU torch actors), start-up %.0f s excluded"
+                       % (steps, procs, el_max, time.perf_counter() - t0 - el_max))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -210,10 +251,12 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    procs = os.cpu_count() or 1
+    procs = len(_host_cores())
     per_step = max(2.0, args.cpu_seconds / max(1, args.steps + args.warmup))
     t0 = time.perf_counter()
     base = cpu_baseline(args.workload, per_step * (args.steps + args.warmup), procs)
+    one = cpu_baseline(args.workload, min(10.0, args.cpu_seconds), 1)      # all cores and 1 core
+    base["one_core"] = {"value": one["value"], "unit": one["unit"], "sample": one["sample"]}
     line = {
         "impl": "reference", "metric": "AO env-steps/s (batched closed-loop step + actor forward)",
         "value": base["value"], "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

@@ -80,6 +80,8 @@ typedef struct aom_config {
   int32_t n_agents;
   int32_t actor_in, actor_hidden, actor_out; /* padded common sizes of the batched actors */
   int32_t action_dim;                   /* length of the global action vector */
+  float reward_factor;                  /* <factor> of reward_type "avg_squared_modes_<factor>" (helper_rewards.py:14-22,
+                                           GlobalConfig.py:86); aom_step scales the per-agent rewards with it */
 } aom_config;
 
 /* Tables uploaded once after aom_create (host pointers; copied to the device). */
@@ -156,6 +158,11 @@ typedef enum aom_option {
                            centroider, as next_part_one_integrator does when an autoencoder is configured
                            (rlSupervisor.py:968-979); needs AOM_T_DENOISER */
   AOM_OPT_PUPIL_PATH,   /* which kernels sweep the pupil-plane phase for aom_comp_strehl / aom_do_control_geo */
+  AOM_OPT_KEEP_IMAGE,   /* != 0: aom_step keeps the detector cube of every frame in AOM_B_BINCUBE (d_bincube readers:
+                           rlSupervisor.py:884-885, obtain_dataset_autoencoder.py:85-88) */
+  AOM_OPT_STREHL,       /* != 0: aom_step evaluates the target Strehl every frame at AOM_OPT_STREHL_LAMBDA_NM, as
+                           next_part_two does with compute_tar_psf=True (rlSupervisor.py:944-947) */
+  AOM_OPT_STREHL_LAMBDA_NM, /* target wavelength in nanometres for AOM_OPT_STREHL (default 1650) */
   AOM_OPT_COUNT
 } aom_option;
 enum {

@@ -98,11 +98,18 @@ class OracleEnv:
         noise = self.tab["wfs"]["noise"] if noise is None else noise
         out = wfs_frame(self.tab, self.wfs_phase(atmos, dms), noise, self.seed, self.frame, keep=keep)
         self.frame += 1
+        self.frame_noise = noise
         if keep:
             self._slopes_frame, self.cube = out
         else:
             self._slopes_frame = out
         return out
+
+    def set_bincube(self, cube):
+        """Continue from a given detector cube [nvalid, npix, npix] (the tests hand the GPU's photon counts over so
+        that a Poisson draw that sat on a rounding boundary does not fork the two closed loops)."""
+        self.cube = np.asarray(cube, F32).reshape(self.tab["wfs"]["nvalid"], self.tab["wfs"]["npix"], -1)
+        self._slopes_frame = af.cog(self.cube, self.tab["wfs"])
 
     def do_centroids(self):
         self.slopes = self._slopes_frame.copy()
@@ -125,12 +132,16 @@ class OracleEnv:
         self.com = (self.Btt.astype(np.float64) @ m.astype(np.float64)).astype(F32)
 
     # -- env-level ---------------------------------------------------------------------------------
-    def linear_step(self):
-        """AoEnv.linear_step: returns the normalised state vector."""
+    def linear_step(self, cube_hook=None):
+        """AoEnv.linear_step: returns the normalised state vector.  cube_hook(own_cube) -> cube to continue from."""
         rl = self.rl
         com_before = self.com.copy()
         self.atm.move()
-        self.comp_wfs_image()
+        if cube_hook is None:
+            self.comp_wfs_image()
+        else:
+            self.comp_wfs_image(keep=True)
+            self.set_bincube(cube_hook(self.cube))
         self.do_centroids()
         self.do_control()
         if rl is None:
@@ -170,11 +181,11 @@ class OracleEnv:
         self.step_count += 1
         return action, mean_v
 
-    def env_step(self, action=None):
+    def env_step(self, action=None, cube_hook=None):
         """TrainerRPC.env_step: rl half-step + reward + linear half-step.  action=None: integrator only."""
         if action is not None:
             self.rl_control(action)
         self.apply_control()
         r = self.rewards() if (self.rl is not None and self.rl.n_agents) else None
-        s = self.linear_step()
+        s = self.linear_step(cube_hook)
         return s, r

@@ -263,6 +263,37 @@ def collect_rl(out):
     out["rl.policy.log_std"] = log_std.numpy()
 
 
+def collect_extrude(out):
+    """One extruded column per direction from the reference's own iterkolmo.extrude (shesha/util/iterkolmo.py:255-288)
+    with np.random.normal patched to return a fixed vector, on a 32 x 32 screen with the operators of the
+    reference's own AB (190-252) for every sign combination of the wind (stencil mirroring 246-249, isty 241-244)."""
+    from shesha.util import iterkolmo as itK
+    n, L0, r0 = 32, 1.0e5, 7.3
+    r = np.random.default_rng(42)
+    p = r.standard_normal((n, n)).astype(np.float32).cumsum(axis=0).cumsum(axis=1) / np.float32(40.0)
+    eps = r.standard_normal(n)
+    out["ext.n"], out["ext.L0"], out["ext.r0"] = np.int64(n), np.float64(L0), np.float64(r0)
+    out["ext.p"], out["ext.eps"] = p.astype(np.float32), eps.astype(np.float64)
+    real_normal = np.random.normal
+    for tag, (dx, dy) in {"pp": (1.0, 1.0), "np": (-1.0, 1.0), "pn": (1.0, -1.0), "nn": (-1.0, -1.0)}.items():
+        A, B, istx, isty = itK.AB(n, L0, dx, dy)
+        if tag == "pp":
+            out["ext.A"], out["ext.B"] = np.ascontiguousarray(A), np.ascontiguousarray(B)
+        out["ext.istx_" + tag], out["ext.isty_" + tag] = istx, isty
+    np.random.normal = lambda loc, scale, size: eps.copy()
+    try:
+        A, B = np.asfortranarray(out["ext.A"]), np.asfortranarray(out["ext.B"])
+        # +x: the reference function as it stands
+        out["ext.p1_px"] = itK.extrude(p.copy(), r0, A, B, out["ext.istx_pp"])
+        # the reference's python extrude always appends on the right; the other three directions are the same call
+        # on the transposed / 180-degree rotated screen with the +x stencil (what the mirrored index lists encode)
+        out["ext.p1_py"] = itK.extrude(np.ascontiguousarray(p.T), r0, A, B, out["ext.istx_pp"]).T.copy()
+        out["ext.p1_nx"] = itK.extrude(np.ascontiguousarray(p[::-1, ::-1]), r0, A, B, out["ext.istx_pp"])[::-1, ::-1].copy()
+        out["ext.p1_ny"] = itK.extrude(np.ascontiguousarray(p.T[::-1, ::-1]), r0, A, B, out["ext.istx_pp"])[::-1, ::-1].T.copy()
+    finally:
+        np.random.normal = real_normal
+
+
 def main(which=None):
     root = prepare_ref.activate(fake_sutra=True)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -275,6 +306,11 @@ def main(which=None):
             out, _ = collect(name, root, par, full=(name == "10x10"))
             np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_tables_%s.npz" % name), **out)
             print("wrote", name, len(out), "entries")
+        if not which or "extrude" in which:
+            out = {}
+            collect_extrude(out)
+            np.savez_compressed(os.path.join(GOLDEN_DIR, "ref_extrude.npz"), **out)
+            print("wrote extrude", len(out), "entries")
         if not which or "rl" in which:
             out = {}
             collect_rl(out)

@@ -66,6 +66,12 @@ def u01(x):
     return ((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0**-24)
 
 
+def u01_open(x):
+    """uint32 -> float32 strictly inside (0,1): ((x >> 9) + 0.5) * 2^-23 (exact in float32).  Used by the Poisson
+    CDF inversion: u01's (x >> 8) + 0.5 rounds to 2^24 for the largest words (u == 1.0), which no float32 CDF reaches."""
+    return ((x >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0**-23)
+
+
 F32 = np.float32
 _LN2 = F32(0.6931471805599453)
 _SQRT2 = F32(1.41421354)
@@ -177,16 +183,16 @@ def actor_noise(seed, agent, step, n):
 def poisson_from_words(lam, x0, x1):
     """Integer Poisson sample for each float32 rate `lam`, driven by Philox words x0, x1.
 
-    lam < 30 : CDF inversion with u = u01(x0), p0 = det_exp(-lam), p_k = (p_{k-1} * lam) / k
+    lam < 30 : CDF inversion with u = u01_open(x0), p0 = det_exp(-lam), p_k = (p_{k-1} * lam) / k; the search ends
+               where the float32 CDF stops growing (k > lam), so the largest words give a tail sample, not the cap
     lam >= 30: floor(lam + sqrt(lam) * z + 0.5), z = first Box-Muller normal of (x0, x1), clamped at 0
     """
     lam = np.asarray(lam, dtype=np.float32)
     out = np.zeros(lam.shape, dtype=np.int32)
     small = (lam < POISSON_SWITCH) & (lam > 0)
-    u = u01(x0)
     if small.any():
         ls = lam[small]
-        us = u[small]
+        us = u01_open(np.asarray(x0, dtype=np.uint32)[small])
         p = det_exp(-ls)
         F = p.copy()
         k = np.zeros(ls.shape, dtype=np.int32)
@@ -197,10 +203,12 @@ def poisson_from_words(lam, x0, x1):
             kf = F32(it)
             pn = ((p * ls) / kf).astype(np.float32)
             Fn = (F + pn).astype(np.float32)
-            p = np.where(active, pn, p)
-            F = np.where(active, Fn, F)
             k = np.where(active, it, k)
-            active = active & (us > F)
+            # the float32 CDF stopped growing beyond the mode: this k is the tail sample (never the loop cap)
+            stalled = active & (Fn == F) & (kf > ls)
+            p = np.where(active, pn, p)
+            F = np.where(active & ~stalled, Fn, F)
+            active = active & ~stalled & (us > F)
         out[small] = k
     big = lam >= POISSON_SWITCH
     if big.any():

@@ -39,6 +39,11 @@ void h_pixel_noise(int n, const float* lam, float noise, int64_t seed, uint32_t 
   for (int i = 0; i < n; ++i) out[i] = aom_pixel_noise(lam[i], noise, (uint32_t)i, frame, wfs, k0, k1);
 }
 
+// raw Poisson sampler on explicit Philox words (tail known-answer tests)
+void h_poisson(int n, const float* lam, const uint32_t* x0, const uint32_t* x1, int32_t* out) {
+  for (int i = 0; i < n; ++i) out[i] = aom_poisson(lam[i], x0[i], x1[i]);
+}
+
 // Pruned 2-D spot: in [16][16] complex -> intensity on the centred (2H x 2H) grid, H = 4R,
 // computed exactly as the kernel does (rows then columns, one aom_fft16_pruned per (vector, b)).
 void h_spot(int R, const float* inr, const float* ini, float* inten) {

@@ -135,3 +135,41 @@ def test_reference_format_parameter_file(tmp_path):
     assert cfg.p_tel.diam == 2.0 and cfg.p_atmos.nscreens == 1 and cfg.p_wfss[0].nxsub == 10
     assert cfg.p_atmos.windspeed.dtype == np.float32 and cfg.p_dms is None
     assert list(cfg.p_wfss[0].get_dms_seen()) == [0, 1]
+
+
+def test_extrude_against_reference():
+    """Row a-1 pinned: the oracle's extrusion (oracle/aoframe.py) against ONE column per direction extruded by the
+    reference's own iterkolmo.extrude (shesha/util/iterkolmo.py:255-288) with a fixed noise vector
+    (tests/golden/ref_extrude.npz, generated by oracle/refharness/gen_golden.py::collect_extrude), and the
+    mirrored / transposed stencil conventions against the reference's AB (iterkolmo.py:241-249)."""
+    import os
+    from oracle import aoframe
+    from ao_marl_b200.init import atmos as atm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_extrude.npz"))
+    n = int(g["ext.n"])
+    p, eps, A, B = g["ext.p"], g["ext.eps"].astype(np.float32), g["ext.A"], g["ext.B"]
+    istx = g["ext.istx_pp"].astype(np.int64)
+    amp = np.float32(float(g["ext.r0"]) ** (-5.0 / 6.0))       # the reference's python works in rad @ 0.5 um, no micron factor
+    # the product's builders reproduce the reference's operators and stencil (bit-exact integers)
+    assert np.array_equal(atm.stencil_indices(n), istx)
+    A2, B2, _ = atm.extrusion_operands(n, float(g["ext.L0"]))
+    assert np.abs(A2 - A).max() < 2e-5 * np.abs(A).max()
+    assert np.abs(B2 @ B2.T - B.astype(np.float64) @ B.astype(np.float64).T).max() < 1e-4 * np.abs(B).max() ** 2   # SVD sign freedom
+    assert np.array_equal(atm.transposed_stencil(istx, n), g["ext.isty_pp"].astype(np.int64))
+    # the reference's mirrored lists: negative wind = the +x stencil read on the 180-degree rotated screen,
+    # y = the +x stencil read on the transposed screen (what oracle.aoframe.extrude does)
+    flat = p.reshape(-1)
+    assert np.array_equal(flat[g["ext.istx_np"].astype(np.int64)], p[::-1, ::-1].reshape(-1)[istx])
+    assert np.array_equal(flat[g["ext.isty_pp"].astype(np.int64)], p.T.reshape(-1)[istx])
+    assert np.array_equal(flat[g["ext.isty_pn"].astype(np.int64)], p.T[::-1, ::-1].reshape(-1)[istx])
+    assert np.array_equal(g["ext.istx_nn"], g["ext.istx_np"]) and np.array_equal(g["ext.isty_nn"], g["ext.isty_pn"])
+    for key, axis, sign in (("px", 0, 1), ("py", 1, 1), ("nx", 0, -1), ("ny", 1, -1)):
+        ref = g["ext.p1_" + key]
+        mine = aoframe.extrude(p.copy(), A, B, istx, amp, eps, axis, sign)
+        assert mine.shape == ref.shape
+        assert np.abs(mine - ref).max() < 2e-6 * np.abs(ref).max(), key      # float32 dot in the reference, float64 in the oracle
+        # the untouched part of the screen is shifted bit-exactly
+        if key == "px":
+            assert np.array_equal(mine[:, :-1], p[:, 1:])
+        if key == "ny":
+            assert np.array_equal(mine[1:, :], p[:-1, :])

@@ -287,6 +287,7 @@ def test_closed_loop_against_oracle(system10, oracle_tab10, torch):
     st = sim.rows("STATE", rl.state_dim).cpu().numpy()
     for e in range(2):
         assert relerr(st[e], states[e]) < RTOL
+    worst = {}
     for it in range(12):
         sim.step(mode=0)
         act = sim.rows("ACTION", rl.action_dim).cpu().numpy()
@@ -296,12 +297,14 @@ def test_closed_loop_against_oracle(system10, oracle_tab10, torch):
         sl = sim.rows("SLOPES", t.nslopes).cpu().numpy()
         for e, o in enumerate(envs):
             a, _ = o.actors(states[e])
-            assert relerr(act[e], a) < 5e-4, "actions, step %d" % it
+            worst["actions"] = max(worst.get("actions", 0), relerr(act[e], a))
             states[e], r = o.env_step(act[e])     # feed the GPU's action so that errors do not compound through tanh
-            assert relerr(sl[e], o.slopes) < 5 * RTOL, "slopes, step %d" % it
-            assert relerr(com[e], o.com) < 5 * RTOL, "commands, step %d" % it
-            assert relerr(rew[e], r) < 1e-3, "rewards, step %d" % it
-            assert relerr(st[e], states[e]) < 1e-3, "state, step %d" % it
+            for k, (x, y) in dict(slopes=(sl[e], o.slopes), commands=(com[e], o.com), rewards=(rew[e], r),
+                                  state=(st[e], states[e])).items():
+                worst[k] = max(worst.get(k, 0), relerr(x, y))
+    print("10x10 closed loop, worst rel errors over 12 steps:", worst)
+    for k, v in worst.items():
+        assert v < RTOL, (k, worst)
 
 
 def test_delay_impulse(system10, torch):

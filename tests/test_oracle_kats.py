@@ -80,6 +80,29 @@ def test_device_headers_bit_equal_to_oracle(harness):
         assert np.array_equal(o, rng.wfs_pixel_noise(99, 0, 5, lam, noise))
 
 
+def test_poisson_tail_known_answers(harness):
+    """The largest Philox words must give a plausible tail sample, never the loop cap (round-1 advisor finding:
+    u01 rounded to exactly 1.0 and the search ran to POISSON_MAXK = 200).  Oracle and device header agree."""
+    lams = np.array([0.1, 0.5, 1, 2, 3, 5, 8, 10, 15, 20, 25, 29.9], np.float32)
+    words = np.array([0xFFFFFFFF, 0xFFFFFF00, 0xFFFFFE00, 0xFFFFFDFF, 0xFFFFF000, 0x80000000, 0, 0x1FF], np.uint32)
+    lam = np.repeat(lams, words.size)
+    x0 = np.tile(words, lams.size)
+    x1 = np.zeros_like(x0)
+    k = rng.poisson_from_words(lam, x0, x1)
+    out = np.zeros(lam.size, np.int32)
+    harness.h_poisson(lam.size, P(lam), P(x0), P(x1), P(out))
+    assert np.array_equal(out, k)
+    assert float(rng.u01_open(np.uint32(0xFFFFFFFF))) < 1.0 and float(rng.u01_open(np.uint32(0))) > 0.0
+    top = k.reshape(lams.size, words.size)[:, 0]
+    # tail sample: beyond the mean, but within a 2^-24 quantile (lam + 12 sqrt(lam) + 12 bounds it generously)
+    assert (top < rng.POISSON_MAXK).all()
+    assert (top > lams).all() and (top <= lams + 12 * np.sqrt(lams) + 12).all(), top
+    # monotone in u
+    order = np.argsort(words.astype(np.uint64) >> np.uint64(9), kind="stable")
+    kk = k.reshape(lams.size, words.size)[:, order]
+    assert (np.diff(kk, axis=1) >= 0).all()
+
+
 @pytest.mark.parametrize("R", [4, 8])
 def test_pruned_dft_matches_fft2(harness, R):
     """fft16.cuh (host build): the kernel's pruned 2-D DFT equals the central Nfft/2 block of numpy's fft2."""
