@@ -14,8 +14,7 @@
 #include "wfs_kernels.cuh"
 #include "wfs_mma.cuh"
 #include "wfs_tma.cuh"
-#include "wfs_pipe.cuh"
-#include "wfs_tc.cuh"
+#include "wfs_umma_host.h"
 #include "geo_kernels.cuh"
 #include "pupil_sweep.cuh"
 #include "denoise_kernels.cuh"
@@ -76,9 +75,14 @@ struct aom_ctx {
   int fast_state;            // 0 = not prepared, 1 = eligible, -1 = not eligible (fast_why says why)
   char fast_why[160];
   WfsFast fast;
-  void* fast_dev[7];
+  void* fast_dev[6];
   CUtensorMap fast_maps[WFT_MAX_LAYERS];
   size_t fast_smem;
+  int fast_geom[6];          // joffx, joffy, c0x, c0y, GW, dm (lattice alignment of the subapertures, wfs_fast_prepare)
+  // tcgen05 Shack-Hartmann kernel (wfs_umma.cuh): derived tables
+  int umma_state;            // 0 = not prepared, 1 = eligible, -1 = not eligible
+  WfsUmmaHost umma;
+  void* umma_dev[6];
   // aom_step runs the turbulence update next to the actor / controller GEMMs on a second stream
   cudaStream_t side_stream;
   cudaEvent_t ev_fork, ev_join;
@@ -150,11 +154,11 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     const char* g = getenv("AOM_GEMM_PATH");
     if (g && !strcmp(g, "simt")) ctx->opt[AOM_OPT_GEMM_PATH] = AOM_GEMM_SIMT;
     const char* w = getenv("AOM_WFS_PATH");
+    if (w && !strcmp(w, "umma_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_UMMA_FAST;
     if (w && !strcmp(w, "simt")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_SIMT;
-    if (w && !strcmp(w, "tensor_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_FAST;
-    if (w && !strcmp(w, "tensor_reg")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_REG;
-    if (w && !strcmp(w, "tensor_pipe")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TENSOR_PIPE;
-    if (w && !strcmp(w, "tcgen05")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_TCGEN05;
+    if (w && !strcmp(w, "tensor_reg")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_MMA_REG;
+    if (w && !strcmp(w, "tensor")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_MMA_STAGED;
+    if (w && !strcmp(w, "tensor_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_MMA_STAGED_FAST;
   }
   *out = ctx;   // returned even on failure so that aom_last_error / aom_destroy work
   CU(cudaGetDevice(&ctx->device));
@@ -244,6 +248,7 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
                   ctx->sweep_mask, ctx->sweep_ttp};
   for (void* b : bufs) cudaFree(b);
   for (void* b : ctx->fast_dev) cudaFree(b);
+  for (void* b : ctx->umma_dev) cudaFree(b);
   for (int i = 0; i < AOM_WFS_TIMERS; ++i)
     for (int j = 0; j < 2; ++j)
       if (ctx->wev[j][i]) cudaEventDestroy(ctx->wev[j][i]);
@@ -301,13 +306,14 @@ extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* hos
   CU(cudaMemcpy(ctx->tab[table][index], host, nbytes, cudaMemcpyHostToDevice));
   ctx->tab_bytes[table][index] = nbytes;
   if (table == AOM_T_MPUPIL || table == AOM_T_SUB_X0 || table == AOM_T_SUB_Y0 || table == AOM_T_STAMP1D ||
-      table == AOM_T_ACT_MAP) {
+      table == AOM_T_ACT_MAP || table == AOM_T_HALFXY || table == AOM_T_TT_PLANES) {
     free(ctx->htab[table]);
     ctx->htab[table] = malloc(nbytes ? nbytes : 4);
     if (!ctx->htab[table]) return fail(ctx, AOM_ERR_INVALID, "out of host memory");
     memcpy(ctx->htab[table], host, nbytes);
     ctx->htab_bytes[table] = nbytes;
-    ctx->fast_state = 0;     // derived tables of the TMA-staged sensor kernel are rebuilt on the next frame
+    ctx->fast_state = 0;     // derived tables of the staged sensor kernels are rebuilt on the next frame
+    ctx->umma_state = 0;
   }
   if (table == AOM_T_MPUPIL || table == AOM_T_TT_PLANES) ctx->sweep_state = 0;
   return AOM_OK;
@@ -705,8 +711,7 @@ static int wfs_fast_prepare(aom_ctx* ctx) {
   float h_fxy[2 * WFT_NG * 16];
   uint4* h_c1 = (uint4*)malloc(8 * 32 * sizeof(uint4));
   uint4* h_c2 = (uint4*)malloc(12 * 32 * sizeof(uint4));
-  unsigned short* h_b2 = (unsigned short*)calloc(2 * WTC_B_BYTES / 2, sizeof(unsigned short));
-  bool ok = h_sub && h_pm && h_amap && h_c1 && h_c2 && h_b2;
+  bool ok = h_sub && h_pm && h_amap && h_c1 && h_c2;
   if (ok) {
     for (int i = 0; i < GW * GW; ++i) h_amap[i] = -1;
     if (dm)
@@ -775,30 +780,15 @@ static int wfs_fast_prepare(aom_ctx* ctx) {
         h_c2[(b * 3 + 2) * 32 + lane] = make_uint4(nh[0], nh[1], nl[0], nl[1]);
       }
   }
-  if (ok) {
-    // stage-2 B tiles of the tcgen05 kernel (wfs_tc.cuh): row n = 2 iota + {Yr, Yi}, K = {Tr(y), Ti(y)},
-    // UMMA canonical K-major no-swizzle layout (8-row x 16-byte core matrices, LBO 128 B, SBO 512 B)
-    for (int n = 0; n < 64; ++n)
-      for (int kk = 0; kk < 32; ++kk) {
-        const int iota = n >> 1, pout = n & 1, pin = kk >> 4, y = kk & 15;
-        const double wr = wft_w(y, iota, 0), wi = wft_w(y, iota, 1);
-        const double v = pout == 0 ? (pin == 0 ? wr : -wi) : (pin == 0 ? wi : wr);
-        const __half hi = __float2half_rn((float)v);
-        const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
-        const size_t off = (size_t)(n >> 3) * 512 + (size_t)(kk >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(kk & 7) * 2;
-        memcpy((unsigned char*)h_b2 + off, &hi, 2);
-        memcpy((unsigned char*)h_b2 + WTC_B_BYTES + off, &lo, 2);
-      }
-  }
   cudaError_t ce = cudaSuccess;
-  const void* srcs[7] = {h_sub, h_amap, h_pm, h_c1, h_c2, h_fxy, h_b2};
-  const size_t sizes[7] = {(size_t)nv * sizeof(uint2), (size_t)GW * GW * sizeof(short), (size_t)nv * 32,
-                           8 * 32 * sizeof(uint4), 12 * 32 * sizeof(uint4), sizeof(h_fxy), (size_t)2 * WTC_B_BYTES};
-  for (int i = 0; i < 7 && ok && ce == cudaSuccess; ++i) {
+  const void* srcs[6] = {h_sub, h_amap, h_pm, h_c1, h_c2, h_fxy};
+  const size_t sizes[6] = {(size_t)nv * sizeof(uint2), (size_t)GW * GW * sizeof(short), (size_t)nv * 32,
+                           8 * 32 * sizeof(uint4), 12 * 32 * sizeof(uint4), sizeof(h_fxy)};
+  for (int i = 0; i < 6 && ok && ce == cudaSuccess; ++i) {
     ce = cudaMalloc(&ctx->fast_dev[i], sizes[i]);
     if (ce == cudaSuccess) ce = cudaMemcpy(ctx->fast_dev[i], srcs[i], sizes[i], cudaMemcpyHostToDevice);
   }
-  free(h_sub); free(h_pm); free(h_amap); free(h_c1); free(h_c2); free(h_b2);
+  free(h_sub); free(h_pm); free(h_amap); free(h_c1); free(h_c2);
   if (ce != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "wfs_fast_prepare: %s", cudaGetErrorString(ce));
   if (!ok) FAST_NO("derived tables out of range");
 
@@ -831,8 +821,159 @@ static int wfs_fast_prepare(aom_ctx* ctx) {
   f.GW = GW;
   f.sub_in_smem = (nv <= 1280) ? 1 : 0;
   f.err = ctx->d_err;
+  ctx->fast_geom[0] = joffx; ctx->fast_geom[1] = joffy; ctx->fast_geom[2] = c0x; ctx->fast_geom[3] = c0y;
+  ctx->fast_geom[4] = GW; ctx->fast_geom[5] = dm ? 1 : 0;
   ctx->fast_state = 1;
   ctx->fast_why[0] = 0;
+  return AOM_OK;
+}
+
+// Host side of wfs_frame_umma_kernel (wfs_umma.cuh): same eligibility as the staged kernel plus an analytic
+// half-pixel phasor; derived tables in the (h, y) lane layout, operand tiles of the two DFT stages, 20 x 17 TMA boxes.
+#define UMMA_NO(...)                                             \
+  do {                                                           \
+    snprintf(ctx->fast_why, sizeof(ctx->fast_why), __VA_ARGS__); \
+    ctx->umma_state = -1;                                        \
+    return AOM_OK;                                               \
+  } while (0)
+
+static void umma_put_half(unsigned short* tile_hi, unsigned short* tile_lo, int n, int kk, double v) {
+  // UMMA canonical K-major no-swizzle layout: 8-row x 16-byte core matrices, LBO 128 B, SBO 512 B (K = 32 halves)
+  const __half hi = __float2half_rn((float)v);
+  const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+  const size_t off = (size_t)(n >> 3) * 512 + (size_t)(kk >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(kk & 7) * 2;
+  memcpy((unsigned char*)tile_hi + off, &hi, 2);
+  memcpy((unsigned char*)tile_lo + off, &lo, 2);
+}
+
+static int wfs_umma_prepare(aom_ctx* ctx) {
+  const aom_config& c = ctx->cfg;
+  if (ctx->umma_state != 0) return AOM_OK;
+  int rc = wfs_fast_prepare(ctx);
+  if (rc) return rc;
+  for (void*& b : ctx->umma_dev) { cudaFree(b); b = nullptr; }
+  if (ctx->fast_state != 1) { ctx->umma_state = -1; return AOM_OK; }      // fast_why already says why
+  if (c.nvalid < WU_WARPS) UMMA_NO("fewer than %d subapertures", WU_WARPS);
+  if (c.n_layers > WU_MAX_LAYERS) UMMA_NO("more than %d layers", WU_MAX_LAYERS);
+  const float* hxy = (const float*)ctx->htab[AOM_T_HALFXY];
+  if (!hxy) UMMA_NO("half-pixel phasor table not uploaded");
+  for (int i = 0; i < 16; ++i)
+    for (int j = 0; j < 16; ++j)
+      if (fabs((double)hxy[i * 16 + j] - M_PI * (double)(i + j) / 64.0) > 2e-6) UMMA_NO("half-pixel phasor is not pi (x + y) / Nfft");
+  const float* pup = (const float*)ctx->htab[AOM_T_MPUPIL];
+  const int* sx = (const int*)ctx->htab[AOM_T_SUB_X0];
+  const int* sy = (const int*)ctx->htab[AOM_T_SUB_Y0];
+  const float* stamp = (const float*)ctx->htab[AOM_T_STAMP1D];
+  const int* amap = (const int*)ctx->htab[AOM_T_ACT_MAP];
+  const int joffx = ctx->fast_geom[0], joffy = ctx->fast_geom[1], c0x = ctx->fast_geom[2], c0y = ctx->fast_geom[3];
+  const int GW = ctx->fast_geom[4];
+  const bool dm = ctx->fast_geom[5] != 0;
+  const int ss = c.stamp_size, nv = c.nvalid;
+  int cx = 0, cy = 0;
+  if (nv > 0) {
+    cx = (((sx[0] + c.pzt_off - c.pzt_i1_0) % 16) + 16) % 16;
+    cy = (((sy[0] + c.pzt_off - c.pzt_j1_0) % 16) + 16) % 16;
+  }
+  uint2* h_sub = (uint2*)malloc((size_t)nv * sizeof(uint2));
+  uint32_t* h_pm = (uint32_t*)malloc((size_t)nv * 32 * sizeof(uint32_t));
+  short* h_amap = (short*)malloc((size_t)GW * GW * sizeof(short));
+  unsigned short* h_b1 = (unsigned short*)calloc(2 * WU_B_BYTES, 1);     // [hi, lo] tiles of WU_B_BYTES each
+  unsigned short* h_b2 = (unsigned short*)calloc(2 * WU_B_BYTES, 1);
+  float h_fxy[2 * WU_NG * 16];
+  bool ok = h_sub && h_pm && h_amap && h_b1 && h_b2;
+  if (ok) {
+    for (int i = 0; i < GW * GW; ++i) h_amap[i] = -1;
+    if (dm)
+      for (int gy = 0; gy < c.pzt_grid_n; ++gy)
+        for (int gx = 0; gx < c.pzt_grid_n; ++gx)
+          h_amap[(gy + WU_PAD) * GW + gx + WU_PAD] = (short)amap[gy * c.pzt_grid_n + gx];
+    for (int k = 0; k < nv; ++k) {
+      int gb = 0;
+      if (dm) {
+        const int gxl = (sx[k] + c.pzt_off - c.pzt_i1_0 - cx) / 16 - joffx + WU_PAD;
+        const int gyl = (sy[k] + c.pzt_off - c.pzt_j1_0 - cy) / 16 - joffy + WU_PAD;
+        gb = gyl * GW + gxl;
+      }
+      bool full = true;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int yy = lane & 15, hh = lane >> 4;
+        unsigned m = 0;
+        for (int cc = 0; cc < 8; ++cc)
+          if (pup[(size_t)(sy[k] + yy) * c.n + sx[k] + 8 * hh + cc] != 0.f) m |= 1u << cc;
+        h_pm[(size_t)k * 32 + lane] = m;
+        full = full && m == 0xffu;
+      }
+      h_sub[k] = make_uint2(((uint32_t)sy[k] << 16) | (uint32_t)sx[k], (uint32_t)gb | (full ? 0x80000000u : 0u));
+    }
+    // x stamp factors [j][x], y stamp factors transposed [y][j]
+    for (int j = 0; j < WU_NG; ++j)
+      for (int x = 0; x < 16; ++x) {
+        const int ax = c0x + x - 16 * j, ay = c0y + x - 16 * j;
+        h_fxy[j * 16 + x] = (dm && ax >= 0 && ax < ss) ? stamp[ax] : 0.f;
+        h_fxy[WU_NG * 16 + x * WU_NG + j] = (dm && ay >= 0 && ay < ss) ? stamp[ay] : 0.f;
+      }
+    // stage 1: B1[n = 32 ro + fx][k = 16 ri + x]:  Tr = Wr Xr - Wi Xi ; Ti = Wi Xr + Wr Xi
+    // stage 2: B2[n = 2 fy + po][k = 16 ro + y]:   Yr = Tr Wr - Ti Wi ; Yi = Tr Wi + Ti Wr
+    unsigned short* b1_lo = (unsigned short*)((unsigned char*)h_b1 + WU_B_BYTES);
+    unsigned short* b2_lo = (unsigned short*)((unsigned char*)h_b2 + WU_B_BYTES);
+    for (int n = 0; n < 64; ++n)
+      for (int kk = 0; kk < 32; ++kk) {
+        {
+          const int ro = n >> 5, fx = n & 31, ri = kk >> 4, x = kk & 15;
+          const double wr = wft_w(x, fx, 0), wi = wft_w(x, fx, 1);
+          umma_put_half(h_b1, b1_lo, n, kk, ro == 0 ? (ri == 0 ? wr : -wi) : (ri == 0 ? wi : wr));
+        }
+        {
+          const int fy = n >> 1, po = n & 1, ro = kk >> 4, yy = kk & 15;
+          const double wr = wft_w(yy, fy, 0), wi = wft_w(yy, fy, 1);
+          umma_put_half(h_b2, b2_lo, n, kk, po == 0 ? (ro == 0 ? wr : -wi) : (ro == 0 ? wi : wr));
+        }
+      }
+  }
+  cudaError_t ce = cudaSuccess;
+  const void* srcs[6] = {h_sub, h_amap, h_pm, h_b1, h_b2, h_fxy};
+  const size_t sizes[6] = {(size_t)nv * sizeof(uint2), (size_t)GW * GW * sizeof(short), (size_t)nv * 32 * sizeof(uint32_t),
+                           (size_t)2 * WU_B_BYTES, (size_t)2 * WU_B_BYTES, sizeof(h_fxy)};
+  for (int i = 0; i < 6 && ok && ce == cudaSuccess; ++i) {
+    ce = cudaMalloc(&ctx->umma_dev[i], sizes[i]);
+    if (ce == cudaSuccess) ce = cudaMemcpy(ctx->umma_dev[i], srcs[i], sizes[i], cudaMemcpyHostToDevice);
+  }
+  free(h_sub); free(h_pm); free(h_amap); free(h_b1); free(h_b2);
+  if (ce != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "wfs_umma_prepare: %s", cudaGetErrorString(ce));
+  if (!ok) UMMA_NO("out of host memory");
+  if (c.n_layers > 0) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess)
+      UMMA_NO("cuTensorMapEncodeTiled not available");
+    for (int l = 0; l < c.n_layers; ++l) {
+      const cuuint64_t N = (cuuint64_t)c.screen_dim[l];
+      const cuuint64_t dims[3] = {N, N, (cuuint64_t)c.n_env};
+      const cuuint64_t strides[2] = {N * 4, N * N * 4};
+      const cuuint32_t box[3] = {WU_TILE_W, WU_TILE_H, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = ((aom_encode_tiled_fn)fn)(&ctx->umma.maps[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ctx->screen[l], dims,
+                                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) UMMA_NO("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+  }
+  WfsUmmaTables& f = ctx->umma.f;
+  memset(&f, 0, sizeof(f));
+  f.sub = (const uint2*)ctx->umma_dev[0];
+  f.amap = (const short*)ctx->umma_dev[1];
+  f.pmask = (const uint32_t*)ctx->umma_dev[2];
+  f.b1 = (const uint4*)ctx->umma_dev[3];
+  f.b2 = (const uint4*)ctx->umma_dev[4];
+  f.fxy = (const float*)ctx->umma_dev[5];
+  f.GW = GW;
+  f.err = ctx->d_err;
+  {
+    const char* sw = getenv("AOM_UMMA_SWAP");
+    f.a2_swap = (sw && sw[0] == '1') ? 1 : 0;
+  }
+  ctx->umma_state = 1;
   return AOM_OK;
 }
 
@@ -860,67 +1001,7 @@ static int wfs_fast_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) 
   return AOM_OK;
 }
 
-template <int NL>
-static int wfs_tc_launch_t(aom_ctx* ctx, const WfsParams& p, cudaStream_t st) {
-  const long long total = (long long)p.E * p.nvalid;
-  // one CTA of 16 warps per SM, about 8 waves, contiguous ranges of work items, at least 8 items per warp
-  long long grid = (long long)ctx->num_sms * 8;
-  long long ipc = (total + grid - 1) / grid;
-  if (ipc < 8 * WTC_WARPS) ipc = 8 * WTC_WARPS;
-  ipc = (ipc + WTC_WARPS - 1) / WTC_WARPS * WTC_WARPS;
-  grid = (total + ipc - 1) / ipc;
-  WfsTcParams P;
-  memset(&P, 0, sizeof(P));
-  P.p = p;
-  P.f = ctx->fast;
-  P.f.items_per_cta = ipc;
-  P.b2 = (const uint4*)ctx->fast_dev[6];
-  for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
-  const size_t smem = wtc_smem_bytes<NL>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
-  {
-    cudaError_t e = cudaFuncSetAttribute(wfs_frame_tc_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_tc_kernel): %s", cudaGetErrorString(e));
-  }
-  wfs_frame_tc_kernel<NL><<<(unsigned)grid, WTC_WARPS * 32, smem, st>>>(P);
-  return AOM_OK;
-}
-
-template <int FULL, int NL, int DM>
-static int wfs_pipe_launch_t(aom_ctx* ctx, const WfsParams& p, int grid, long long ipc, cudaStream_t st) {
-  WfsTmaParams P;
-  memset(&P, 0, sizeof(P));
-  P.p = p;
-  P.f = ctx->fast;
-  P.f.items_per_cta = ipc;
-  for (int l = 0; l < NL; ++l) P.maps[l] = ctx->fast_maps[l];
-  const size_t smem = wft_smem_bytes<NL>(P.f.GW, P.f.sub_in_smem ? p.nvalid : 0);
-  {
-    cudaError_t e = cudaFuncSetAttribute(wfs_frame_pipe_kernel<FULL, NL, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "cudaFuncSetAttribute(wfs_frame_pipe_kernel): %s", cudaGetErrorString(e));
-  }
-  wfs_frame_pipe_kernel<FULL, NL, DM><<<grid, WFT_WARPS * 32, smem, st>>>(P);
-  return AOM_OK;
-}
-
 static int wfs_fast_launch(aom_ctx* ctx, const WfsParams& p, int full, cudaStream_t st) {
-  if (ctx->opt[AOM_OPT_WFS_PATH] == AOM_WFS_TCGEN05 && full) {
-    switch (p.n_layers) {
-      case 0: return wfs_tc_launch_t<0>(ctx, p, st);
-      case 1: return wfs_tc_launch_t<1>(ctx, p, st);
-      case 3: return wfs_tc_launch_t<3>(ctx, p, st);
-    }
-  }
-  if (ctx->opt[AOM_OPT_WFS_PATH] == AOM_WFS_TENSOR_PIPE && full && (p.n_layers == 1 || p.n_layers == 3)) {
-    // software-pipelined variant (wfs_pipe.cuh): measured equal to the staged kernel, kept as an experiment
-    const long long total = (long long)p.E * p.nvalid;
-    long long grid = (long long)ctx->num_sms * 2 * 8;
-    long long ipc = (total + grid - 1) / grid;
-    if (ipc < 16 * WFT_WARPS) ipc = 16 * WFT_WARPS;
-    ipc = (ipc + WFT_WARPS - 1) / WFT_WARPS * WFT_WARPS;
-    grid = (total + ipc - 1) / ipc;
-    if (p.n_layers == 3) return p.use_dm ? wfs_pipe_launch_t<1, 3, 1>(ctx, p, (int)grid, ipc, st) : wfs_pipe_launch_t<1, 3, 0>(ctx, p, (int)grid, ipc, st);
-    return p.use_dm ? wfs_pipe_launch_t<1, 1, 1>(ctx, p, (int)grid, ipc, st) : wfs_pipe_launch_t<1, 1, 0>(ctx, p, (int)grid, ipc, st);
-  }
 #define WFT_GO(NL) return full ? wfs_fast_launch_t<1, NL>(ctx, p, st) : wfs_fast_launch_t<0, NL>(ctx, p, st)
   switch (p.n_layers) {
     case 0: WFT_GO(0);
@@ -996,18 +1077,23 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
       if (!ctx->wev[j][ctx->wev_n]) CU(cudaEventCreate(&ctx->wev[j][ctx->wev_n]));
     CU(cudaEventRecord(ctx->wev[0][ctx->wev_n], st));
   }
-  const bool staged = (path == AOM_WFS_TENSOR || path == AOM_WFS_TENSOR_FAST || path == AOM_WFS_TENSOR_PIPE ||
-                       path == AOM_WFS_TCGEN05);
+  const bool umma = (path == AOM_WFS_UMMA || path == AOM_WFS_UMMA_FAST);
+  const bool staged = umma || path == AOM_WFS_MMA_STAGED || path == AOM_WFS_MMA_STAGED_FAST;
+  const bool fast = (path == AOM_WFS_UMMA_FAST || path == AOM_WFS_MMA_STAGED_FAST);
   if (c.nfft == 64 && staged) {
-    rc = wfs_fast_prepare(ctx);
+    rc = umma ? wfs_umma_prepare(ctx) : wfs_fast_prepare(ctx);
     if (rc) return rc;
   }
-  if (c.nfft == 64 && staged && ctx->fast_state == 1) {
-    rc = wfs_fast_launch(ctx, p, path != AOM_WFS_TENSOR_FAST, st);
+  if (c.nfft == 64 && umma && ctx->umma_state == 1) {
+    cudaError_t le = wfs_umma_launch(p, ctx->umma, ctx->num_sms, !fast, st);
+    if (le != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "wfs_umma_launch: %s", cudaGetErrorString(le));
+  }
+  else if (c.nfft == 64 && staged && ctx->fast_state == 1) {
+    rc = wfs_fast_launch(ctx, p, !fast, st);
     if (rc) return rc;
   }
   else if (c.nfft == 64 && path != AOM_WFS_SIMT) {
-    const int full = (path != AOM_WFS_TENSOR_FAST);
+    const int full = !fast;
 #define WFM_LAUNCH(F, NL) wfs_frame_mma_kernel<F, NL><<<grid, WFM_WARPS * 32, 0, st>>>(p)
     switch (p.n_layers) {
       case 0: if (full) WFM_LAUNCH(1, 0); else WFM_LAUNCH(0, 0); break;
@@ -1048,15 +1134,14 @@ extern "C" const char* aom_wfs_kernel(aom_ctx* ctx) {
   if (!ctx) return "";
   const int path = ctx->opt[AOM_OPT_WFS_PATH];
   if (ctx->cfg.nfft != 64 || path == AOM_WFS_SIMT) return "wfs_frame_kernel";
-  if (path == AOM_WFS_TENSOR_REG) return "wfs_frame_mma_kernel";
+  if (path == AOM_WFS_MMA_REG) return "wfs_frame_mma_kernel";
+  if (path == AOM_WFS_UMMA || path == AOM_WFS_UMMA_FAST) {
+    if (wfs_umma_prepare(ctx) != AOM_OK) return "";
+    if (ctx->umma_state == 1) return "wfs_frame_umma_kernel";
+  }
   if (wfs_fast_prepare(ctx) != AOM_OK) return "";
-  if (ctx->fast_state == 1 && path == AOM_WFS_TCGEN05 &&
-      (ctx->cfg.n_layers == 0 || ctx->cfg.n_layers == 1 || ctx->cfg.n_layers == 3))
-    return "wfs_frame_tc_kernel";
-  if (ctx->fast_state == 1)
-    return (path == AOM_WFS_TENSOR_PIPE && (ctx->cfg.n_layers == 1 || ctx->cfg.n_layers == 3)) ? "wfs_frame_pipe_kernel"
-                                                                                             : "wfs_frame_tma_kernel";
-  snprintf(ctx->err, sizeof(ctx->err), "staged sensor kernel not eligible: %s", ctx->fast_why);
+  if (ctx->fast_state == 1) return "wfs_frame_tma_kernel";
+  snprintf(ctx->err, sizeof(ctx->err), "staged sensor kernels not eligible: %s", ctx->fast_why);
   return "wfs_frame_mma_kernel";
 }
 
@@ -1255,7 +1340,7 @@ extern "C" int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream) {
 extern "C" int aom_set_option(aom_ctx* ctx, int option, int value) {
   if (!ctx) return AOM_ERR_INVALID;
   if (option < 0 || option >= AOM_OPT_COUNT) return fail(ctx, AOM_ERR_INVALID, "unknown option %d", option);
-  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_TCGEN05))
+  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_MMA_STAGED_FAST))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_WFS_PATH: value %d out of range", value);
   if (option == AOM_OPT_TIME_WFS) ctx->wev_n = 0;
   if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_SIMT))

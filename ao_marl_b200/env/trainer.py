@@ -92,3 +92,58 @@ class BatchedTrainer(BatchedRollout):
                 stats = self.learner.update()
             self.learner.upload_actors(self.sim)
         return r_total, stats
+
+
+class StepLearner:
+    """Config 5 without the gym wrapper: the simulator's fused step on the main stream, one batched SAC update of every
+    agent per env-step on a second stream (the reference runs updates_per_episode_rpc = 1000 updates per 1000-step
+    episode per agent, GlobalConfig.py:63, train_rpc.py:759-781, 1084-1133), gradients all-reduced over the process
+    group when there is one.  Transitions go to the learner's device replay with the credit assignment window of
+    `DelayedMDP` (oldest state / action, newest next state, current reward; train_rpc.py:734-757)."""
+
+    def __init__(self, sim, rl, learner, depth=None):
+        import torch
+        self.torch = torch
+        self.sim, self.rl, self.learner = sim, rl, learner
+        dev = learner.device
+        idx = torch.as_tensor(rl.agent_idx.astype(np.int64), device=dev)
+        act = torch.as_tensor(rl.agent_act.astype(np.int64), device=dev)
+        self._idx, self._idx_ok = idx.clamp(min=0), (idx >= 0).float()
+        self._act, self._act_ok = act.clamp(min=0), (act >= 0).float()
+        e = rl.env_rl
+        self.mdp = DelayedMDP(e["delayed_assignment"], e["modification_online"]) if depth is None else DelayedMDP(depth, False)
+        self.stream = torch.cuda.Stream()
+        self.E = sim.n_env
+        self._s = sim.rows("STATE", rl.state_dim).clone()
+
+    def states_per_agent(self, state):
+        return state[:, self._idx].permute(1, 0, 2) * self._idx_ok[:, None, :]
+
+    def actions_per_agent(self, action):
+        return action[:, self._act].permute(1, 0, 2) * self._act_ok[:, None, :]
+
+    def step(self, learn=True, overlap=True):
+        """One env-step of the whole batch + (learn) one SAC update of all agents, the update on the second stream while
+        the step runs (overlap) or after it."""
+        torch = self.torch
+        sim, rl, L = self.sim, self.rl, self.learner
+        main = torch.cuda.current_stream()
+        can_learn = learn and len(L.memory) > L.batch_size
+        if can_learn and overlap:
+            self.stream.wait_stream(main)
+            with torch.cuda.stream(self.stream):
+                L.update()
+        sim.step(mode=0)
+        a = sim.rows("ACTION", rl.action_dim).clone()
+        r = sim.buffer("REWARD").view(self.E, rl.n_agents).clone()
+        s_next = sim.rows("STATE", rl.state_dim).clone()
+        if can_learn and not overlap:
+            L.update()
+        if can_learn and overlap:
+            main.wait_stream(self.stream)          # the replay is written below; the new actors are uploaded by the caller
+        if self.mdp.check_update_possibility():
+            s0, a0, s2 = self.mdp.credit_assignment()
+            L.memory.push(self.states_per_agent(s0), self.actions_per_agent(a0), r.t().contiguous(),
+                          self.states_per_agent(s2), torch.ones_like(r.t()))
+        self.mdp.save(self._s, a, s_next)
+        self._s = s_next

@@ -274,10 +274,11 @@ class Simulator:
         self.lib.aom_device_count_launches(self._ctx, ctypes.byref(n))
         return n.value
 
-    WFS_PATHS = {"tensor": 0, "tensor_fast": 1, "simt": 2, "tensor_reg": 3, "tensor_pipe": 4, "tcgen05": 5}
+    WFS_PATHS = {"umma": 0, "umma_fast": 1, "simt": 2, "tensor_reg": 3, "tensor": 4, "tensor_fast": 5}
 
     def set_wfs_path(self, name):
-        """Select the Shack-Hartmann frame kernel: 'tensor' (default), 'tensor_fast', 'tensor_reg' or 'simt'."""
+        """Select the Shack-Hartmann frame kernel: 'umma' (default: both DFT stages on tcgen05), 'umma_fast', 'simt'
+        (float32 FFT cross-check), 'tensor' / 'tensor_fast' / 'tensor_reg' (the round-1 mma.sync kernels)."""
         self._check(self.lib.aom_set_option(self._ctx, O["WFS_PATH"], self.WFS_PATHS[name]), "aom_set_option")
 
     def wfs_kernel(self):

@@ -33,11 +33,20 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # DRAM bytes per environment per launch of the sensor kernel from `ncu --set full` (dram__bytes_read.sum +
-# dram__bytes_write.sum of one launch at E = 1024, divided by 1024): profiles/r01_wfs_tma_E1024_metrics.csv,
-# profiles/r01_wfs_mma_E1024_metrics.csv.  Used for roofline.traffic (scaled to the E of this run).
-NCU_DRAM_BYTES_PER_ENV = {("40x40", "wfs_frame_pipe_kernel"): (4.108122e9 + 13.919744e6) / 1024,   # same tiles / boxes
-                          ("40x40", "wfs_frame_tma_kernel"): (4.108122e9 + 13.919744e6) / 1024,
+# dram__bytes_write.sum of one launch at E = 1024, divided by 1024).  Used for roofline.traffic (scaled to the E of this run).
+NCU_DRAM_BYTES_PER_ENV = {("40x40", "wfs_frame_umma_kernel"): (4.072948e9 + 13.814528e6) / 1024,   # profiles/r02_wfs_umma_v3_E1024_*
+                          ("40x40", "wfs_frame_tma_kernel"): (4.108122e9 + 13.919744e6) / 1024,    # profiles/r01_wfs_tma_E1024_*
                           ("40x40", "wfs_frame_mma_kernel"): (4.062998e9 + 18.132992e6) / 1024}
+
+ROOFLINE_NOTES = {
+    "wfs_frame_umma_kernel": "both DFT stages on tcgen05 (UTCHMMA, no HMMA; tensor pipe 14 %, DRAM 21 %): bound by the CUDA-core "
+                             "instruction stream around the tensor core (~1060 useful warp instructions per subaperture: bilinear "
+                             "trace, mirrors, sincos, fp16 hi/lo splits of both operands, |.|^2, centroid) at ~0.5 IPC per scheduler "
+                             "with 16 warps per SM; neither HBM nor tensor bound, see DESIGN.md section 4",
+    "wfs_frame_tma_kernel": "round-1 kernel: bound by its instruction count (~1110 warp instructions per subaperture, 144 of them "
+                            "mma.sync, at ~0.53 IPC per scheduler; HMMA pipe 50 %, DRAM 19 %)",
+    "wfs_frame_kernel": "issue-bound on the FP32 pipe (SIMT pruned FFT), not on HBM",
+}
 
 WORKLOADS = {
     "40x40": dict(par="production_sh_40x40_8m_3layers.py", world_size=44,
@@ -64,8 +73,14 @@ def parse():
                     help="run the fused per-subaperture denoiser inside every step (row a-6; the *_d0_noise files use it)")
     ap.add_argument("--geo", action="store_true",
                     help="also run the parameter file's geometric controller every step (SURVEY 8(f) rank 4; off by default)")
-    ap.add_argument("--wfs-path", default="tensor", choices=["tensor", "tensor_fast", "simt", "tensor_reg", "tensor_pipe", "tcgen05"],
-                    help="Shack-Hartmann frame kernel (tensor = default product path)")
+    ap.add_argument("--wfs-path", default=None,
+                    choices=["umma", "umma_fast", "simt", "tensor", "tensor_fast", "tensor_reg"],
+                    help="Shack-Hartmann frame kernel (default: the library's product path)")
+    ap.add_argument("--strehl", action="store_true",
+                    help="evaluate the target Strehl inside every timed step, as the reference's next_part_two does by "
+                         "default (compute_tar_psf=True, rlSupervisor.py:944-947); without the flag the figure is still "
+                         "reported as a variant beside the headline")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra sections (Strehl variant, learner, reset timing)")
     return ap.parse_args()
 
 
@@ -272,6 +287,102 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measure_variants(args, sim, t, rl, E, dist, barrier, ev):
+    """Extra timed sections of the same run (device times in ms, max over ranks taken by the caller):
+    strehl_ms   one env-step with the target Strehl evaluated every frame (the reference's default compute_tar_psf=True)
+    learn_*     config 5: one batched SAC update of all agents per env-step, gradients all-reduced over NCCL"""
+    import torch
+    out = {}
+    k = max(2, min(args.steps, 5))
+    if not args.strehl:
+        sim.step_with_strehl(True, 1.65)
+        for _ in range(2):
+            sim.step(mode=0)
+        barrier()
+        a, b = ev(enable_timing=True), ev(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            sim.step(mode=0)
+        b.record()
+        barrier()
+        out["strehl_ms"] = a.elapsed_time(b) / k
+        sim.step_with_strehl(False)
+    if rl.n_agents:
+        from ao_marl_b200.env.trainer import StepLearner
+        from ao_marl_b200.rl.sac import BatchedSAC
+        learner = BatchedSAC.from_layout(rl, device="cuda", seed=3, dist=dist, memory_size=4 * E)
+        sl = StepLearner(sim, rl, learner)
+        for _ in range(sl.mdp.depth + 2):           # fill the credit-assignment window and the replay
+            sl.step(learn=False)
+        for _ in range(2):                          # warm-up of the update (autograd graphs, optimiser state)
+            sl.step(learn=True, overlap=True)
+        barrier()
+        times = {}
+        for name, kw in (("learn_step_ms", dict(learn=True, overlap=True)), ("learn_serial_ms", dict(learn=True, overlap=False)),
+                         ("learn_env_only_ms", dict(learn=False))):
+            a, b = ev(enable_timing=True), ev(enable_timing=True)
+            a.record()
+            for _ in range(k):
+                sl.step(**kw)
+            b.record()
+            barrier()
+            times[name] = a.elapsed_time(b) / k
+        out.update(times)
+        # the update alone, and its gradient all-reduces alone (three buckets: critics, actors, temperatures)
+        a, b = ev(enable_timing=True), ev(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            learner.update()
+        b.record()
+        barrier()
+        out["learn_update_ms"] = a.elapsed_time(b) / k
+        buckets = [learner.critic_params, learner.actor_params, [learner.log_alpha]]
+        out["allreduce_bytes"] = int(sum(p.numel() for bk in buckets for p in bk) * 4)
+        out["allreduce_ms"] = 0.0
+        if dist is not None:
+            for bk in buckets:
+                for p in bk:
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+            a, b = ev(enable_timing=True), ev(enable_timing=True)
+            a.record()
+            for _ in range(k):
+                for bk in buckets:
+                    learner._allreduce(bk)
+            b.record()
+            barrier()
+            out["allreduce_ms"] = a.elapsed_time(b) / k
+        out["learn_agents"] = int(rl.n_agents)
+        out["learn_batch"] = int(learner.batch_size)
+        del sl, learner
+        torch.cuda.empty_cache()
+    return out
+
+
+def format_variants(v, args, E, world, ms):
+    out = {}
+    if "strehl_ms" in v:
+        out["with_strehl_every_frame"] = {
+            "ms_per_step": v["strehl_ms"], "value": E * world / (v["strehl_ms"] * 1e-3), "unit": "env-steps/s",
+            "note": "aom_step with AOM_OPT_STREHL: target Strehl (pupil sums, no focal-plane image) evaluated after "
+                    "apply_control on every frame, as the reference's default next_part_two does (rlSupervisor.py:944-947); "
+                    "the turbulence update then cannot run beside the actor GEMMs"}
+    if "learn_step_ms" in v:
+        out["learn"] = {
+            "config": "config 5: %d agents, batch %d, one SAC update of every agent per env-step, gradients "
+                      "all-reduced over %d rank(s)" % (v.get("learn_agents", 0), v.get("learn_batch", 0), world),
+            "ms_per_step_overlapped": v["learn_step_ms"], "ms_per_step_serial": v["learn_serial_ms"],
+            "ms_per_step_env_only": v["learn_env_only_ms"], "ms_per_update_alone": v["learn_update_ms"],
+            "env_steps_per_s": E * world / (v["learn_step_ms"] * 1e-3), "updates_per_s": 1e3 / v["learn_step_ms"],
+            "agent_updates_per_s": v.get("learn_agents", 0) * 1e3 / v["learn_step_ms"],
+            "allreduce_bytes_per_update": v.get("allreduce_bytes", 0), "allreduce_ms_per_update": v.get("allreduce_ms", 0.0),
+            "overlap": "update on a second stream beside aom_step: hidden fraction = %.2f"
+                       % max(0.0, min(1.0, (v["learn_serial_ms"] - v["learn_step_ms"]) / max(v["learn_update_ms"], 1e-9))),
+            "note": "env-only includes the replay pushes (state / action gathers per agent); reference semantics "
+                    "train_rpc.py:759-781, 1084-1133"}
+    return out
+
+
 def run_ours(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -289,7 +400,10 @@ def run_ours(args):
     E = args.envs or (4096 if args.workload == "40x40" else 1024)
     t_build = time.perf_counter()
     sim, t, rl = build_system(wl["par"], E, env_rl=dict(wl["env_rl"]), world_size=wl["world_size"], seed=0)
-    sim.set_wfs_path(args.wfs_path)
+    if args.wfs_path:
+        sim.set_wfs_path(args.wfs_path)
+    if args.strehl:
+        sim.step_with_strehl(True, 1.65)
     if args.denoise:
         from ao_marl_b200.denoiser import Autoencoder
         Autoencoder(dict(type="cnn_single_subaperture", path="autoencoder_M9_rms_3"), device="cuda", sim=sim)
@@ -300,7 +414,15 @@ def run_ours(args):
         sim.step_with_geo(True)
     wfs_kernel_name = sim.wfs_kernel()
     seeds = 1234 + rank * E + np.arange(E, dtype=np.int64)
-    sim.reset(seeds)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l_reset = sim.launches()
+    r0.record()
+    sim.reset(seeds)                  # RlSupervisor.reset: 2N extrusions per layer, timed on its own
+    r1.record()
+    torch.cuda.synchronize()
+    reset_ms = r0.elapsed_time(r1)
+    l_reset = sim.launches() - l_reset
     # first frame of the episode (AoEnv.reset ends with one linear step)
     sim.state_begin(); sim.move_atmos(); sim.comp_wfs_image(); sim.do_centroids(); sim.do_control(); sim.state_end()
     torch.cuda.synchronize()
@@ -339,6 +461,10 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     wfs_ms, _ = sim.wfs_time_ms()
     sim.time_wfs(False)
+
+    variants = {}
+    if not args.no_variants:
+        variants = measure_variants(args, sim, t, rl, E, dist, barrier, ev)
 
     # end to end through host buffers: the actions of every step come from pinned host memory (H2D) and go back to
     # it (D2H) -- the host is in the action loop, as in the reference's env.step -- and the step's state and rewards
@@ -394,10 +520,14 @@ def run_ours(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    t_all = torch.tensor([ms, ms_e2e, wfs_ms], dtype=torch.float64, device="cuda")
+    vkeys = sorted(k for k, v in variants.items() if isinstance(v, float))
+    t_all = torch.tensor([ms, ms_e2e, wfs_ms, reset_ms] + [variants[k] for k in vkeys], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, wfs_ms = [float(x) for x in t_all.cpu()]
+    vals = [float(x) for x in t_all.cpu()]
+    ms, ms_e2e, wfs_ms, reset_ms = vals[:4]
+    for k, v in zip(vkeys, vals[4:]):
+        variants[k] = v
     if rank == 0:
         peaks = {}
         try:
@@ -417,6 +547,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "envs_per_gpu": E, "total_envs": E * world,
+                       "strehl_every_frame": bool(args.strehl),
                        "parallelism": "env-sharded x%d, no collective on the step path" % world, "wfs_path": args.wfs_path,
                        "geo_controller": bool(args.geo), "denoiser": bool(args.denoise),
                        "l2": "inputs larger than L2 (%.1f GB of screens per GPU)" % (
@@ -431,11 +562,7 @@ def run_ours(args):
                          "peak_source": "measured" if peaks else "fallback",
                          "ms_per_launch": wfs_ms, "share_of_step": wfs_ms / (ms / args.steps),
                          "fp32_tflops_algorithmic": flops_per_frame * E / (wfs_ms * 1e-3) / 1e12,
-                         "note": "bound by its instruction count (~1110 warp instructions per subaperture, 144 of them "
-                                 "mma.sync, at ~0.53 IPC per scheduler; HMMA pipe 50 %, DRAM 19 %): neither HBM nor "
-                                 "tensor bound, see DESIGN.md section 4"
-                                 if args.wfs_path != "simt" else
-                                 "issue-bound on the FP32 pipe (SIMT pruned FFT), not on HBM: see DESIGN.md"},
+                         "note": ROOFLINE_NOTES.get(wfs_kernel_name, "see DESIGN.md section 4")},
             "e2e": {"value": k_e2e * E * world / (ms_e2e * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": int(E * rl.action_dim * 4),
                     "d2h_bytes_per_step": int(E * (rl.action_dim + rl.state_dim + rl.n_agents) * 4), "steps": k_e2e,
@@ -443,7 +570,14 @@ def run_ours(args):
                             "device snapshot on a copy stream, overlapped with the next step; the next step's turbulence "
                             "update (independent of the actions) runs on a second stream during the round trip"},
             "gpu_launches": int(launches), "clocks": clocks,
+            "reset": {"ms": reset_ms, "gpu_launches": int(l_reset),
+                      "extrusions": int(sum(2 * int(n) for n in t.dim_screens)),
+                      "ms_per_step_amortised_over_1000": reset_ms / 1000.0,
+                      "value_with_reset_per_1000_steps": total_steps / ((ms + args.steps * reset_ms / 1000.0) * 1e-3),
+                      "note": "RlSupervisor.reset (rlSupervisor.py:236-246): 2N sequential extrusions per layer, once per "
+                              "1000-step episode; not inside the timed steps"},
         }
+        line.update(format_variants(variants, args, E, world, ms))
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_seconds, 1)

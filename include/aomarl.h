@@ -171,14 +171,14 @@ enum {
   AOM_PUPIL_PIXEL = 1      /* one thread per pixel / one warp per row with plain global loads (cross-check path) */
 };
 enum {
-  AOM_WFS_TENSOR = 0,      /* TMA-staged tiles + tensor-pipe DFT, three fp16 MMAs per product in both stages (fp32-grade;
-                              default; geometries the staged kernel does not cover fall back to AOM_WFS_TENSOR_REG) */
-  AOM_WFS_TENSOR_FAST = 1, /* same, twiddle low parts dropped in stage 2 (slopes ~1e-5 relative) */
+  AOM_WFS_UMMA = 0,        /* both stages of the pruned DFT on tcgen05 / TMEM, eight subapertures per tensor-core tile, TMA-staged
+                              screen tiles, three fp16 products per stage (fp32-grade; default; wfs_umma.cuh).  Geometries it does
+                              not cover fall back to AOM_WFS_MMA_STAGED, then AOM_WFS_MMA_REG (aom_last_error says why) */
+  AOM_WFS_UMMA_FAST = 1,   /* same, the stage-1 result handed to stage 2 as one rounded fp16 (slopes ~3e-5 relative) */
   AOM_WFS_SIMT = 2,        /* float32 shared-memory FFT on the FP32 pipe (cross-check path) */
-  AOM_WFS_TENSOR_REG = 3,  /* tensor-pipe DFT fed by plain global loads (generation 2; cross-check path) */
-  AOM_WFS_TENSOR_PIPE = 4, /* staged kernel software-pipelined across subapertures inside each warp (experiment: measured
-                              equal to the default; 1- and 3-layer atmospheres, otherwise the default kernel runs) */
-  AOM_WFS_TCGEN05 = 5      /* staged kernel with stage 2 of the DFT on tcgen05 / TMEM (0-, 1- and 3-layer atmospheres) */
+  AOM_WFS_MMA_REG = 3,     /* round-1 generation 2: warp-level mma.sync DFT fed by plain global loads (any Nfft = 64 geometry) */
+  AOM_WFS_MMA_STAGED = 4,  /* round-1 default: TMA-staged tiles + warp-level mma.sync DFT (cross-check / comparison path) */
+  AOM_WFS_MMA_STAGED_FAST = 5  /* same, twiddle low parts dropped in stage 2 */
 };
 
 enum {
@@ -216,7 +216,7 @@ int aom_set_layer(aom_ctx* ctx, int layer, float deltax, float deltay, float amp
 int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* stream);
 
 /* Name of the kernel the next aom_comp_wfs_image will launch under the current AOM_OPT_WFS_PATH
- * ("wfs_frame_pipe_kernel", "wfs_frame_tma_kernel", "wfs_frame_mma_kernel" or "wfs_frame_kernel"); when the staged kernel is not
+ * ("wfs_frame_umma_kernel", "wfs_frame_tma_kernel", "wfs_frame_mma_kernel" or "wfs_frame_kernel"); when the staged kernel is not
  * eligible for the geometry, aom_last_error() says why. */
 const char* aom_wfs_kernel(aom_ctx* ctx);
 

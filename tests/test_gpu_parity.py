@@ -162,7 +162,8 @@ def test_phase_and_frame(sim10, oracle_tab10, oracle_imat10, static10, torch):
 
 
 def test_wfs_paths_agree(sim10, static10, torch):
-    """Tensor-pipe DFT (fp16 split, 3 MMAs per product) against the float32 shared-memory FFT on the same frame."""
+    """Every tensor-core DFT path (tcgen05 default and the round-1 mma.sync kernels; fp16 split, 3 products per stage) against
+    the float32 shared-memory FFT on the same frame."""
     seeds = np.array([21, 22, 23, 24], dtype=np.int64)
     sim10.reset(seeds)
     r = np.random.default_rng(9)
@@ -170,26 +171,25 @@ def test_wfs_paths_agree(sim10, static10, torch):
     sim10.set_dm_volts(torch.as_tensor(volts, device="cuda"))
     out = {}
     try:
-        for path in ("simt", "tensor", "tensor_fast", "tensor_reg", "tensor_pipe", "tcgen05"):
+        for path in ("simt", "tensor", "tensor_fast", "tensor_reg", "umma", "umma_fast"):
             sim10.set_wfs_path(path)
+            if path in ("umma", "umma_fast"):
+                assert sim10.wfs_kernel() == "wfs_frame_umma_kernel", sim10.lib.aom_last_error(sim10._ctx)
             if path in ("tensor", "tensor_fast"):
                 assert sim10.wfs_kernel() == "wfs_frame_tma_kernel", sim10.lib.aom_last_error(sim10._ctx)
-            if path == "tensor_pipe":
-                assert sim10.wfs_kernel() == "wfs_frame_pipe_kernel", sim10.lib.aom_last_error(sim10._ctx)
-            if path == "tcgen05":
-                assert sim10.wfs_kernel() == "wfs_frame_tc_kernel", sim10.lib.aom_last_error(sim10._ctx)
             sim10.comp_wfs_image(keep_image=True, noise=-1.0)
             sim10.do_centroids()
             out[path] = (sim10.rows("SLOPES", static10.nslopes).cpu().numpy().copy(),
                          sim10.buffer("BINCUBE").cpu().numpy().copy())
     finally:
-        sim10.set_wfs_path("tensor")
+        sim10.set_wfs_path("umma")
     assert relerr(out["tensor"][1], out["simt"][1]) < 2e-5
     assert relerr(out["tensor"][0], out["simt"][0]) < 2e-5
     assert relerr(out["tensor_fast"][0], out["simt"][0]) < 5e-4
-    for path in ("tensor_reg", "tensor_pipe", "tcgen05"):
+    for path in ("tensor_reg", "umma"):
         assert relerr(out[path][1], out["simt"][1]) < 2e-5
         assert relerr(out[path][0], out["simt"][0]) < 2e-5
+    assert relerr(out["umma_fast"][0], out["simt"][0]) < 5e-4
 
 
 def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
@@ -206,17 +206,16 @@ def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
             for _ in range(3):
                 sim10.move_atmos()
             res = {}
-            for path in ("simt", "tensor", "tensor_pipe", "tcgen05"):
+            for path in ("simt", "tensor", "umma"):
                 sim10.set_wfs_path(path)
                 sim10.comp_wfs_image(keep_image=(it % 2 == 0), noise=-1.0)
                 sim10.do_centroids()
                 res[path] = sim10.rows("SLOPES", n).cpu().numpy().copy()
             sim10.check_device()
             assert relerr(res["tensor"], res["simt"]) < 2e-5, it
-            assert relerr(res["tensor_pipe"], res["simt"]) < 2e-5, it
-            assert relerr(res["tcgen05"], res["simt"]) < 2e-5, it
+            assert relerr(res["umma"], res["simt"]) < 2e-5, it
     finally:
-        sim10.set_wfs_path("tensor")
+        sim10.set_wfs_path("umma")
 
 
 def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
@@ -226,7 +225,7 @@ def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
     from oracle import aoframe
     seeds = np.array([11, 12, 13, 14], dtype=np.int64)
     try:
-        for path in ("tensor", "tensor_pipe", "tcgen05", "tensor_reg", "simt"):
+        for path in ("umma", "tensor", "tensor_reg", "simt"):
             sim10.set_wfs_path(path)
             sim10.reset(seeds)
             sim10.comp_wfs_image(keep_image=True, noise=-1.0)       # frame 0
@@ -239,7 +238,7 @@ def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
                 ref = aoframe.sh_noise(clean[e], 3.0, int(seeds[e]), static10.wfs_index, 0)
                 assert np.array_equal(noisy[e], ref), path
     finally:
-        sim10.set_wfs_path("tensor")
+        sim10.set_wfs_path("umma")
 
 
 def test_imat_matches_oracle(static10, oracle_imat10, torch):
@@ -380,7 +379,7 @@ def test_40x40_flat_and_tilt(system40, torch):
     """Flat wavefront -> zero slopes; a tip-tilt command -> the same slope on every subaperture, linear in the
     command; all on the staged kernel."""
     sim, t, rl = system40
-    assert sim.wfs_kernel() == "wfs_frame_tma_kernel", sim.lib.aom_last_error(sim._ctx)
+    assert sim.wfs_kernel() == "wfs_frame_umma_kernel", sim.lib.aom_last_error(sim._ctx)
     nv = t.p_wfs._nvalid
     sim.reset(np.arange(6, dtype=np.int64) + 500)
     sim.reset_dm()
@@ -423,7 +422,7 @@ def test_40x40_kernel_generations_agree(system40, torch):
             for _ in range(1 + 40 * it):
                 sim.move_atmos()
             res = {}
-            for path in ("simt", "tensor", "tensor_reg", "tensor_pipe", "tcgen05"):
+            for path in ("simt", "tensor", "tensor_reg", "umma"):
                 sim.set_wfs_path(path)
                 sim.comp_wfs_image(noise=-1.0)
                 sim.do_centroids()
@@ -432,10 +431,9 @@ def test_40x40_kernel_generations_agree(system40, torch):
             assert np.abs(res["simt"]).max() > 1e-3
             assert relerr(res["tensor"], res["simt"]) < 2e-5, it
             assert relerr(res["tensor_reg"], res["simt"]) < 2e-5, it
-            assert relerr(res["tensor_pipe"], res["simt"]) < 2e-5, it
-            assert relerr(res["tcgen05"], res["simt"]) < 2e-5, it
+            assert relerr(res["umma"], res["simt"]) < 2e-5, it
     finally:
-        sim.set_wfs_path("tensor")
+        sim.set_wfs_path("umma")
 
 
 def test_40x40_closed_loop_properties(system40, torch):

@@ -180,9 +180,16 @@ def closed_loop_compare(name, sim, t, rl, envs, steps, torch, noisy=False):
     sim.state_begin(); sim.move_atmos(); sim.comp_wfs_image(keep_image=noisy); sim.do_centroids(); sim.do_control(); sim.state_end()
     states = [o.linear_step(hook_for(e)) for e, o in enumerate(envs)]
     st = sim.rows("STATE", rl.state_dim).cpu().numpy()
+    # State entries of the modes the command matrix filters out are rounding noise divided by the reference's own
+    # statistics of rounding noise (std ~2e-9 in the committed normalisation files, modes 1276..1280): they are
+    # chaotic in the reference too and are compared only for finiteness.  Every other entry is held to RTOL.
+    live = np.tile((rl.norm["dm"]["std"] > 1e-6) & (rl.norm["dm_residual"]["std"] > 1e-6), rl.state_dim // rl.state_modes)
+    REPORT.setdefault(name, {})["state_entries_compared"] = int(live.sum())
+    REPORT[name]["state_entries_degenerate"] = int((~live).sum())
     for e in range(len(envs)):
-        record(name, "state", relerr(st[e], states[e]))
+        record(name, "state", relerr(st[e][live], states[e][live]))
     for it in range(steps):
+        st_in = st                    # the state both actors read
         sim.step(mode=0)
         act = sim.rows("ACTION", rl.action_dim).cpu().numpy()
         rew = sim.buffer("REWARD").view(E, rl.n_agents).cpu().numpy()
@@ -190,15 +197,17 @@ def closed_loop_compare(name, sim, t, rl, envs, steps, torch, noisy=False):
         com = sim.rows("COM", t.nactu).cpu().numpy()
         err = sim.rows("ERR", t.nactu).cpu().numpy()
         sl = sim.rows("SLOPES", t.nslopes).cpu().numpy()
+        assert np.isfinite(st).all()
         for e, o in enumerate(envs):
-            a, _ = o.actors(states[e])
+            # actors on the SAME input (the GPU's state, degenerate entries included): parity of the policy evaluation
+            a, _ = o.actors(st_in[e])
             record(name, "actions", relerr(act[e], a))
             states[e], r = o.env_step(act[e], hook_for(e))
             record(name, "slopes", relerr(sl[e], o.slopes))
             record(name, "commands", relerr(com[e], o.com))
             record(name, "err", relerr(err[e], o.err))
             record(name, "rewards", relerr(rew[e], r))
-            record(name, "state", relerr(st[e], states[e]))
+            record(name, "state", relerr(st[e][live], states[e][live]))
     # the frame the loop ended on: pupil phase (atmosphere + mirrors) and, noise-free, the detector cube
     ph = sim.raytrace_wfs().cpu().numpy()
     for e, o in enumerate(envs):
