@@ -15,6 +15,7 @@
 #include "wfs_mma.cuh"
 #include "wfs_tma.cuh"
 #include "wfs_umma_host.h"
+#include "extrude_i8_host.h"
 #include "geo_kernels.cuh"
 #include "pupil_sweep.cuh"
 #include "denoise_kernels.cuh"
@@ -39,6 +40,13 @@ struct aom_ctx {
   uint32_t *k0, *k1;
   float *Z, *zref, *newcol;
   int ldz_max, ldn_max;
+  // exact integer extrusion (extrude_i8.cuh): operator digit planes per layer, environment digit planes, row scales
+  uint8_t* oz_ab[AOM_MAX_LAYERS];
+  int* oz_ea[AOM_MAX_LAYERS];
+  int oz_kb[AOM_MAX_LAYERS], oz_nt[AOM_MAX_LAYERS];
+  uint8_t* oz_zs;
+  int* oz_ev;
+  size_t oz_zs_bytes;
   // sensor / rtc
   float *slopes_frame, *slopes, *err_v, *com, *com1, *volts, *com_before;
   float *bincube, *phase;
@@ -247,6 +255,8 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
                   ctx->geo_com, ctx->geo_volts, ctx->geo_b, ctx->geo_T, ctx->strehl_geo, ctx->geo_acc, ctx->geo_mom,
                   ctx->sweep_mask, ctx->sweep_ttp};
   for (void* b : bufs) cudaFree(b);
+  for (int l = 0; l < AOM_MAX_LAYERS; ++l) { cudaFree(ctx->oz_ab[l]); cudaFree(ctx->oz_ea[l]); }
+  cudaFree(ctx->oz_zs); cudaFree(ctx->oz_ev);
   for (void* b : ctx->fast_dev) cudaFree(b);
   for (void* b : ctx->umma_dev) cudaFree(b);
   for (int i = 0; i < AOM_WFS_TIMERS; ++i)
@@ -316,6 +326,26 @@ extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* hos
     ctx->umma_state = 0;
   }
   if (table == AOM_T_MPUPIL || table == AOM_T_TT_PLANES) ctx->sweep_state = 0;
+  if (table == AOM_T_AB) {
+    // digit planes of [A | B] for the exact integer extrusion
+    const aom_config& c = ctx->cfg;
+    const int N = c.screen_dim[index], K = c.stencil_size[index] + N, ld = AOM_LD(K);
+    const int KB = (K + OZ_BK - 1) / OZ_BK, NT = (N + OZ_BN - 1) / OZ_BN;
+    const size_t bytes = (size_t)NT * KB * OZ_SLICES_B * OZ_B_TILE;
+    uint8_t* planes = (uint8_t*)calloc(bytes, 1);
+    int* ea = (int*)calloc((size_t)NT * OZ_BN, sizeof(int));
+    if (!planes || !ea) { free(planes); free(ea); return fail(ctx, AOM_ERR_INVALID, "out of host memory"); }
+    oz_slice_operator((const float*)host, N, ld, K, KB, NT, planes, ea);
+    cudaFree(ctx->oz_ab[index]); cudaFree(ctx->oz_ea[index]);
+    ctx->oz_ab[index] = nullptr; ctx->oz_ea[index] = nullptr;
+    cudaError_t e1 = cudaMalloc((void**)&ctx->oz_ab[index], bytes);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void**)&ctx->oz_ea[index], (size_t)NT * OZ_BN * sizeof(int)) : e1;
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->oz_ab[index], planes, bytes, cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->oz_ea[index], ea, (size_t)NT * OZ_BN * sizeof(int), cudaMemcpyHostToDevice);
+    free(planes); free(ea);
+    if (e2 != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "extrusion digit planes: %s", cudaGetErrorString(e2));
+    ctx->oz_kb[index] = KB; ctx->oz_nt[index] = NT;
+  }
   return AOM_OK;
 }
 
@@ -536,11 +566,36 @@ static int extrude_once(aom_ctx* ctx, int l, int axis, int sign, cudaStream_t st
   p.N = c.screen_dim[l]; p.S = c.stencil_size[l]; p.E = c.n_env; p.layer = l; p.axis = axis; p.sign = sign;
   p.amp = c.amp[l];
   p.ldz = AOM_LD(p.S + p.N); p.Z = ctx->Z; p.zref = ctx->zref; p.ldn = AOM_LD(p.N); p.newcol = ctx->newcol;
-  extrude_gather_kernel<<<c.n_env, 256, 0, st>>>(p);
-  KCHECK();
-  int rc = launch_gemm(ctx, 0, ctx->Z, p.ldz, 0, (const float*)ctx->tab[AOM_T_AB][l], p.ldz, 0, ctx->newcol, p.ldn, 0,
-                       c.n_env, p.N, p.S + p.N, nullptr, 0, 0, 1, st, nullptr, 0, true);
-  if (rc) return rc;
+  if (ctx->opt[AOM_OPT_EXTRUDE_PATH] == AOM_EXTRUDE_I8) {
+    // exact integer contraction on tcgen05 (extrude_i8.cuh): digits of the inputs, 13 int8 digit-pair products with
+    // int32 accumulators, one rounding to float32 after adding the reference pixel
+    const int KB = ctx->oz_kb[l], NT = ctx->oz_nt[l], MT = (c.n_env + OZ_BM - 1) / OZ_BM;
+    const size_t need = (size_t)MT * KB * OZ_SLICES * OZ_A_TILE;
+    if (need > ctx->oz_zs_bytes) {
+      cudaFree(ctx->oz_zs); ctx->oz_zs = nullptr; ctx->oz_zs_bytes = 0;
+      CU(cudaMalloc((void**)&ctx->oz_zs, need));
+      CU(cudaMemset(ctx->oz_zs, 0, need));
+      ctx->oz_zs_bytes = need;
+    }
+    if (!ctx->oz_ev) CU(dalloc(&ctx->oz_ev, (size_t)c.n_env));
+    OzGatherParams g;
+    g.screen = p.screen; g.ox = p.ox; g.oy = p.oy; g.count = p.count; g.k0 = p.k0; g.k1 = p.k1; g.stencil = p.stencil;
+    g.zref = ctx->zref; g.ev = ctx->oz_ev; g.Zs = ctx->oz_zs; g.N = p.N; g.S = p.S; g.E = p.E; g.KB = KB; g.layer = l;
+    g.axis = axis; g.sign = sign; g.amp = p.amp;
+    OzGemmParams m;
+    m.Zs = ctx->oz_zs; m.ABs = ctx->oz_ab[l]; m.ev = ctx->oz_ev; m.ea = ctx->oz_ea[l]; m.zref = ctx->zref;
+    m.out = ctx->newcol; m.ldo = p.ldn; m.E = p.E; m.N = p.N; m.KB = KB; m.err = ctx->d_err;
+    cudaError_t le = oz_extrude_launch(g, m, MT, NT, st);
+    if (le != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "oz_extrude_launch: %s", cudaGetErrorString(le));
+    ctx->launches += 2;
+    p.zref = nullptr;                                  // the reference pixel is already in the new column
+  } else {
+    extrude_gather_kernel<<<c.n_env, 256, 0, st>>>(p);
+    KCHECK();
+    int rc = launch_gemm(ctx, 0, ctx->Z, p.ldz, 0, (const float*)ctx->tab[AOM_T_AB][l], p.ldz, 0, ctx->newcol, p.ldn, 0,
+                         c.n_env, p.N, p.S + p.N, nullptr, 0, 0, 1, st, nullptr, 0, true);
+    if (rc) return rc;
+  }
   extrude_scatter_kernel<<<(c.n_env + 7) / 8, 256, 0, st>>>(p);
   KCHECK();
   return AOM_OK;

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) extrude_scatter_kernel(ExtrudeParams p) {
   const int N = p.N;
   float* scr = p.screen + (size_t)e * N * N;
   const int ox = p.ox[e], oy = p.oy[e];
-  const float zr = p.zref[e];
+  const float zr = p.zref ? p.zref[e] : 0.f;           // null: the GEMM already added the reference pixel
   __syncwarp();                                              // every lane holds the old ring origin
   int nox = ox, noy = oy;
   if (p.axis == 0) nox = (p.sign > 0) ? wrapN(ox + 1, N) : (ox == 0 ? N - 1 : ox - 1);

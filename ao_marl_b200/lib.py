@@ -47,7 +47,7 @@ BUFFERS = ["SCREEN", "RING_OX", "RING_OY", "SLOPES", "ERR", "COM", "VOLTS", "BIN
            "RES_MODES", "STATE", "REWARD", "ACTION", "ACTION_MEAN", "STREHL", "GEO_COM", "GEO_VOLTS", "STREHL_GEO", "GEO_PROJ"]
 B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
-OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH", "KEEP_IMAGE", "STREHL", "STREHL_LAMBDA_NM"]
+OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH", "KEEP_IMAGE", "STREHL", "STREHL_LAMBDA_NM", "EXTRUDE_PATH"]
 O = {name: i for i, name in enumerate(OPTIONS)}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
@@ -294,6 +294,10 @@ class Simulator:
         ms, n = ctypes.c_float(), ctypes.c_int()
         self._check(self.lib.aom_wfs_time_ms(self._ctx, ctypes.byref(ms), ctypes.byref(n)), "aom_wfs_time_ms")
         return float(ms.value), int(n.value)
+
+    def set_extrude_path(self, name):
+        """Contraction behind the screen extrusion: 'i8' (default: exact integer digits on tcgen05) or 'ffma' (float32)."""
+        self._check(self.lib.aom_set_option(self._ctx, O["EXTRUDE_PATH"], {"i8": 0, "ffma": 1}[name]), "aom_set_option")
 
     GEMM_PATHS = {"tcgen05": 0, "simt": 1}
 

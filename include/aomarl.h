@@ -163,8 +163,14 @@ typedef enum aom_option {
   AOM_OPT_STREHL,       /* != 0: aom_step evaluates the target Strehl every frame at AOM_OPT_STREHL_LAMBDA_NM, as
                            next_part_two does with compute_tar_psf=True (rlSupervisor.py:944-947) */
   AOM_OPT_STREHL_LAMBDA_NM, /* target wavelength in nanometres for AOM_OPT_STREHL (default 1650) */
+  AOM_OPT_EXTRUDE_PATH, /* which contraction serves the screen extrusion (aom_move_atmos / aom_reset) */
   AOM_OPT_COUNT
 } aom_option;
+enum {
+  AOM_EXTRUDE_I8 = 0,      /* exact integer contraction on tcgen05 (int8 digit planes, int32 accumulators, one rounding to
+                              float32 per new pixel; default; extrude_i8.cuh) */
+  AOM_EXTRUDE_FFMA = 1     /* float32 FFMA accumulation with round-to-nearest (round-1 kernel, cross-check path) */
+};
 enum {
   AOM_PUPIL_SWEEP = 0,     /* staged screen rows, one warp per strip of pupil rows (pitch-16 lattices; default; other
                               geometries fall back to AOM_PUPIL_PIXEL) */
