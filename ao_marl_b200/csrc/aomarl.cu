@@ -47,6 +47,14 @@ struct aom_ctx {
   uint8_t* oz_zs;
   int* oz_ev;
   size_t oz_zs_bytes;
+  // the same integer contraction for the controller's operator products (cmat, v2m, m2v): operator digit planes per
+  // table, scratch digit planes of the per-environment vectors (main stream; the extrusion has its own on the side stream)
+  uint8_t* ozop[AOM_T_COUNT];
+  int* ozop_ea[AOM_T_COUNT];
+  int ozop_kb[AOM_T_COUNT], ozop_nt[AOM_T_COUNT];
+  uint8_t* oz_xs;
+  int* oz_xev;
+  size_t oz_xs_bytes;
   // sensor / rtc
   float *slopes_frame, *slopes, *err_v, *com, *com1, *volts, *com_before;
   float *bincube, *phase;
@@ -256,7 +264,8 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
                   ctx->sweep_mask, ctx->sweep_ttp};
   for (void* b : bufs) cudaFree(b);
   for (int l = 0; l < AOM_MAX_LAYERS; ++l) { cudaFree(ctx->oz_ab[l]); cudaFree(ctx->oz_ea[l]); }
-  cudaFree(ctx->oz_zs); cudaFree(ctx->oz_ev);
+  for (int t = 0; t < AOM_T_COUNT; ++t) { cudaFree(ctx->ozop[t]); cudaFree(ctx->ozop_ea[t]); }
+  cudaFree(ctx->oz_zs); cudaFree(ctx->oz_ev); cudaFree(ctx->oz_xs); cudaFree(ctx->oz_xev);
   for (void* b : ctx->fast_dev) cudaFree(b);
   for (void* b : ctx->umma_dev) cudaFree(b);
   for (int i = 0; i < AOM_WFS_TIMERS; ++i)
@@ -304,6 +313,27 @@ static size_t table_expected_bytes(const aom_ctx* ctx, int t, int index) {
   return 0;
 }
 
+// digit planes of an operator [rows][ld] (K valid columns) for the integer contraction (extrude_i8.cuh)
+static int oz_upload_operator(aom_ctx* ctx, const float* host, int rows, int ld, int K, uint8_t** planes_d, int** ea_d,
+                              int* kb_out, int* nt_out) {
+  const int KB = (K + OZ_BK - 1) / OZ_BK, NT = (rows + OZ_BN - 1) / OZ_BN;
+  const size_t bytes = (size_t)NT * KB * OZ_SLICES_B * OZ_B_TILE;
+  uint8_t* planes = (uint8_t*)calloc(bytes, 1);
+  int* ea = (int*)calloc((size_t)NT * OZ_BN, sizeof(int));
+  if (!planes || !ea) { free(planes); free(ea); return fail(ctx, AOM_ERR_INVALID, "out of host memory"); }
+  oz_slice_operator(host, rows, ld, K, KB, NT, planes, ea);
+  cudaFree(*planes_d); cudaFree(*ea_d);
+  *planes_d = nullptr; *ea_d = nullptr;
+  cudaError_t e = cudaMalloc((void**)planes_d, bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)ea_d, (size_t)NT * OZ_BN * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(*planes_d, planes, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(*ea_d, ea, (size_t)NT * OZ_BN * sizeof(int), cudaMemcpyHostToDevice);
+  free(planes); free(ea);
+  if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "operator digit planes: %s", cudaGetErrorString(e));
+  *kb_out = KB; *nt_out = NT;
+  return AOM_OK;
+}
+
 extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* host, size_t nbytes) {
   if (!ctx || !host) return fail(ctx, AOM_ERR_INVALID, "null argument");
   if (table < 0 || table >= AOM_T_COUNT || index < 0 || index >= AOM_MAX_LAYERS)
@@ -329,22 +359,18 @@ extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* hos
   if (table == AOM_T_AB) {
     // digit planes of [A | B] for the exact integer extrusion
     const aom_config& c = ctx->cfg;
-    const int N = c.screen_dim[index], K = c.stencil_size[index] + N, ld = AOM_LD(K);
-    const int KB = (K + OZ_BK - 1) / OZ_BK, NT = (N + OZ_BN - 1) / OZ_BN;
-    const size_t bytes = (size_t)NT * KB * OZ_SLICES_B * OZ_B_TILE;
-    uint8_t* planes = (uint8_t*)calloc(bytes, 1);
-    int* ea = (int*)calloc((size_t)NT * OZ_BN, sizeof(int));
-    if (!planes || !ea) { free(planes); free(ea); return fail(ctx, AOM_ERR_INVALID, "out of host memory"); }
-    oz_slice_operator((const float*)host, N, ld, K, KB, NT, planes, ea);
-    cudaFree(ctx->oz_ab[index]); cudaFree(ctx->oz_ea[index]);
-    ctx->oz_ab[index] = nullptr; ctx->oz_ea[index] = nullptr;
-    cudaError_t e1 = cudaMalloc((void**)&ctx->oz_ab[index], bytes);
-    cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc((void**)&ctx->oz_ea[index], (size_t)NT * OZ_BN * sizeof(int)) : e1;
-    if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->oz_ab[index], planes, bytes, cudaMemcpyHostToDevice);
-    if (e2 == cudaSuccess) e2 = cudaMemcpy(ctx->oz_ea[index], ea, (size_t)NT * OZ_BN * sizeof(int), cudaMemcpyHostToDevice);
-    free(planes); free(ea);
-    if (e2 != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "extrusion digit planes: %s", cudaGetErrorString(e2));
-    ctx->oz_kb[index] = KB; ctx->oz_nt[index] = NT;
+    const int N = c.screen_dim[index], K = c.stencil_size[index] + N;
+    int rc = oz_upload_operator(ctx, (const float*)host, N, AOM_LD(K), K, &ctx->oz_ab[index], &ctx->oz_ea[index],
+                                &ctx->oz_kb[index], &ctx->oz_nt[index]);
+    if (rc) return rc;
+  }
+  if (table == AOM_T_CMAT || table == AOM_T_V2M || table == AOM_T_M2V) {
+    const aom_config& c = ctx->cfg;
+    const int rows = table == AOM_T_V2M ? c.nmodes : c.nactu;
+    const int K = table == AOM_T_CMAT ? c.nslopes : table == AOM_T_V2M ? c.nactu : c.nmodes;
+    int rc = oz_upload_operator(ctx, (const float*)host, rows, AOM_LD(K), K, &ctx->ozop[table], &ctx->ozop_ea[table],
+                                &ctx->ozop_kb[table], &ctx->ozop_nt[table]);
+    if (rc) return rc;
   }
   return AOM_OK;
 }
@@ -508,7 +534,7 @@ static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long
   p.com = com; p.ldcom = ldcom; p.gain = ctx->gain; p.closed = ctx->closed;
   // `exact`: float32 FFMA accumulation with round-to-nearest (the recursive screen extrusion needs it: the
   // tensor core truncates its float32 accumulator, a ~1e-5 systematic shrink that an autoregression integrates)
-  if (!exact && ctx->opt[AOM_OPT_GEMM_PATH] == AOM_GEMM_TCGEN05) {
+  if (!exact && ctx->opt[AOM_OPT_GEMM_PATH] != AOM_GEMM_SIMT) {
     // column tile: the wide one when it saves CTA waves (two CTAs per SM)
     const long long slots = 2LL * ctx->num_sms, rows = (M + GTC_BM - 1) / GTC_BM;
     auto waves = [&](int bn) { return (double)((rows * ((ldc + bn - 1) / bn) * batch + slots - 1) / slots) * bn; };
@@ -546,6 +572,32 @@ static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long
     else gemm_tn_kernel<1><<<grid, 256, 0, st>>>(p);
   }
   KCHECK();
+  return AOM_OK;
+}
+
+// out[E][ldo] = X[E][ldx] . OP^T with the operator's digit planes (table id `op`): exact integer accumulation, one
+// rounding to float32 -- the oracle's float64 evaluation of the controller products (oracle/loop.py)
+static int launch_oz_product(aom_ctx* ctx, int op, const float* X, int ldx, int K, float* out, int ldo, int N, int integrator,
+                             float* com, int ldcom, cudaStream_t st) {
+  const aom_config& c = ctx->cfg;
+  const int KB = ctx->ozop_kb[op], NT = ctx->ozop_nt[op], MT = (c.n_env + OZ_BM - 1) / OZ_BM;
+  const size_t need = (size_t)MT * KB * OZ_SLICES * OZ_A_TILE;
+  if (need > ctx->oz_xs_bytes) {
+    cudaFree(ctx->oz_xs); ctx->oz_xs = nullptr; ctx->oz_xs_bytes = 0;
+    CU(cudaMalloc((void**)&ctx->oz_xs, need));
+    CU(cudaMemset(ctx->oz_xs, 0, need));
+    ctx->oz_xs_bytes = need;
+  }
+  if (!ctx->oz_xev) CU(dalloc(&ctx->oz_xev, (size_t)c.n_env));
+  OzSliceParams sl;
+  sl.X = X; sl.ld = ldx; sl.K = K; sl.E = c.n_env; sl.KB = KB; sl.Zs = ctx->oz_xs; sl.ev = ctx->oz_xev;
+  OzGemmParams m;
+  memset(&m, 0, sizeof(m));
+  m.Zs = ctx->oz_xs; m.ABs = ctx->ozop[op]; m.ev = ctx->oz_xev; m.ea = ctx->ozop_ea[op]; m.out = out; m.ldo = ldo;
+  m.E = c.n_env; m.N = N; m.KB = KB; m.com = com; m.ldcom = ldcom; m.gain = ctx->gain; m.closed = ctx->closed; m.err = ctx->d_err;
+  cudaError_t le = oz_product_launch(sl, m, integrator, MT, NT, st);
+  if (le != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "oz_product_launch: %s", cudaGetErrorString(le));
+  ctx->launches += 2;
   return AOM_OK;
 }
 
@@ -1358,6 +1410,9 @@ extern "C" int aom_do_control(aom_ctx* ctx, void* stream) {
   if (!ctx) return AOM_ERR_INVALID;
   const aom_config& c = ctx->cfg;
   NEED(AOM_T_CMAT, 0);
+  if (ctx->opt[AOM_OPT_GEMM_PATH] == AOM_GEMM_TCGEN05 && ctx->ozop[AOM_T_CMAT])
+    return launch_oz_product(ctx, AOM_T_CMAT, ctx->slopes, ctx->lds, c.nslopes, ctx->err_v, ctx->lda, c.nactu, 1, ctx->com,
+                             ctx->lda, (cudaStream_t)stream);
   return launch_gemm(ctx, 1, ctx->slopes, ctx->lds, 0, (const float*)ctx->tab[AOM_T_CMAT][0], ctx->lds, 0, ctx->err_v,
                      ctx->lda, 0, c.n_env, c.nactu, c.nslopes, nullptr, 0, 0, 1, (cudaStream_t)stream, ctx->com, ctx->lda);
 }
@@ -1398,7 +1453,7 @@ extern "C" int aom_set_option(aom_ctx* ctx, int option, int value) {
   if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_MMA_STAGED_FAST))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_WFS_PATH: value %d out of range", value);
   if (option == AOM_OPT_TIME_WFS) ctx->wev_n = 0;
-  if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_SIMT))
+  if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_TF32))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_GEMM_PATH: value %d out of range", value);
   ctx->opt[option] = value;
   return AOM_OK;
@@ -1447,6 +1502,8 @@ extern "C" int aom_reset_dm(aom_ctx* ctx, void* stream) {
 static int project_v2m(aom_ctx* ctx, const float* v, float* out, cudaStream_t st) {
   const aom_config& c = ctx->cfg;
   NEED(AOM_T_V2M, 0);
+  if (ctx->opt[AOM_OPT_GEMM_PATH] == AOM_GEMM_TCGEN05 && ctx->ozop[AOM_T_V2M])
+    return launch_oz_product(ctx, AOM_T_V2M, v, ctx->lda, c.nactu, out, ctx->ldm, c.nmodes, 0, nullptr, 0, st);
   return launch_gemm(ctx, 0, v, ctx->lda, 0, (const float*)ctx->tab[AOM_T_V2M][0], ctx->lda, 0, out, ctx->ldm, 0, c.n_env,
                      c.nmodes, c.nactu, nullptr, 0, 0, 1, st);
 }
@@ -1465,6 +1522,8 @@ extern "C" int aom_rl_control(aom_ctx* ctx, const float* daction, void* stream) 
                                              (const float*)ctx->tab[AOM_T_FREEDOM][0], c.action_dim, c.n_env,
                                              c.env_act_scale, c.env_act_bias);
   KCHECK();
+  if (ctx->opt[AOM_OPT_GEMM_PATH] == AOM_GEMM_TCGEN05 && ctx->ozop[AOM_T_M2V])
+    return launch_oz_product(ctx, AOM_T_M2V, ctx->modes, ctx->ldm, c.nmodes, ctx->com, ctx->lda, c.nactu, 0, nullptr, 0, st);
   return launch_gemm(ctx, 0, ctx->modes, ctx->ldm, 0, (const float*)ctx->tab[AOM_T_M2V][0], ctx->ldm, 0, ctx->com, ctx->lda, 0,
                      c.n_env, c.nactu, c.nmodes, nullptr, 0, 0, 1, st);
 }

@@ -4,17 +4,34 @@
 #include <string.h>
 #include "extrude_i8_host.h"
 
-cudaError_t oz_extrude_launch(const OzGatherParams& g, const OzGemmParams& m, int MT, int NT, cudaStream_t st) {
+static cudaError_t oz_attrs() {
   static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  oz_gather_slice_kernel<<<g.E, 256, (size_t)g.KB * OZ_BK * sizeof(double), st>>>(g);
-  cudaError_t e = cudaGetLastError();
+  if (attr_set) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(oz_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  attr_set = e == cudaSuccess;
+  return e;
+}
+
+cudaError_t oz_extrude_launch(const OzGatherParams& g, const OzGemmParams& m, int MT, int NT, cudaStream_t st) {
+  cudaError_t e = oz_attrs();
   if (e != cudaSuccess) return e;
-  oz_gemm_kernel<<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
+  oz_gather_slice_kernel<<<g.E, 256, (size_t)g.KB * OZ_BK * sizeof(double), st>>>(g);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  oz_gemm_kernel<0><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
+  return cudaGetLastError();
+}
+
+cudaError_t oz_product_launch(const OzSliceParams& sl, const OzGemmParams& m, int integrator, int MT, int NT, cudaStream_t st) {
+  cudaError_t e = oz_attrs();
+  if (e != cudaSuccess) return e;
+  oz_slice_rows_kernel<<<sl.E, 256, 0, st>>>(sl);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (integrator) oz_gemm_kernel<2><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
+  else oz_gemm_kernel<1><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
   return cudaGetLastError();
 }
 

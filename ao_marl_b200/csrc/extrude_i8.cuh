@@ -64,10 +64,18 @@ struct OzGemmParams {
   const uint8_t* ABs;       // [NT][KB][OZ_SLICES_B][OZ_B_TILE]
   const int* ev;            // [E]
   const int* ea;            // [NT * OZ_BN]
-  const float* zref;        // [E]
-  float* out; int ldo;      // [E][ldo] new column, zref included
+  const float* zref;        // [E]  (extrusion epilogue)
+  float* out; int ldo;      // [E][ldo]
   int E, N, KB;
+  float* com; int ldcom;    // integrator epilogue: com += gain * out when closed
+  float gain; int closed;
   int* err;
+};
+
+// digit planes of a per-environment float32 matrix X [E][ld] (K valid columns): the A operand of oz_gemm_kernel
+struct OzSliceParams {
+  const float* X; int ld, K, E, KB;
+  uint8_t* Zs; int* ev;
 };
 
 // element (row r, k) of a [rows x 32] int8 tile: 8-row x 16-byte core matrices, 128 B between the two k halves,
@@ -85,6 +93,18 @@ __host__ __device__ __forceinline__ void oz_digits(double x, double scale, int (
     const double r = rint(t);
     q[s] = (int)r;
     t = (t - r) * 128.0;
+  }
+}
+
+// the same digits of a float32 value: every step is exact in float32 (the remainders only lose leading bits)
+template <int NS>
+__host__ __device__ __forceinline__ void oz_digits_f32(float x, float scale, int (&q)[NS]) {
+  float t = x * scale * 64.0f;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const float r = rintf(t);
+    q[s] = (int)r;
+    t = (t - r) * 128.0f;
   }
 }
 
@@ -174,6 +194,57 @@ __global__ void __launch_bounds__(256) oz_gather_slice_kernel(OzGatherParams p) 
   }
 }
 
+// grid: E blocks of 256 threads.  Row scale + digit planes of one environment's input vector (slopes, commands, modes).
+__global__ void __launch_bounds__(256) oz_slice_rows_kernel(OzSliceParams p) {
+  __shared__ float s_red[8];
+  const int e = blockIdx.x, Kp = p.KB * OZ_BK;
+  const float* x = p.X + (size_t)e * p.ld;
+  float amax = 0.f;
+  for (int k = threadIdx.x; k < p.K; k += blockDim.x) amax = fmaxf(amax, fabsf(x[k]));
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, s));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) amax = fmaxf(amax, s_red[i]);
+  const int ex = oz_exponent((double)amax);
+  if (threadIdx.x == 0) p.ev[e] = ex;
+  const float scale = __int_as_float((127 - ex) << 23);          // 2^-ex
+  const int mt = e >> 7, r = e & 127;
+  for (int j = threadIdx.x; j < Kp / 16; j += blockDim.x) {
+    uint32_t w[OZ_SLICES][4];
+#pragma unroll
+    for (int s = 0; s < OZ_SLICES; ++s)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[s][i] = 0u;
+    // rows are padded to a multiple of 16 floats: whole 16-float groups can be read; columns >= K count as zeros
+    float v[16];
+    if (16 * j + 16 <= p.ld) {
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const float4 f = *reinterpret_cast<const float4*>(x + 16 * j + 4 * i4);
+        v[4 * i4] = f.x; v[4 * i4 + 1] = f.y; v[4 * i4 + 2] = f.z; v[4 * i4 + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int q[OZ_SLICES];
+      oz_digits_f32<OZ_SLICES>((16 * j + i < p.K) ? v[i] : 0.f, scale, q);
+#pragma unroll
+      for (int s = 0; s < OZ_SLICES; ++s) w[s][i >> 2] |= ((uint32_t)q[s] & 0xffu) << (8 * (i & 3));
+    }
+    const int kb = j >> 1;
+    uint8_t* base = p.Zs + ((size_t)(mt * p.KB + kb) * OZ_SLICES) * OZ_A_TILE + oz_tile_offset(r, (j & 1) * 16);
+#pragma unroll
+    for (int s = 0; s < OZ_SLICES; ++s)
+      *reinterpret_cast<uint4*>(base + (size_t)s * OZ_A_TILE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+  }
+}
+
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
@@ -219,6 +290,9 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
 //   warp 0  lane 0: two bulk copies per stage (24 KB of environment digits, 15 KB of operator digits)
 //   warp 1  TMEM allocation; lane 0 issues the 21 digit-pair MMAs of every stage
 //   warps 2-5  epilogue: TMEM lane quarter warp % 4 -> 32 environments, five int32 accumulators -> float64 -> float32
+// EPI 0: screen extrusion (+ zref, every column of the row written)   1: plain product (pad columns zero)
+// EPI 2: least-squares integrator: out = -product, com += gain * out when the loop is closed (rtcCompass.py:527-547)
+template <int EPI>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) {
   extern __shared__ __align__(1024) uint8_t oz_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -291,7 +365,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) 
     const int e = mt * OZ_BM + 32 * q + lane;
     const bool live = e < p.E;
     const int ev = live ? p.ev[e] : 0;
-    const double zr = live ? (double)p.zref[e] : 0.0;
+    const double zr = (EPI == 0 && live) ? (double)p.zref[e] : 0.0;
 #pragma unroll 1
     for (int cb = 0; cb < OZ_BN / 8; ++cb) {
       uint32_t v[OZ_LEVELS][8];
@@ -317,19 +391,31 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) 
           acc = fma(acc, 0.0078125, (double)(int)v[0][j]);
           const int ex = ev + p.ea[n] - 12;
           const double sc = __longlong_as_double((long long)(1023 + ex) << 52);
-          o[j] = (float)fma(acc, sc, zr);
+          if (EPI == 0) o[j] = (float)fma(acc, sc, zr);        // pad columns get zref: harmless, the scatter reads n < N
+          else {
+            const float r = (float)(acc * sc);
+            o[j] = (n < p.N) ? (EPI == 2 ? -r : r) : 0.f;       // pad columns stay zero
+          }
         }
         const int n0 = nt * OZ_BN + cb * 8;
         float* dst = p.out + (size_t)e * p.ldo + n0;
         if (n0 + 8 <= p.ldo) {
-          // pad columns (n >= N) of the row receive the zero products of the zero operator rows (+ zref): harmless,
-          // the scatter reads n < N only
           *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          if (EPI == 2 && p.closed) {
+            float4* cp = reinterpret_cast<float4*>(p.com + (size_t)e * p.ldcom + n0);
+            float4 c0 = cp[0], c1 = cp[1];
+            c0.x = fmaf(p.gain, o[0], c0.x); c0.y = fmaf(p.gain, o[1], c0.y); c0.z = fmaf(p.gain, o[2], c0.z); c0.w = fmaf(p.gain, o[3], c0.w);
+            c1.x = fmaf(p.gain, o[4], c1.x); c1.y = fmaf(p.gain, o[5], c1.y); c1.z = fmaf(p.gain, o[6], c1.z); c1.w = fmaf(p.gain, o[7], c1.w);
+            cp[0] = c0; cp[1] = c1;
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (n0 + j < p.ldo) dst[j] = o[j];
+            if (n0 + j < p.ldo) {
+              dst[j] = o[j];
+              if (EPI == 2 && p.closed) p.com[(size_t)e * p.ldcom + n0 + j] = fmaf(p.gain, o[j], p.com[(size_t)e * p.ldcom + n0 + j]);
+            }
         }
       }
     }

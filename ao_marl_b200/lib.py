@@ -299,7 +299,7 @@ class Simulator:
         """Contraction behind the screen extrusion: 'i8' (default: exact integer digits on tcgen05) or 'ffma' (float32)."""
         self._check(self.lib.aom_set_option(self._ctx, O["EXTRUDE_PATH"], {"i8": 0, "ffma": 1}[name]), "aom_set_option")
 
-    GEMM_PATHS = {"tcgen05": 0, "simt": 1}
+    GEMM_PATHS = {"tcgen05": 0, "simt": 1, "tf32": 2}
 
     def set_gemm_path(self, name):
         """Select the GEMM kernel of the env-batched contractions: 'tcgen05' (default) or 'simt'."""

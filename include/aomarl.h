@@ -188,8 +188,12 @@ enum {
 };
 
 enum {
-  AOM_GEMM_TCGEN05 = 0,    /* tcgen05 / TMEM, three TF32 MMAs per product (fp32-grade; default) */
-  AOM_GEMM_SIMT = 1        /* float32 FFMA tiles (cross-check path) */
+  AOM_GEMM_TCGEN05 = 0,    /* tensor cores (default): the controller's operator products (cmat, v2m, m2v) as exact integer
+                              contractions (int8 digit planes on tcgen05 kind::i8, int32 accumulators, one rounding:
+                              extrude_i8.cuh); the actors and everything else as three TF32 MMAs per product */
+  AOM_GEMM_SIMT = 1,       /* float32 FFMA tiles (cross-check path) */
+  AOM_GEMM_TF32 = 2        /* three TF32 MMAs per product everywhere (round-1 path: the tensor core truncates its float32
+                              accumulator, ~3e-5 on K = 2400; comparison path) */
 };
 
 /* lifetime */
