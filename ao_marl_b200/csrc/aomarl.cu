@@ -36,6 +36,7 @@ struct aom_ctx {
   int* ox[AOM_MAX_LAYERS];
   int* oy[AOM_MAX_LAYERS];
   uint32_t* ext_count[AOM_MAX_LAYERS];
+  float* amp_env[AOM_MAX_LAYERS];     // optional per-environment innovation amplitude (aom_set_layer_amp)
   double accx[AOM_MAX_LAYERS], accy[AOM_MAX_LAYERS];
   uint32_t *k0, *k1;
   float *Z, *zref, *newcol;
@@ -59,7 +60,7 @@ struct aom_ctx {
   float *slopes_frame, *slopes, *err_v, *com, *com1, *volts, *com_before;
   float *bincube, *phase;
   const float* cube_override;
-  double* tar_mom;            // [E][5] pupil sums of the target phase (aom_comp_strehl)
+  double* tar_mom;            // [2][E][5] pupil sums of the target phase (aom_comp_strehl): main target, geometric one
   float* tar_acc;             // [E][2] running sums for the long-exposure figures
   int tar_n;
   // geometric controller (geo_kernels.cuh), allocated on first use
@@ -208,7 +209,7 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
   CU(dalloc(&ctx->volts, E * ctx->lda));
   CU(dalloc(&ctx->com_before, E * ctx->lda));
   CU(dalloc(&ctx->strehl, E * 4));
-  CU(dalloc(&ctx->tar_mom, E * 5));
+  CU(dalloc(&ctx->tar_mom, E * 10));     // main target, then the geometric controller's
   CU(dalloc(&ctx->tar_acc, E * 2));
   if (cfg->nmodes > 0) {
     CU(dalloc(&ctx->modes, E * ctx->ldm));
@@ -255,6 +256,7 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
     for (int l = 0; l < AOM_MAX_LAYERS; ++l) cudaFree(ctx->tab[t][l]);
   for (int l = 0; l < AOM_MAX_LAYERS; ++l) {
     cudaFree(ctx->screen[l]); cudaFree(ctx->ox[l]); cudaFree(ctx->oy[l]); cudaFree(ctx->ext_count[l]);
+    cudaFree(ctx->amp_env[l]);
   }
   void* bufs[] = {ctx->k0, ctx->k1, ctx->Z, ctx->zref, ctx->newcol, ctx->slopes_frame, ctx->slopes, ctx->err_v,
                   ctx->com, ctx->com1, ctx->volts, ctx->com_before, ctx->bincube, ctx->phase, ctx->modes,
@@ -616,7 +618,7 @@ static int extrude_once(aom_ctx* ctx, int l, int axis, int sign, cudaStream_t st
   p.screen = ctx->screen[l]; p.ox = ctx->ox[l]; p.oy = ctx->oy[l]; p.count = ctx->ext_count[l];
   p.k0 = ctx->k0; p.k1 = ctx->k1; p.stencil = (const int*)ctx->tab[AOM_T_STENCIL][l];
   p.N = c.screen_dim[l]; p.S = c.stencil_size[l]; p.E = c.n_env; p.layer = l; p.axis = axis; p.sign = sign;
-  p.amp = c.amp[l];
+  p.amp = c.amp[l]; p.amp_env = ctx->amp_env[l];
   p.ldz = AOM_LD(p.S + p.N); p.Z = ctx->Z; p.zref = ctx->zref; p.ldn = AOM_LD(p.N); p.newcol = ctx->newcol;
   if (ctx->opt[AOM_OPT_EXTRUDE_PATH] == AOM_EXTRUDE_I8) {
     // exact integer contraction on tcgen05 (extrude_i8.cuh): digits of the inputs, 13 int8 digit-pair products with
@@ -633,7 +635,7 @@ static int extrude_once(aom_ctx* ctx, int l, int axis, int sign, cudaStream_t st
     OzGatherParams g;
     g.screen = p.screen; g.ox = p.ox; g.oy = p.oy; g.count = p.count; g.k0 = p.k0; g.k1 = p.k1; g.stencil = p.stencil;
     g.zref = ctx->zref; g.ev = ctx->oz_ev; g.Zs = ctx->oz_zs; g.N = p.N; g.S = p.S; g.E = p.E; g.KB = KB; g.layer = l;
-    g.axis = axis; g.sign = sign; g.amp = p.amp;
+    g.axis = axis; g.sign = sign; g.amp = p.amp; g.amp_env = ctx->amp_env[l];
     OzGemmParams m;
     m.Zs = ctx->oz_zs; m.ABs = ctx->oz_ab[l]; m.ev = ctx->oz_ev; m.ea = ctx->oz_ea[l]; m.zref = ctx->zref;
     m.out = ctx->newcol; m.ldo = p.ldn; m.E = p.E; m.N = p.N; m.KB = KB; m.err = ctx->d_err;
@@ -1281,19 +1283,23 @@ extern "C" int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int acc
     p.volts = ctx->geo_volts;
   }
   int& n_le = geo ? ctx->geo_tar_n : ctx->tar_n;
-  CU(cudaMemsetAsync(ctx->tar_mom, 0, (size_t)c.n_env * 5 * sizeof(double), st));
-  rc = sweep_prepare(ctx, st);
-  if (rc) return rc;
-  if (ctx->sweep_state == 1 && ctx->opt[AOM_OPT_PUPIL_PATH] == AOM_PUPIL_SWEEP) {
-    rc = sweep_launch<1>(ctx, p, nullptr, ctx->tar_mom, st, (float)(2.0 * M_PI / (double)lambda_um));
+  double* mom = ctx->tar_mom + (geo ? (size_t)c.n_env * 5 : 0);
+  if (!(flags & AOM_TAR_PUBLISH)) {
+    CU(cudaMemsetAsync(mom, 0, (size_t)c.n_env * 5 * sizeof(double), st));
+    rc = sweep_prepare(ctx, st);
     if (rc) return rc;
-  } else {
-    dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
-    target_moments_kernel<<<grid, blk, 0, st>>>(p, ctx->tar_mom, (float)(2.0 * M_PI / (double)lambda_um));
-    KCHECK();
+    if (ctx->sweep_state == 1 && ctx->opt[AOM_OPT_PUPIL_PATH] == AOM_PUPIL_SWEEP) {
+      rc = sweep_launch<1>(ctx, p, nullptr, mom, st, (float)(2.0 * M_PI / (double)lambda_um));
+      if (rc) return rc;
+    } else {
+      dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
+      target_moments_kernel<<<grid, blk, 0, st>>>(p, mom, (float)(2.0 * M_PI / (double)lambda_um));
+      KCHECK();
+    }
+    if (flags & AOM_TAR_TRACE) return AOM_OK;        // sums pending until AOM_TAR_PUBLISH
   }
   if (accumulate) n_le += 1;
-  target_strehl_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(ctx->tar_mom, geo ? ctx->strehl_geo : ctx->strehl,
+  target_strehl_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(mom, geo ? ctx->strehl_geo : ctx->strehl,
                                                              geo ? ctx->geo_acc : ctx->tar_acc, c.n_env,
                                                              accumulate ? n_le : 0);
   KCHECK();
@@ -1492,6 +1498,16 @@ extern "C" int aom_set_layer(aom_ctx* ctx, int layer, float deltax, float deltay
   return AOM_OK;
 }
 
+extern "C" int aom_set_layer_amp(aom_ctx* ctx, int layer, const float* amp_host) {
+  if (!ctx) return AOM_ERR_INVALID;
+  if (layer < 0 || layer >= ctx->cfg.n_layers) return fail(ctx, AOM_ERR_INVALID, "layer index out of range");
+  if (!amp_host) { cudaFree(ctx->amp_env[layer]); ctx->amp_env[layer] = nullptr; return AOM_OK; }
+  CU(cudaDeviceSynchronize());                       // an extrusion in flight may still read the old amplitudes
+  if (!ctx->amp_env[layer]) CU(cudaMalloc((void**)&ctx->amp_env[layer], (size_t)ctx->cfg.n_env * sizeof(float)));
+  CU(cudaMemcpy(ctx->amp_env[layer], amp_host, (size_t)ctx->cfg.n_env * sizeof(float), cudaMemcpyHostToDevice));
+  return AOM_OK;
+}
+
 extern "C" int aom_reset_dm(aom_ctx* ctx, void* stream) {
   if (!ctx) return AOM_ERR_INVALID;
   CU(cudaMemsetAsync(ctx->volts, 0, (size_t)ctx->cfg.n_env * ctx->lda * 4, (cudaStream_t)stream));
@@ -1612,7 +1628,7 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   mode &= ~AOM_STEP_ATMOS_DONE;
   // with the per-frame Strehl the target sweep reads the screens of the previous frame after apply_control, so the
   // turbulence update cannot run ahead of it: no fork, no caller-side update
-  const bool strehl = ctx->opt[AOM_OPT_STREHL] != 0;
+  const int strehl = ctx->opt[AOM_OPT_STREHL];
   if (strehl && atmos_done)
     return fail(ctx, AOM_ERR_STATE, "AOM_OPT_STREHL needs the screens of the previous frame: do not combine with AOM_STEP_ATMOS_DONE");
   const bool fork = ctx->cfg.n_layers > 0 && ctx->seeded && !atmos_done && !strehl;
@@ -1625,13 +1641,13 @@ extern "C" int aom_step(aom_ctx* ctx, int mode, int eval_mode, void* stream) {
   // rl half-step: TrainerRPC.env_step -> AoEnv.rl_step -> RlSupervisor.next_part_two (rlSupervisor.py:900-947)
   if (mode == 0) { rc = aom_actor_forward(ctx, eval_mode, stream); if (rc) return rc; }
   if (mode != 2) { rc = aom_rl_control(ctx, nullptr, stream); if (rc) return rc; }
+  // next_part_two: target.comp_tar_image + comp_strehl (rlSupervisor.py:936-947).  The atmosphere is still the one of
+  // the previous frame; the mirrors carry the voltages the target was traced with in next_part_one (option value 1:
+  // before apply_control) or, with "pure delay 0", the new ones (value 2: re-traced after apply_control)
+  const int nm = ctx->opt[AOM_OPT_STREHL_LAMBDA_NM] > 0 ? ctx->opt[AOM_OPT_STREHL_LAMBDA_NM] : 1650;
+  if (strehl == 1) { rc = aom_comp_strehl(ctx, 3, (float)nm * 1e-3f, 1, stream); if (rc) return rc; }
   rc = aom_apply_control(ctx, 1, stream); if (rc) return rc;
-  if (strehl) {
-    // next_part_two: target.comp_tar_image + comp_strehl right after apply_control (rlSupervisor.py:936-947): the
-    // mirrors carry the new voltages, the atmosphere is still the one of the previous frame
-    const int nm = ctx->opt[AOM_OPT_STREHL_LAMBDA_NM] > 0 ? ctx->opt[AOM_OPT_STREHL_LAMBDA_NM] : 1650;
-    rc = aom_comp_strehl(ctx, 3, (float)nm * 1e-3f, 1, stream); if (rc) return rc;
-  }
+  if (strehl >= 2) { rc = aom_comp_strehl(ctx, 3, (float)nm * 1e-3f, 1, stream); if (rc) return rc; }
   if (ctx->reward) { rc = aom_reward(ctx, ctx->cfg.reward_factor, stream); if (rc) return rc; }
   // linear half-step: AoEnv.linear_step -> RlSupervisor.next_part_one (rlSupervisor.py:1015-1051)
   rc = aom_state_begin(ctx, stream); if (rc) return rc;

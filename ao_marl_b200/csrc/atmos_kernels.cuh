@@ -24,6 +24,7 @@ struct ExtrudeParams {
   float* newcol; int ldn; // [E][ldn]
   int N, S, E, layer, axis, sign;
   float amp;
+  const float* amp_env;   // [E] per-environment amplitude, or null
 };
 
 __device__ __forceinline__ void extr_logical(int r, int c, int N, int axis, int sign, int& lr, int& lc) {
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) extrude_gather_kernel(ExtrudeParams p) {
     Z[k] = scr[(size_t)wrapN(lr + oy, N) * N + wrapN(lc + ox, N)] - zr;
   }
   const uint32_t cnt = p.count[e], k0 = p.k0[e], k1 = p.k1[e];
+  const float amp = p.amp_env ? p.amp_env[e] : p.amp;
   for (int b = threadIdx.x; 4 * b < N; b += blockDim.x) {
     const aom_u4 w = aom_philox((uint32_t)b, cnt, AOM_TAG_ATMOS, (uint32_t)p.layer, k0, k1);
     float z[4];
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256) extrude_gather_kernel(ExtrudeParams p) {
     aom_normal_pair(w.z, w.w, z[2], z[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (4 * b + i < N) Z[p.S + 4 * b + i] = aom_mul(z[i], p.amp);
+      if (4 * b + i < N) Z[p.S + 4 * b + i] = aom_mul(z[i], amp);
   }
   for (int k = p.S + N + threadIdx.x; k < p.ldz; k += blockDim.x) Z[k] = 0.f;
 }

@@ -57,6 +57,7 @@ struct OzGatherParams {
   uint8_t* Zs;              // [MT][KB][OZ_SLICES][OZ_A_TILE] digit planes, canonical tile layout
   int N, S, E, KB, layer, axis, sign;
   float amp;
+  const float* amp_env;     // [E] per-environment amplitude, or null
 };
 
 struct OzGemmParams {
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(256) oz_gather_slice_kernel(OzGatherParams p) 
     amax = fmax(amax, fabs(v));
   }
   const uint32_t cnt = p.count[e], k0 = p.k0[e], k1 = p.k1[e];
+  const float amp = p.amp_env ? p.amp_env[e] : p.amp;
   for (int b = threadIdx.x; 4 * b < N; b += blockDim.x) {
     const aom_u4 w = aom_philox((uint32_t)b, cnt, AOM_TAG_ATMOS, (uint32_t)p.layer, k0, k1);
     float z[4];
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(256) oz_gather_slice_kernel(OzGatherParams p) 
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (4 * b + i < N) {
-        const double v = (double)z[i] * (double)p.amp;
+        const double v = (double)z[i] * (double)amp;
         oz_v[p.S + 4 * b + i] = v;
         amax = fmax(amax, fabs(v));
       }

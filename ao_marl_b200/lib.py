@@ -51,7 +51,7 @@ OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH", 
 O = {name: i for i, name in enumerate(OPTIONS)}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
-           "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_wfs_time_ms", "aom_raytrace_wfs",
+           "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_set_layer_amp", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_wfs_time_ms", "aom_raytrace_wfs",
            "aom_comp_strehl", "aom_reset_strehl", "aom_do_control_geo", "aom_apply_control_geo", "aom_denoise", "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
            "aom_set_gain", "aom_set_loop", "aom_reset_dm", "aom_set_dm_volts", "aom_rl_control",
            "aom_state_begin", "aom_state_end", "aom_reward", "aom_actor_forward", "aom_step", "aom_gemm_tn",
@@ -89,6 +89,7 @@ def load_library():
     lib.aom_reset.argtypes = [vp, vp, vp]
     lib.aom_move_atmos.argtypes = [vp, vp]
     lib.aom_set_layer.argtypes = [vp, i32, f32, f32, f32]
+    lib.aom_set_layer_amp.argtypes = [vp, i32, vp]
     lib.aom_comp_wfs_image.argtypes = [vp, i32, f32, vp]
     lib.aom_raytrace_wfs.argtypes = [vp, i32, vp]
     lib.aom_wfs_time_ms.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32)]
@@ -370,6 +371,14 @@ class Simulator:
         self._check(self.lib.aom_set_layer(self._ctx, int(layer), float(deltax), float(deltay), float(amp)),
                     "aom_set_layer")
 
+    def set_layer_amp(self, layer, amp):
+        """Innovation amplitude of one layer per environment (float [E]); None restores the common amplitude."""
+        if amp is None:
+            self._check(self.lib.aom_set_layer_amp(self._ctx, int(layer), None), "aom_set_layer_amp")
+            return
+        amp = np.ascontiguousarray(np.broadcast_to(np.asarray(amp, dtype=np.float32), (self.n_env,)))
+        self._check(self.lib.aom_set_layer_amp(self._ctx, int(layer), amp.ctypes.data_as(ctypes.c_void_p)), "aom_set_layer_amp")
+
     def comp_wfs_image(self, atmos=True, dms=True, keep_image=False, noise=None):
         flags = (1 if atmos else 0) | (2 if dms else 0) | (4 if keep_image else 0)
         noise = float(self.cfg.noise if noise is None else noise)
@@ -380,10 +389,11 @@ class Simulator:
         self._check(self.lib.aom_raytrace_wfs(self._ctx, flags, self.stream), "aom_raytrace_wfs")
         return self.buffer("PHASE").view(self.n_env, self.cfg.n, self.cfg.n)
 
-    def comp_strehl(self, lambda_um, atmos=True, dms=True, accumulate=True, geo=False):
+    def comp_strehl(self, lambda_um, atmos=True, dms=True, accumulate=True, geo=False, phase="both"):
         """Pupil phase variance -> AOM_B_STREHL [E, 4] = (SE, LE, variance, mean variance); geo=True: the target
-        behind the geometric controller's mirrors (AOM_B_STREHL_GEO)."""
-        flags = (1 if atmos else 0) | (2 if dms else 0) | (0x100 if geo else 0)
+        behind the geometric controller's mirrors (AOM_B_STREHL_GEO).  phase: "both" (trace now and publish), "trace"
+        (TargetCompass.raytrace: sweep now, keep pending) or "publish" (comp_tar_image / comp_strehl on the pending sums)."""
+        flags = (1 if atmos else 0) | (2 if dms else 0) | (0x100 if geo else 0) | {"both": 0, "trace": 0x200, "publish": 0x400}[phase]
         self._check(self.lib.aom_comp_strehl(self._ctx, flags, float(lambda_um), 1 if accumulate else 0, self.stream),
                     "aom_comp_strehl")
         return self.buffer("STREHL_GEO" if geo else "STREHL").view(self.n_env, 4)
@@ -416,11 +426,12 @@ class Simulator:
         """aom_step keeps every frame's detector cube in AOM_B_BINCUBE (AOM_OPT_KEEP_IMAGE)."""
         self._check(self.lib.aom_set_option(self._ctx, O["KEEP_IMAGE"], 1 if on else 0), "aom_set_option")
 
-    def step_with_strehl(self, on=True, lambda_um=1.65):
+    def step_with_strehl(self, on=True, lambda_um=1.65, pure_delay_0=False):
         """aom_step evaluates the target Strehl every frame, as the reference's next_part_two does by default
-        (compute_tar_psf=True, rlSupervisor.py:944-947)."""
+        (compute_tar_psf=True, rlSupervisor.py:944-947): with the voltages the target was traced with in next_part_one, or
+        (pure_delay_0, the reference's modification_online) re-traced after apply_control."""
         self._check(self.lib.aom_set_option(self._ctx, O["STREHL_LAMBDA_NM"], int(round(lambda_um * 1000))), "aom_set_option")
-        self._check(self.lib.aom_set_option(self._ctx, O["STREHL"], 1 if on else 0), "aom_set_option")
+        self._check(self.lib.aom_set_option(self._ctx, O["STREHL"], (2 if pure_delay_0 else 1) if on else 0), "aom_set_option")
 
     def step_with_geo(self, on=True):
         """aom_step also runs the geometric controller every frame (AOM_OPT_GEO)."""

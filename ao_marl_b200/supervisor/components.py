@@ -44,16 +44,27 @@ class AtmosB200(_Base):
         so that E == 1 reproduces the reference's single stream) or an int64 array [E]."""
         self._sim.reset(self._sim.env_seeds(seed))
 
-    def _amp(self, layer):
+    def _amp(self, layer, r0=None):
         a = self._config.p_atmos
-        r0_px = a.r0 / (a.frac[layer] ** (3.0 / 5.0) * a.pupixsize)
-        return float(np.float32(np.float32(r0_px) ** np.float32(-5.0 / 6.0) * np.float32(0.5 / (2 * np.pi))))
+        r0_px = (a.r0 if r0 is None else np.asarray(r0, dtype=np.float64)) / (a.frac[layer] ** (3.0 / 5.0) * a.pupixsize)
+        amp = np.float32(r0_px) ** np.float32(-5.0 / 6.0) * np.float32(0.5 / (2 * np.pi))
+        return float(np.float32(amp)) if np.ndim(amp) == 0 else np.asarray(amp, dtype=np.float32)
 
     def set_r0(self, r0, *, reset_seed=-1):
-        self._config.p_atmos.r0 = r0
+        """atmosCompass.py:79-101.  `r0` may be a scalar (every environment) or an array [E]: one seeing condition per
+        environment of the batch (the reference changes the r0 of its single simulator at run time, train_rpc.py:429-449)."""
         a = self._config.p_atmos
-        for l in range(a.nscreens):
-            self._sim.set_layer(l, a._deltax[l], a._deltay[l], self._amp(l))
+        if np.ndim(r0) == 0:
+            a.r0 = float(r0)
+            for l in range(a.nscreens):
+                self._sim.set_layer(l, a._deltax[l], a._deltay[l], self._amp(l))
+                self._sim.set_layer_amp(l, None)
+        else:
+            r0 = np.asarray(r0, dtype=np.float64)
+            if r0.shape != (self._sim.n_env,):
+                raise ValueError("Dimension mismatch")
+            for l in range(a.nscreens):
+                self._sim.set_layer_amp(l, self._amp(l, r0))
         if reset_seed != -1:
             seed = np.random.randint(int(1e4)) if reset_seed == 0 else reset_seed
             self._sim.reset(self._sim.env_seeds(1234 + seed))
@@ -315,10 +326,16 @@ class TargetB200(_Base):
     frames; the 2048^2 image of comp_tar_image is not computed.  One sweep kernel (aom_comp_strehl) evaluates the on-axis
     phase per pupil pixel and reduces it without materialising it; the figures live in AOM_B_STREHL."""
 
-    def __init__(self, sim, config, tables):
+    def __init__(self, sim, config, tables, eager_trace=False):
         super().__init__(sim, config)
         self._tables = tables
         self._flags = {}
+        # eager_trace: raytrace() sweeps the pupil at once, as sutra does, so that a Strehl published later refers to the
+        # mirrors of the moment of the trace (the reference's ordering when apply_control falls between
+        # next_part_one's target trace and next_part_two's comp_strehl).  Default: the sweep runs when the image is asked
+        # for -- one sweep per frame instead of one per trace, equal to the reference's "pure delay 0" ordering.
+        self.eager_trace = bool(eager_trace)
+        self._pending = set()
         # target i looks through the mirrors of the geometric controller when its dms are that controller's
         # (parameter layout "geo": target 1 <-> DMs [1, 3] <-> controller 1)
         geo = next((c for c in config.p_controllers if getattr(c, "type", "") == "geo"), None)
@@ -336,11 +353,16 @@ class TargetB200(_Base):
         if dms is not None:
             d = True
         self._flags[index] = (a, d)
+        if self.eager_trace:
+            lam = float(self._config.p_targets[index].Lambda)
+            self._sim.comp_strehl(lam, atmos=a, dms=d, geo=self._is_geo(index), phase="trace")
+            self._pending.add(index)
 
     def comp_tar_image(self, tarNum, *, puponly=0, compLE=True):
         lam = float(self._config.p_targets[tarNum].Lambda)
         a, d = self._flags.get(tarNum, (False, False))
-        self._sim.comp_strehl(lam, atmos=a, dms=d, accumulate=bool(compLE), geo=self._is_geo(tarNum))
+        phase = "publish" if (self.eager_trace and tarNum in self._pending) else "both"
+        self._sim.comp_strehl(lam, atmos=a, dms=d, accumulate=bool(compLE), geo=self._is_geo(tarNum), phase=phase)
 
     def comp_strehl(self, tarNum, *, do_fit=True):
         pass

@@ -44,9 +44,9 @@ class RlSupervisor:
         self.n_modes_start_end = env_rl["n_zernike_start_end"]
         self.n_reverse_filtered_from_cmat = env_rl["n_reverse_filtered_from_cmat"]
         self.include_tip_tilt = env_rl["include_tip_tilt"]
-        self.pure_delay_0 = env_rl["modification_online"]
-        if self.pure_delay_0:
-            raise NotImplementedError("modification_online (pure delay 0 re-trace of the target) is not implemented")
+        # modification_online ("pure delay 0", rlSupervisor.py:936-940): the target is re-traced right after apply_control,
+        # so the published Strehl already contains the new command; DelayedMDP shortens its window accordingly
+        self.pure_delay_0 = bool(env_rl["modification_online"])
         self.autoencoder = autoencoder
         self.freedom_vector_actuator_space = None
         self.initial_seed = initial_seed
@@ -83,7 +83,9 @@ class RlSupervisor:
         self.tel = TelescopeB200(self.sim, config)
         self.atmos = AtmosB200(self.sim, config)
         self.dms = DmB200(self.sim, config, int(ctrl.ndm[0]), int(ctrl.ndm[1]))
-        self.target = TargetB200(self.sim, config, t)
+        # faithful ordering of the target trace: without pure delay 0 the Strehl of next_part_two refers to the mirrors of
+        # the trace in next_part_one (eager sweep at raytrace); with it the sweep after apply_control is the reference's own
+        self.target = TargetB200(self.sim, config, t, eager_trace=not self.pure_delay_0)
         self.wfs = WfsB200(self.sim, config, t.wfs_index)
         self.rtc = RtcB200(self.sim, config, t)
         self.basis = _Basis(t)
@@ -166,9 +168,26 @@ class RlSupervisor:
             self.rl_control(action, 0, evaluation_rl_full_action)
         if apply_control:
             self.rtc.apply_control(0)
+            if self.pure_delay_0:
+                self.raytrace_target(0)
         if compute_tar_psf:
             self.target.comp_tar_image(0)
             self.target.comp_strehl(0)
+
+    def generic_delay_0_next(self, *, move_atmos=True, ncontrol=0, tar_trace=None, wfs_trace=None, do_control=True,
+                             apply_control=True, compute_tar_psf=True):
+        """rlSupervisor.py:329-394: the vanilla frame with the target re-traced right after apply_control (used by the
+        reference's dataset dumps, obtain_dataset_autoencoder.py:85-88)."""
+        if move_atmos and self.atmos is not None:
+            self.atmos.move_atmos()
+        self.next_part_one_integrator(ncontrol=ncontrol, do_control=do_control)
+        if apply_control:
+            self.rtc.apply_control(ncontrol)
+            self.raytrace_target(ncontrol)
+        if compute_tar_psf:
+            self.target.comp_tar_image(0)
+            self.target.comp_strehl(0)
+        self.iter += 1
 
     def next_part_one_integrator(self, *, ncontrol=0, do_control=True):
         self.raytrace_target(ncontrol)

@@ -34,7 +34,8 @@ if ROOT not in sys.path:
 
 # DRAM bytes per environment per launch of the sensor kernel from `ncu --set full` (dram__bytes_read.sum +
 # dram__bytes_write.sum of one launch at E = 1024, divided by 1024).  Used for roofline.traffic (scaled to the E of this run).
-NCU_DRAM_BYTES_PER_ENV = {("40x40", "wfs_frame_umma_kernel"): (4.072948e9 + 13.814528e6) / 1024,   # profiles/r02_wfs_umma_v3_E1024_*
+NCU_DRAM_BYTES_PER_ENV = {("40x40_d0_noise", "wfs_frame_umma_kernel"): (4.072948e9 + 13.814528e6) / 1024,
+                          ("40x40", "wfs_frame_umma_kernel"): (4.072948e9 + 13.814528e6) / 1024,   # profiles/r02_wfs_umma_v3_E1024_*
                           ("40x40", "wfs_frame_tma_kernel"): (4.108122e9 + 13.919744e6) / 1024,    # profiles/r01_wfs_tma_E1024_*
                           ("40x40", "wfs_frame_mma_kernel"): (4.062998e9 + 18.132992e6) / 1024}
 
@@ -53,6 +54,12 @@ WORKLOADS = {
                   env_rl=dict(n_zernike_start_end=[0, 1260], window_n_zernike=20, include_tip_tilt_windowed=True,
                               n_reverse_filtered_from_cmat=5, delayed_assignment=2),
                   name="production_sh_40x40_8m_3layers, 43 agents (42x30 modes + TT, window 20), delay 1"),
+    # BASELINE.json config 4: its own parameter file (delay 0, magnitude 9 -> 241 photons per subaperture, 3 e- read
+    # noise, gain 0.3) with the conv autoencoder denoiser in the state path (selected by --denoise)
+    "40x40_d0_noise": dict(par="production_sh_40x40_8m_3layers_d0_noise.py", world_size=44,
+                           env_rl=dict(n_zernike_start_end=[0, 1260], window_n_zernike=20, include_tip_tilt_windowed=True,
+                                       n_reverse_filtered_from_cmat=5, delayed_assignment=1),
+                           name="production_sh_40x40_8m_3layers_d0_noise, 43 agents, delay 0, photon + 3 e- read noise"),
     "10x10": dict(par="production_sh_10x10_2m.py", world_size=3,
                   env_rl=dict(n_zernike_start_end=[0, 80], n_reverse_filtered_from_cmat=5),
                   name="production_sh_10x10_2m, 2 agents (80 modes + TT), delay 1"),
@@ -81,7 +88,10 @@ def parse():
                          "default (compute_tar_psf=True, rlSupervisor.py:944-947); without the flag the figure is still "
                          "reported as a variant beside the headline")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra sections (Strehl variant, learner, reset timing)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.denoise and a.workload == "40x40":
+        a.workload = "40x40_d0_noise"          # config 4 runs on its own parameter file
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -397,7 +407,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from ao_marl_b200.system import build_system
     wl = WORKLOADS[args.workload]
-    E = args.envs or (4096 if args.workload == "40x40" else 1024)
+    E = args.envs or (4096 if args.workload.startswith("40x40") else 1024)
     t_build = time.perf_counter()
     sim, t, rl = build_system(wl["par"], E, env_rl=dict(wl["env_rl"]), world_size=wl["world_size"], seed=0)
     if args.wfs_path:
@@ -494,8 +504,8 @@ def run_ours(args):
         b = i & 1
         act_d.copy_(act_h, non_blocking=True)       # H2D: this step's actions
         main.wait_stream(atmos_stream)              # the turbulence of this step was advanced during the last round trip
-        sim.step(mode=1, atmos_done=i > 0)          # rl half-step + reward + linear half-step
-        if i + 1 < k_e2e:
+        sim.step(mode=1, atmos_done=(i > 0 and not args.strehl))   # rl half-step + reward + linear half-step
+        if i + 1 < k_e2e and not args.strehl:
             # the next step's turbulence does not depend on the actions: it runs on a second stream while the
             # actions make their round trip through the host (the GPU would idle on PCIe and the host sync)
             frame_done.record(main)

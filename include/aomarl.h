@@ -161,7 +161,9 @@ typedef enum aom_option {
   AOM_OPT_KEEP_IMAGE,   /* != 0: aom_step keeps the detector cube of every frame in AOM_B_BINCUBE (d_bincube readers:
                            rlSupervisor.py:884-885, obtain_dataset_autoencoder.py:85-88) */
   AOM_OPT_STREHL,       /* != 0: aom_step evaluates the target Strehl every frame at AOM_OPT_STREHL_LAMBDA_NM, as
-                           next_part_two does with compute_tar_psf=True (rlSupervisor.py:944-947) */
+                           next_part_two does with compute_tar_psf=True (rlSupervisor.py:944-947).  1: the phase as traced
+                           in the previous next_part_one, i.e. before this step's apply_control (the reference's default);
+                           2: re-traced after apply_control (modification_online / "pure delay 0", rlSupervisor.py:936-940) */
   AOM_OPT_STREHL_LAMBDA_NM, /* target wavelength in nanometres for AOM_OPT_STREHL (default 1650) */
   AOM_OPT_EXTRUDE_PATH, /* which contraction serves the screen extrusion (aom_move_atmos / aom_reset) */
   AOM_OPT_COUNT
@@ -219,6 +221,11 @@ int aom_move_atmos(aom_ctx* ctx, void* stream);
  * amplitude of one layer; a sign change of the wind needs no stencil upload (mirroring is index arithmetic). */
 int aom_set_layer(aom_ctx* ctx, int layer, float deltax, float deltay, float amp);
 
+/* AtmosCompass.set_r0 per environment (the reference changes r0 of its single simulator at run time,
+ * train_rpc.py:429-449; a batch can hold one condition per environment): innovation amplitude of `layer` for every
+ * environment, host float [E] (NULL: back to the layer's common amplitude).  The wind stays common to the batch. */
+int aom_set_layer_amp(aom_ctx* ctx, int layer, const float* amp_host);
+
 /* WfsCompass.raytrace + compute_wfs_image fused (wfsCompass.py:334-343, sourceCompass.py:54-85).
  * flags: bit0 atmosphere, bit1 mirrors, bit2 keep image (writes AOM_B_BINCUBE). noise: sensor noise for
  * this frame (pass cfg.noise for the configured value).  Also leaves the centre-of-gravity slopes of the
@@ -245,6 +252,12 @@ int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream);
  * The 2048^2 focal-plane PSF is not computed. */
 #define AOM_TAR_GEO 0x100   /* flags bit: the target behind the geometric controller's mirrors (reads AOM_B_GEO_VOLTS,
                                writes AOM_B_STREHL_GEO) instead of the main ones */
+#define AOM_TAR_TRACE 0x200 /* flags bit: TargetCompass.raytrace only -- sweep the pupil now (current screens and voltages) and
+                               keep the sums pending; nothing is published */
+#define AOM_TAR_PUBLISH 0x400 /* flags bit: comp_tar_image / comp_strehl only -- publish (and accumulate) the pending sums of
+                               the last AOM_TAR_TRACE.  Together they reproduce the reference's ordering when the mirrors
+                               move between the target trace of next_part_one and the Strehl of next_part_two
+                               (rlSupervisor.py:964-965, 944-947; "modification_online" re-traces after apply_control) */
 int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int accumulate, void* stream);
 int aom_reset_strehl(aom_ctx* ctx, void* stream);     /* TargetCompass.reset_strehl */
 

@@ -673,6 +673,51 @@ def test_strehl_kernel_matches_the_materialised_phase(sim10, static10, torch):
     sim10.check_device()
 
 
+def test_strehl_ordering_in_the_fused_step(system10, torch):
+    """AOM_OPT_STREHL inside aom_step: value 1 publishes the phase as traced in the previous next_part_one, i.e. with the
+    voltages that were on the mirrors before this step's apply_control (rlSupervisor.py:964-965 then 944-947); value 2
+    re-traces after apply_control ("modification_online", rlSupervisor.py:936-940).  Checked (a) against the stand-alone
+    call issued right before each step and (b), without atmosphere, through the identity SE2[t] == SE1[t+1]: both see
+    the voltages of step t."""
+    from ao_marl_b200.lib import Simulator
+    sim, t, rl = system10
+    seeds = np.array([7, 8, 9], dtype=np.int64)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    actions = [torch.randn((3, rl.action_dim), device="cuda", generator=g).clamp_(-1, 1) for _ in range(5)]
+
+    def run(s, how, delay0=False):
+        s.reset(seeds)
+        s.reset_strehl()
+        s.step_with_strehl(how == "fused", 1.65, pure_delay_0=delay0)
+        s.state_begin(); s.move_atmos(); s.comp_wfs_image(); s.do_centroids(); s.do_control(); s.state_end()
+        out = []
+        for a in actions:
+            if how == "standalone":
+                out.append(s.comp_strehl(1.65)[:, :2].clone())
+            s.rows("ACTION", rl.action_dim).copy_(a)
+            s.step(mode=1)
+            if how == "fused":
+                out.append(s.buffer("STREHL").view(3, 4)[:, :2].clone())
+        s.step_with_strehl(False)
+        return torch.stack(out)
+
+    fused1 = run(sim, "fused")
+    alone = run(sim, "standalone")
+    assert torch.equal(fused1, alone)                       # same kernels on the same screens and voltages
+    fused2 = run(sim, "fused", delay0=True)
+    assert float((fused2[:, :, 0] - fused1[:, :, 0]).abs().max()) > 1e-4
+    flat = Simulator(t, 3, rl, atmosphere=False)
+    try:
+        f1 = run(flat, "fused")[:, :, 0]
+        f2 = run(flat, "fused", delay0=True)[:, :, 0]
+        assert torch.equal(f2[:-1], f1[1:])
+        assert float((f2 - f1).abs().max()) > 1e-4
+        assert float(f1.min()) > 0.0 and float(f1.max()) <= 1.0 + 1e-6
+    finally:
+        flat.close()
+    sim.check_device()
+
+
 def test_error_behaviour_and_edge_sizes(static10, torch):
     """Edge cases of the C ABI: rejected sizes raise (ValueError for dimension problems, as the reference's
     set_command does, rtcCompass.py:471-472), empty work is a no-op, calls before their prerequisites report

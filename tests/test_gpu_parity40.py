@@ -98,6 +98,49 @@ def test_extrusion_directions(static10, oracle_tab10, torch, wind):
         sim.close()
 
 
+def test_per_environment_r0(static10, oracle_tab10, torch):
+    """AtmosCompass.set_r0 with one seeing value per environment (the reference changes r0 of its single simulator at run
+    time, train_rpc.py:429-449): every environment's screens follow the oracle run with that environment's r0, through
+    the supervisor component's own method."""
+    from ao_marl_b200.lib import Simulator
+    from ao_marl_b200.supervisor.components import AtmosB200
+    from oracle import aoframe
+    sim = Simulator(static10, 3, rl=None)
+    try:
+        atm = AtmosB200(sim, static10.config)
+        r0 = np.array([0.16, 0.08, 0.25])
+        with pytest.raises(ValueError):
+            atm.set_r0(np.array([0.1, 0.2]))
+        atm.set_r0(r0)
+        seeds = np.array([900, 901, 902], dtype=np.int64)
+        sim.reset(seeds)
+        for _ in range(5):
+            sim.move_atmos()
+        n = int(sim.cfg.screen_dim[0])
+        a = static10.config.p_atmos
+        rms = []
+        for e in range(3):
+            tab = dict(oracle_tab10)
+            tab["r0_layers"] = np.array([r0[e] / (a.frac[0] ** (3.0 / 5.0) * a.pupixsize)])
+            o = aoframe.OracleAtmos(tab, int(seeds[e]))
+            o.reset(int(seeds[e]))
+            for _ in range(5):
+                o.move()
+            g = gpu_logical_screen(sim, 0, e)
+            record("per_env_r0", "screen", relerr(g, o.screens[0]))
+            assert relerr(g, o.screens[0]) < 3e-5
+            rms.append(float(np.std(g - g.mean())))
+        assert rms[1] > 1.3 * rms[0] > 1.3 * 1.3 * rms[2] * 0.8        # worse seeing, larger excursions (r0^-5/6)
+        atm.set_r0(0.16)                                             # scalar: back to one value for the batch
+        sim.reset(seeds)
+        o = aoframe.OracleAtmos(dict(oracle_tab10), int(seeds[1]))
+        o.reset(int(seeds[1]))
+        assert relerr(gpu_logical_screen(sim, 0, 1), o.screens[0]) < 3e-5
+        sim.check_device()
+    finally:
+        sim.close()
+
+
 @pytest.mark.parametrize("par", ["production_sh_10x10_2m.py", "production_sh_40x40_8m_3layers.py"])
 def test_single_extrusion_is_exact(par, torch):
     """One extrusion from IDENTICAL screens, every direction and layer: the integer contraction (extrude_i8.cuh: exact
