@@ -703,14 +703,14 @@ def test_strehl_ordering_in_the_fused_step(system10, torch):
 
     fused1 = run(sim, "fused")
     alone = run(sim, "standalone")
-    assert torch.equal(fused1, alone)                       # same kernels on the same screens and voltages
+    assert float((fused1 - alone).abs().max()) < 1e-6       # same kernels, same screens and voltages (atomic sum order differs)
     fused2 = run(sim, "fused", delay0=True)
     assert float((fused2[:, :, 0] - fused1[:, :, 0]).abs().max()) > 1e-4
     flat = Simulator(t, 3, rl, atmosphere=False)
     try:
         f1 = run(flat, "fused")[:, :, 0]
         f2 = run(flat, "fused", delay0=True)[:, :, 0]
-        assert torch.equal(f2[:-1], f1[1:])
+        assert float((f2[:-1] - f1[1:]).abs().max()) < 1e-6
         assert float((f2 - f1).abs().max()) > 1e-4
         assert float(f1.min()) > 0.0 and float(f1.max()) <= 1.0 + 1e-6
     finally:
