@@ -61,7 +61,7 @@ struct aom_ctx {
   float *bincube, *phase;
   const float* cube_override;
   double* tar_mom;            // [2][E][5] pupil sums of the target phase (aom_comp_strehl): main target, geometric one
-  float* tar_acc;             // [E][2] running sums for the long-exposure figures
+  float* tar_acc;             // [E][TAR_ACC] running sums for the long-exposure figures (SE, variance, 9 core pixels)
   int tar_n;
   // geometric controller (geo_kernels.cuh), allocated on first use
   float *geo_com, *geo_volts, *geo_b, *geo_T, *strehl_geo, *geo_acc;
@@ -78,6 +78,7 @@ struct aom_ctx {
   int closed;
   uint32_t frame;
   int opt[AOM_OPT_COUNT];
+  int tar_peak, geo_tar_peak; // whether the pending target sums hold the PSF core (AOM_TAR_PEAK)
   int* d_err;                 // device error word raised by bounded waits (gemm_tc.cuh)
   // RL
   float *modes, *modes_before, *modes_res, *state, *hist, *reward, *action, *action_mean, *strehl;
@@ -209,8 +210,8 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
   CU(dalloc(&ctx->volts, E * ctx->lda));
   CU(dalloc(&ctx->com_before, E * ctx->lda));
   CU(dalloc(&ctx->strehl, E * 4));
-  CU(dalloc(&ctx->tar_mom, E * 10));     // main target, then the geometric controller's
-  CU(dalloc(&ctx->tar_acc, E * 2));
+  CU(dalloc(&ctx->tar_mom, E * 2 * PSW_MOM2));     // main target, then the geometric controller's
+  CU(dalloc(&ctx->tar_acc, E * TAR_ACC));
   if (cfg->nmodes > 0) {
     CU(dalloc(&ctx->modes, E * ctx->ldm));
     CU(dalloc(&ctx->modes_before, E * ctx->ldm));
@@ -430,13 +431,14 @@ static int sweep_launch_t(aom_ctx* ctx, const SweepParams& P, cudaStream_t st) {
 
 // MODE 0: Tp / mom = geometric projection ; MODE 1: mom = pupil sums of m, m phi, m phi^2
 template <int MODE>
-static int sweep_launch(aom_ctx* ctx, const WfsParams& w, float* Tp, double* mom, cudaStream_t st, float k2t = 0.f) {
+static int sweep_launch(aom_ctx* ctx, const WfsParams& w, float* Tp, double* mom, cudaStream_t st, float k2t = 0.f,
+                        float core_step = 0.f) {
   const aom_config& c = ctx->cfg;
   SweepParams P;
   memset(&P, 0, sizeof(P));
   P.w = w;
   P.maskw = ctx->sweep_mask; P.ttp = ctx->sweep_ttp;
-  P.Tp = Tp; P.mom = mom; P.k2t = k2t;
+  P.Tp = Tp; P.mom = mom; P.k2t = k2t; P.core_step = core_step;
   P.nb = ctx->sweep_nb;
   P.n_strips = (c.n + PSW_STRIP - 1) / PSW_STRIP;
   P.err = ctx->d_err;
@@ -466,7 +468,7 @@ static int geo_prepare(aom_ctx* ctx) {
   }
   CU(dalloc(&ctx->geo_mom, E * 4));
   CU(dalloc(&ctx->strehl_geo, E * 4));
-  CU(dalloc(&ctx->geo_acc, E * 2));
+  CU(dalloc(&ctx->geo_acc, E * TAR_ACC));
   CU(cudaEventCreateWithFlags(&ctx->ev_geo, cudaEventDisableTiming));
   CU(dalloc(&ctx->geo_com, E * ctx->lda));
   return AOM_OK;
@@ -689,13 +691,13 @@ static int clear_loop_state(aom_ctx* ctx, cudaStream_t st) {
   ctx->hist_head = 0;
   ctx->cube_override = nullptr;
   ctx->tar_n = 0;
-  CU(cudaMemsetAsync(ctx->tar_acc, 0, E * 2 * sizeof(float), st));
+  CU(cudaMemsetAsync(ctx->tar_acc, 0, E * TAR_ACC * sizeof(float), st));
   CU(cudaMemsetAsync(ctx->strehl, 0, E * 4 * sizeof(float), st));
   if (ctx->geo_com) {
     ctx->geo_tar_n = 0;
     CU(cudaMemsetAsync(ctx->geo_com, 0, E * ctx->lda * 4, st));
     CU(cudaMemsetAsync(ctx->geo_volts, 0, E * ctx->lda * 4, st));
-    CU(cudaMemsetAsync(ctx->geo_acc, 0, E * 2 * sizeof(float), st));
+    CU(cudaMemsetAsync(ctx->geo_acc, 0, E * TAR_ACC * sizeof(float), st));
     CU(cudaMemsetAsync(ctx->strehl_geo, 0, E * 4 * sizeof(float), st));
   }
   return AOM_OK;
@@ -1283,25 +1285,33 @@ extern "C" int aom_comp_strehl(aom_ctx* ctx, int flags, float lambda_um, int acc
     p.volts = ctx->geo_volts;
   }
   int& n_le = geo ? ctx->geo_tar_n : ctx->tar_n;
-  double* mom = ctx->tar_mom + (geo ? (size_t)c.n_env * 5 : 0);
+  double* mom = ctx->tar_mom + (geo ? (size_t)c.n_env * PSW_MOM2 : 0);
+  // AOM_TAR_PEAK: brightest pixel of the PSF core with a three-point fit (comp_strehl(do_fit=True)) instead of the
+  // on-axis pixel; the pending sums remember which of the two a trace produced
+  int& peak = geo ? ctx->geo_tar_peak : ctx->tar_peak;
   if (!(flags & AOM_TAR_PUBLISH)) {
-    CU(cudaMemsetAsync(mom, 0, (size_t)c.n_env * 5 * sizeof(double), st));
+    peak = (flags & AOM_TAR_PEAK) != 0 || ctx->opt[AOM_OPT_STREHL_PEAK] != 0;
+    const int nfft = ctx->opt[AOM_OPT_PSF_NFFT];
+    if (peak && nfft < c.n) return fail(ctx, AOM_ERR_STATE, "AOM_OPT_PSF_NFFT (focal-plane grid of the target, >= pupil size) is not set");
+    CU(cudaMemsetAsync(mom, 0, (size_t)c.n_env * PSW_MOM2 * sizeof(double), st));
     rc = sweep_prepare(ctx, st);
     if (rc) return rc;
+    const float k2t = (float)(2.0 * M_PI / (double)lambda_um);
     if (ctx->sweep_state == 1 && ctx->opt[AOM_OPT_PUPIL_PATH] == AOM_PUPIL_SWEEP) {
-      rc = sweep_launch<1>(ctx, p, nullptr, mom, st, (float)(2.0 * M_PI / (double)lambda_um));
+      rc = peak ? sweep_launch<2>(ctx, p, nullptr, mom, st, k2t, 1.f / (float)nfft) : sweep_launch<1>(ctx, p, nullptr, mom, st, k2t);
       if (rc) return rc;
     } else {
       dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
-      target_moments_kernel<<<grid, blk, 0, st>>>(p, mom, (float)(2.0 * M_PI / (double)lambda_um));
+      target_moments_kernel<<<grid, blk, 0, st>>>(p, mom, k2t, peak ? PSW_MOM2 : 5, peak ? 1.f / (float)nfft : 0.f);
       KCHECK();
     }
     if (flags & AOM_TAR_TRACE) return AOM_OK;        // sums pending until AOM_TAR_PUBLISH
   }
   if (accumulate) n_le += 1;
-  target_strehl_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(mom, geo ? ctx->strehl_geo : ctx->strehl,
-                                                             geo ? ctx->geo_acc : ctx->tar_acc, c.n_env,
-                                                             accumulate ? n_le : 0);
+  float* out = geo ? ctx->strehl_geo : ctx->strehl;
+  float* acc = geo ? ctx->geo_acc : ctx->tar_acc;
+  if (peak) target_strehl_core_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(mom, out, acc, c.n_env, accumulate ? n_le : 0);
+  else target_strehl_kernel<<<(c.n_env + 127) / 128, 128, 0, st>>>(mom, 5, out, acc, c.n_env, accumulate ? n_le : 0);
   KCHECK();
   return AOM_OK;
 }
@@ -1352,11 +1362,11 @@ extern "C" int aom_apply_control_geo(aom_ctx* ctx, void* stream) {
 extern "C" int aom_reset_strehl(aom_ctx* ctx, void* stream) {
   if (!ctx) return AOM_ERR_INVALID;
   ctx->tar_n = 0;
-  CU(cudaMemsetAsync(ctx->tar_acc, 0, (size_t)ctx->cfg.n_env * 2 * sizeof(float), (cudaStream_t)stream));
+  CU(cudaMemsetAsync(ctx->tar_acc, 0, (size_t)ctx->cfg.n_env * TAR_ACC * sizeof(float), (cudaStream_t)stream));
   CU(cudaMemsetAsync(ctx->strehl, 0, (size_t)ctx->cfg.n_env * 4 * sizeof(float), (cudaStream_t)stream));
   if (ctx->geo_com) {
     ctx->geo_tar_n = 0;
-    CU(cudaMemsetAsync(ctx->geo_acc, 0, (size_t)ctx->cfg.n_env * 2 * sizeof(float), (cudaStream_t)stream));
+    CU(cudaMemsetAsync(ctx->geo_acc, 0, (size_t)ctx->cfg.n_env * TAR_ACC * sizeof(float), (cudaStream_t)stream));
     CU(cudaMemsetAsync(ctx->strehl_geo, 0, (size_t)ctx->cfg.n_env * 4 * sizeof(float), (cudaStream_t)stream));
   }
   return AOM_OK;

@@ -8,6 +8,11 @@
 //   MODE 1  target Strehl (TargetCompass.comp_tar_image / comp_strehl, shesha/supervisor/components/targetCompass.py:139-196,
 //           atmosphere + mirrors, pupil sums of m, m phi, m phi^2 (variance) and of m exp(i k phi): the on-axis
 //           intensity |<exp(i k phi)>|^2 is the peak of the PSF the reference's FFT would give for a tilt-free residual.
+//   MODE 2  MODE 1 + the 3 x 3 central pixels of that PSF on the reference's focal grid (zero-padded FFT of size Nfft:
+//           pixel (a, b) = |sum m exp(i k phi) exp(-2 pi i (a x + b y) / Nfft)|^2), by direct summation: the brightest
+//           pixel and its neighbours are what the reference's comp_strehl(do_fit=True) looks at in closed loop.
+//           Separable twiddles: per pixel four products with the lane's constant column twiddles, per row twelve with
+//           the row twiddle (16 more accumulators, no second pass).
 //
 // Layout of the work.  A warp owns a 128-pixel column block of a strip of consecutive pupil rows of one environment:
 // one lane = four pixels of the current row.  Pupil row y needs the screen rows r(y), r(y)+1 of every layer, and
@@ -34,6 +39,7 @@
 #define PSW_STRIP 46        // pupil rows per warp: 644 = 14 x 46 on the 40x40 grid
 #define PSW_BW 136          // staged floats per layer and screen row: 128 pixels + 1, rounded to 16 bytes, + alignment slack
 #define PSW_TP 12           // partial lattice sums per block and row (11 used)
+#define PSW_MOM2 24         // doubles per environment of the MODE 2 sums (21 used)
 
 struct SweepParams {
   WfsParams w;
@@ -42,7 +48,10 @@ struct SweepParams {
   float* Tp;                // MODE 0: [E][n][nb][PSW_TP]
   double* mom;              // MODE 0: [E][4] sums of m phi, m phi tt_x, m phi tt_y
                             // MODE 1: [E][5] sums of m, m phi, m phi^2, m cos(k phi), m sin(k phi)
+                            // MODE 2: [E][PSW_MOM2]: the five above, then T1..T4 of a = -1, 0, +1 and (Re, Im) of
+                            //         (a, b) = (-1, 0), (+1, 0)  (see psw_core_pixels)
   float k2t;                // MODE 1: 2 pi / target wavelength
+  float core_step;          // MODE 2: 1 / Nfft (turns of the focal twiddle per pupil pixel)
   int nb;                   // column blocks per row
   int n_strips;
   int* err;
@@ -109,7 +118,7 @@ __device__ __forceinline__ void psw_layer(const float* __restrict__ up, const fl
 }
 
 template <int NL, int MODE>
-__global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __grid_constant__ SweepParams P) {
+__global__ void __launch_bounds__(PSW_WARPS * 32, MODE == 2 ? 3 : 4) pupil_sweep_kernel(const __grid_constant__ SweepParams P) {
   extern __shared__ __align__(128) float psw_smem[];
   const WfsParams& p = P.w;
   // the warp index through a shuffle: the compiler then keeps everything derived from it (strip, column block, the
@@ -192,10 +201,26 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
   float tt0 = 0.f, tt1 = 0.f;
   const float* volts = nullptr;
-  const bool dm = MODE == 1 && p.use_dm;
+  const bool dm = MODE >= 1 && p.use_dm;
   if (dm) {
     volts = p.volts + (size_t)e * p.ldv;
     tt0 = __ldg(volts + p.pzt_nact); tt1 = __ldg(volts + p.pzt_nact + 1);
+  }
+  // MODE 2: column twiddles of this lane's four pixels (any origin: a shift of the pupil is a phase factor of the focal
+  // amplitude) and the sums T1..T4 = sum_rows (Re cy, Im sy, Im cy, Re sy) of the three row amplitudes R_a
+  float cxw[4], sxw[4], tc[3][4], tz[4];
+  if (MODE == 2) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sincospif(2.f * (float)(128 * cb + 4 * lane + c) * P.core_step, &sxw[c], &cxw[c]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { tc[a][0] = tc[a][1] = tc[a][2] = tc[a][3] = 0.f; }
+    tz[0] = tz[1] = tz[2] = tz[3] = 0.f;
+  }
+  // row twiddle exp(2 pi i y / Nfft), advanced by a rotation per row (46 rows per strip: the recurrence stays at 1e-6)
+  float cyw = 1.f, syw = 0.f, cdw = 1.f, sdw = 0.f;
+  if (MODE == 2) {
+    sincospif(2.f * (float)yb * P.core_step, &syw, &cyw);
+    sincospif(2.f * P.core_step, &sdw, &cdw);
   }
   float fq[16];                                    // MODE 0: the 16 taps of this lane's lattice offset u = lane & 3
   if (MODE == 0) {
@@ -286,15 +311,37 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
       } else {
         s0 += (float)__popc(mask);
         s2 = fmaf(v[0], v[0], s2); s2 = fmaf(v[1], v[1], s2); s2 = fmaf(v[2], v[2], s2); s2 = fmaf(v[3], v[3], s2);
+        float rc = 0.f, rs = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, p4 = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if ((mask >> (8 * c)) & 1u) {
             float sn, cs;
             wfm_sincos(P.k2t * v[c], sn, cs);
-            s3 += cs; s4 += sn;
+            rc += cs; rs += sn;
+            if (MODE == 2) {
+              p1 = fmaf(cs, cxw[c], p1); p2 = fmaf(sn, sxw[c], p2);
+              p3 = fmaf(sn, cxw[c], p3); p4 = fmaf(cs, sxw[c], p4);
+            }
           }
         }
+        s3 += rc; s4 += rs;
+        if (MODE == 2) {
+          // row amplitudes R_a = sum_x f exp(-i a d x): a = -1: (p1 - p2, p3 + p4), 0: (rc, rs), +1: (p1 + p2, p3 - p4)
+          const float sy = syw, cy = cyw;
+          const float re[3] = {p1 - p2, rc, p1 + p2}, im[3] = {p3 + p4, rs, p3 - p4};
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            tc[a][0] = fmaf(re[a], cy, tc[a][0]); tc[a][1] = fmaf(im[a], sy, tc[a][1]);
+            tc[a][2] = fmaf(im[a], cy, tc[a][2]); tc[a][3] = fmaf(re[a], sy, tc[a][3]);
+          }
+          tz[0] += re[0]; tz[1] += im[0]; tz[2] += re[2]; tz[3] += im[2];
+        }
       }
+    }
+    if (MODE == 2) {
+      const float cn = cyw * cdw - syw * sdw;
+      syw = fmaf(syw, cdw, cyw * sdw);
+      cyw = cn;
     }
     if (MODE == 0) *reinterpret_cast<float4*>(s_out + 20 * jl + k0) = make_float4(v[0], v[1], v[2], v[3]);
     __syncwarp();
@@ -346,11 +393,103 @@ __global__ void __launch_bounds__(PSW_WARPS * 32, 4) pupil_sweep_kernel(const __
       if (s2 != 0.f) atomicAdd(P.mom + (size_t)e * 4 + 1, (double)s2);
       if (s3 != 0.f) atomicAdd(P.mom + (size_t)e * 4 + 2, (double)s3);
     } else {
-      if (s0 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 0, (double)s0);
-      if (s1 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 1, (double)s1);
-      if (s2 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 2, (double)s2);
-      if (s3 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 3, (double)s3);
-      if (s4 != 0.f) atomicAdd(P.mom + (size_t)e * 5 + 4, (double)s4);
+      double* m = P.mom + (size_t)e * (MODE == 2 ? PSW_MOM2 : 5);
+      if (s0 != 0.f) atomicAdd(m + 0, (double)s0);
+      if (s1 != 0.f) atomicAdd(m + 1, (double)s1);
+      if (s2 != 0.f) atomicAdd(m + 2, (double)s2);
+      if (s3 != 0.f) atomicAdd(m + 3, (double)s3);
+      if (s4 != 0.f) atomicAdd(m + 4, (double)s4);
     }
+  }
+  if (MODE == 2) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = tc[a][j];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) t += __shfl_xor_sync(0xffffffffu, t, sft);
+        if (lane == 0 && t != 0.f) atomicAdd(P.mom + (size_t)e * PSW_MOM2 + 5 + 4 * a + j, (double)t);
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = tz[j];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) t += __shfl_xor_sync(0xffffffffu, t, sft);
+      if (lane == 0 && t != 0.f) atomicAdd(P.mom + (size_t)e * PSW_MOM2 + 17 + j, (double)t);
+    }
+  }
+}
+
+// The nine central PSF pixels from the MODE 2 sums, normalised to a flat wavefront's peak: I[b + 1][a + 1].
+__host__ __device__ inline void psw_core_pixels(const double* m, double (&I)[3][3]) {
+  const double s0 = m[0], inv = s0 > 0.0 ? 1.0 / (s0 * s0) : 0.0;
+  for (int a = 0; a < 3; ++a) {
+    const double t1 = m[5 + 4 * a], t2 = m[6 + 4 * a], t3 = m[7 + 4 * a], t4 = m[8 + 4 * a];
+    I[2][a] = ((t1 + t2) * (t1 + t2) + (t3 - t4) * (t3 - t4)) * inv;     // b = +1
+    I[0][a] = ((t1 - t2) * (t1 - t2) + (t3 + t4) * (t3 + t4)) * inv;     // b = -1
+  }
+  I[1][0] = (m[17] * m[17] + m[18] * m[18]) * inv;
+  I[1][1] = (m[3] * m[3] + m[4] * m[4]) * inv;
+  I[1][2] = (m[19] * m[19] + m[20] * m[20]) * inv;
+}
+
+// Brightest of the nine pixels refined by a three-point fit per axis (a parabola through the logarithms, i.e. a Gaussian
+// through the pixel and its two neighbours) when the neighbours exist inside the core; the stand-in for sutra's
+// comp_strehl(do_fit=True) (un-vendored; targetCompass.py:139-196), exact same estimate as oracle/aoframe.py::psf_peak on
+// the full image whenever the brightest pixel of the image is the on-axis one.
+__host__ __device__ inline double psw_core_peak(const double (&I)[3][3]) {
+  int bj = 1, bi = 1;
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i)
+      if (I[j][i] > I[bj][bi]) { bj = j; bi = i; }
+  const double pk = I[bj][bi];
+  if (!(pk > 0.0)) return 0.0;
+  double lg = log(pk);
+  if (bj == 1 && I[0][bi] > 0.0 && I[2][bi] > 0.0) {
+    const double m1 = log(I[0][bi]), p1 = log(I[2][bi]);
+    const double a = 0.5 * (m1 + p1) - log(pk), b = 0.5 * (p1 - m1);
+    if (a < 0.0) lg += -b * b / (4.0 * a);
+  }
+  if (bi == 1 && I[bj][0] > 0.0 && I[bj][2] > 0.0) {
+    const double m1 = log(I[bj][0]), p1 = log(I[bj][2]);
+    const double a = 0.5 * (m1 + p1) - log(pk), b = 0.5 * (p1 - m1);
+    if (a < 0.0) lg += -b * b / (4.0 * a);
+  }
+  return exp(lg);
+}
+
+
+// Strehl figures from the MODE 2 sums: SE = fitted peak of this frame's core, LE = fitted peak of the accumulated core
+// (the reference takes the maximum of the long-exposure image, not the mean of the short-exposure maxima).
+__global__ void target_strehl_core_kernel(const double* mom, float* strehl, float* acc, int E, int n_le) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const double* m = mom + (size_t)e * PSW_MOM2;
+  const double s0 = m[0];
+  double I[3][3];
+  psw_core_pixels(m, I);
+  float var = 0.f, se = 1.f;
+  if (s0 > 0.0) {
+    const double mean = m[1] / s0;
+    var = (float)fmax(m[2] / s0 - mean * mean, 0.0);
+    se = (float)psw_core_peak(I);
+  } else {
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) I[j][i] = (j == 1 && i == 1) ? 1.0 : 0.0;
+  }
+  strehl[e * 4 + 0] = se;
+  strehl[e * 4 + 2] = var;
+  if (n_le > 0) {
+    float* a = acc + (size_t)e * TAR_ACC;
+    a[0] += se;
+    a[1] += var;
+    double L[3][3];
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) {
+        a[2 + 3 * j + i] += (float)I[j][i];
+        L[j][i] = (double)a[2 + 3 * j + i] / (double)n_le;
+      }
+    strehl[e * 4 + 1] = (float)psw_core_peak(L);
+    strehl[e * 4 + 3] = a[1] / (float)n_le;
   }
 }

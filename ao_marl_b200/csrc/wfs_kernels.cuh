@@ -302,7 +302,8 @@ __global__ void wfs_phase_kernel(WfsParams p, float* phase) {
 // wfs_phase_kernel is evaluated per pixel and reduced on the fly -- sum m, sum m phi, sum m phi^2, sum m cos(k phi),
 // sum m sin(k phi) per environment (double atomics) -- instead of materialising [E][n][n].
 // grid (ceil(n/32), ceil(n/8), E), block (32, 8).  (Per-pixel cross-check form of pupil_sweep.cuh MODE 1.)
-__global__ void target_moments_kernel(WfsParams p, double* mom, float k2t) {
+#define TAR_ACC 12   // floats per environment of the long-exposure accumulators: SE sum, variance sum, 9 core pixels
+__global__ void target_moments_kernel(WfsParams p, double* mom, float k2t, int stride, float core_step) {
   const int e = blockIdx.z;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -341,29 +342,41 @@ __global__ void target_moments_kernel(WfsParams p, double* mom, float k2t) {
       acc += dm;
     }
   }
-  float s0 = m, s1 = m * acc, s2 = m * acc * acc, s3 = 0.f, s4 = 0.f;
-  if (m != 0.f) {
-    sincosf(k2t * acc, &s4, &s3);
-    s3 *= m; s4 *= m;
-  }
+  // sv[0..4]: m, m phi, m phi^2, m cos, m sin ; with the PSF core (stride > 5, same slots as pupil_sweep.cuh MODE 2):
+  // sv[5 + 4 a + j] = T1..T4 of a = -1, 0, +1 ; sv[17..20] = (Re, Im) of (a, b) = (-1, 0), (+1, 0)
+  float sv[21];
 #pragma unroll
-  for (int sft = 16; sft > 0; sft >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, sft);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, sft);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, sft);
-    s3 += __shfl_xor_sync(0xffffffffu, s3, sft);
-    s4 += __shfl_xor_sync(0xffffffffu, s4, sft);
+  for (int j = 0; j < 21; ++j) sv[j] = 0.f;
+  sv[0] = m; sv[1] = m * acc; sv[2] = m * acc * acc;
+  const int nsum = stride > 5 ? 21 : 5;
+  if (m != 0.f) {
+    float sn, cs;
+    sincosf(k2t * acc, &sn, &cs);
+    sv[3] = cs * m; sv[4] = sn * m;
+    if (stride > 5) {
+      float sx, cx, sy, cy;
+      sincospif(2.f * (float)x * core_step, &sx, &cx);
+      sincospif(2.f * (float)y * core_step, &sy, &cy);
+      const float re[3] = {cs * cx - sn * sx, cs, cs * cx + sn * sx}, im[3] = {sn * cx + cs * sx, sn, sn * cx - cs * sx};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        sv[5 + 4 * a] = re[a] * cy; sv[6 + 4 * a] = im[a] * sy; sv[7 + 4 * a] = im[a] * cy; sv[8 + 4 * a] = re[a] * sy;
+      }
+      sv[17] = re[0]; sv[18] = im[0]; sv[19] = re[2]; sv[20] = im[2];
+    }
   }
-  __shared__ float red[8][5];
-  if (threadIdx.x == 0) {
-    red[threadIdx.y][0] = s0; red[threadIdx.y][1] = s1; red[threadIdx.y][2] = s2;
-    red[threadIdx.y][3] = s3; red[threadIdx.y][4] = s4;
+  __shared__ float red[8][21];
+  for (int j = 0; j < nsum; ++j) {
+    float t = sv[j];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) t += __shfl_xor_sync(0xffffffffu, t, sft);
+    if (threadIdx.x == 0) red[threadIdx.y][j] = t;
   }
   __syncthreads();
-  if (threadIdx.y == 0 && threadIdx.x < 5) {
+  if (threadIdx.y == 0 && threadIdx.x < nsum) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    if (t != 0.f) atomicAdd(mom + (size_t)e * 5 + threadIdx.x, (double)t);
+    if (t != 0.f) atomicAdd(mom + (size_t)e * stride + threadIdx.x, (double)t);
   }
 }
 
@@ -373,10 +386,11 @@ __global__ void target_moments_kernel(WfsParams p, double* mom, float k2t) {
 // and stays meaningful in open loop where that underflows.  The long-exposure PSF is the mean of the short ones, so
 // its peak is the running mean.  acc [E][2] running sums of SE and var, n_le the number of accumulated frames
 // including this one (0: no accumulation).
-__global__ void target_strehl_kernel(const double* mom, float* strehl, float* acc, int E, int n_le) {
+__global__ void target_strehl_kernel(const double* mom, int stride, float* strehl, float* acc, int E, int n_le) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
-  const double s0 = mom[e * 5], s1 = mom[e * 5 + 1], s2 = mom[e * 5 + 2], sc = mom[e * 5 + 3], ss = mom[e * 5 + 4];
+  const double* m = mom + (size_t)e * stride;
+  const double s0 = m[0], s1 = m[1], s2 = m[2], sc = m[3], ss = m[4];
   float var = 0.f, se = 1.f;
   if (s0 > 0.0) {
     const double mean = s1 / s0;
@@ -386,10 +400,10 @@ __global__ void target_strehl_kernel(const double* mom, float* strehl, float* ac
   strehl[e * 4 + 0] = se;
   strehl[e * 4 + 2] = var;
   if (n_le > 0) {
-    acc[e * 2 + 0] += se;
-    acc[e * 2 + 1] += var;
-    strehl[e * 4 + 1] = acc[e * 2 + 0] / (float)n_le;
-    strehl[e * 4 + 3] = acc[e * 2 + 1] / (float)n_le;
+    acc[e * TAR_ACC + 0] += se;
+    acc[e * TAR_ACC + 1] += var;
+    strehl[e * 4 + 1] = acc[e * TAR_ACC + 0] / (float)n_le;
+    strehl[e * 4 + 3] = acc[e * TAR_ACC + 1] / (float)n_le;
   }
 }
 

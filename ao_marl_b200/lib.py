@@ -47,7 +47,7 @@ BUFFERS = ["SCREEN", "RING_OX", "RING_OY", "SLOPES", "ERR", "COM", "VOLTS", "BIN
            "RES_MODES", "STATE", "REWARD", "ACTION", "ACTION_MEAN", "STREHL", "GEO_COM", "GEO_VOLTS", "STREHL_GEO", "GEO_PROJ"]
 B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
-OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH", "KEEP_IMAGE", "STREHL", "STREHL_LAMBDA_NM", "EXTRUDE_PATH"]
+OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH", "KEEP_IMAGE", "STREHL", "STREHL_LAMBDA_NM", "EXTRUDE_PATH", "STREHL_PEAK", "PSF_NFFT"]
 O = {name: i for i, name in enumerate(OPTIONS)}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
@@ -228,6 +228,12 @@ class Simulator:
             raise (ValueError if rc == -1 else RuntimeError)("aom_create: " + msg)
         self._stream = stream
         self._views = {}
+        # focal-plane grid of the target image (p_geom._ipupil, geom_init: 2^ceil(log2(pupdiam) + 1)) for the PSF core
+        try:
+            self.psf_nfft = int(np.asarray(t.config.p_geom._ipupil).shape[0])
+        except Exception:
+            self.psf_nfft = int(2 ** np.ceil(np.log2(max(int(t.n) - 4, 2)) + 1))
+        self._check(self.lib.aom_set_option(self._ctx, O["PSF_NFFT"], self.psf_nfft), "aom_set_option")
         self._upload_static(amap)
         if cfg.nmodes:
             self.set_basis(t.Btt, t.P)
@@ -389,11 +395,14 @@ class Simulator:
         self._check(self.lib.aom_raytrace_wfs(self._ctx, flags, self.stream), "aom_raytrace_wfs")
         return self.buffer("PHASE").view(self.n_env, self.cfg.n, self.cfg.n)
 
-    def comp_strehl(self, lambda_um, atmos=True, dms=True, accumulate=True, geo=False, phase="both"):
+    def comp_strehl(self, lambda_um, atmos=True, dms=True, accumulate=True, geo=False, phase="both", peak=False):
         """Pupil phase variance -> AOM_B_STREHL [E, 4] = (SE, LE, variance, mean variance); geo=True: the target
         behind the geometric controller's mirrors (AOM_B_STREHL_GEO).  phase: "both" (trace now and publish), "trace"
-        (TargetCompass.raytrace: sweep now, keep pending) or "publish" (comp_tar_image / comp_strehl on the pending sums)."""
-        flags = (1 if atmos else 0) | (2 if dms else 0) | (0x100 if geo else 0) | {"both": 0, "trace": 0x200, "publish": 0x400}[phase]
+        (TargetCompass.raytrace: sweep now, keep pending) or "publish" (comp_tar_image / comp_strehl on the pending sums).
+        peak: SE / LE from the brightest pixel of the 3 x 3 PSF core with a three-point fit (comp_strehl(do_fit=True))
+        instead of the on-axis pixel."""
+        flags = ((1 if atmos else 0) | (2 if dms else 0) | (0x100 if geo else 0) | (0x800 if peak else 0)
+                 | {"both": 0, "trace": 0x200, "publish": 0x400}[phase])
         self._check(self.lib.aom_comp_strehl(self._ctx, flags, float(lambda_um), 1 if accumulate else 0, self.stream),
                     "aom_comp_strehl")
         return self.buffer("STREHL_GEO" if geo else "STREHL").view(self.n_env, 4)
@@ -425,6 +434,10 @@ class Simulator:
     def step_keeps_image(self, on=True):
         """aom_step keeps every frame's detector cube in AOM_B_BINCUBE (AOM_OPT_KEEP_IMAGE)."""
         self._check(self.lib.aom_set_option(self._ctx, O["KEEP_IMAGE"], 1 if on else 0), "aom_set_option")
+
+    def strehl_from_peak(self, on=True):
+        """Every Strehl evaluation (aom_comp_strehl and the one inside aom_step) uses the fitted PSF-core peak."""
+        self._check(self.lib.aom_set_option(self._ctx, O["STREHL_PEAK"], 1 if on else 0), "aom_set_option")
 
     def step_with_strehl(self, on=True, lambda_um=1.65, pure_delay_0=False):
         """aom_step evaluates the target Strehl every frame, as the reference's next_part_two does by default

@@ -323,7 +323,8 @@ class TargetB200(_Base):
     """targetCompass.py (next-row scope) without the focal-plane image: get_strehl() = [SE, LE, phase variance, mean
     variance] with SE = |<exp(i k phi)>|^2 over the pupil -- the on-axis intensity ratio, i.e. the peak of the PSF the
     reference's FFT gives for a tilt-free residual (Marechal's exp(-sigma^2) for small ones) -- and LE its mean over the
-    frames; the 2048^2 image of comp_tar_image is not computed.  One sweep kernel (aom_comp_strehl) evaluates the on-axis
+    frames; with peak_fit (default) SE / LE are the brightest pixel of the 3 x 3 PSF core on the reference's focal grid,
+    refined by a three-point fit per axis (comp_strehl(do_fit=True)); the full image only exists on demand (get_tar_image).  One sweep kernel (aom_comp_strehl) evaluates the on-axis
     phase per pupil pixel and reduces it without materialising it; the figures live in AOM_B_STREHL."""
 
     def __init__(self, sim, config, tables, eager_trace=False):
@@ -336,6 +337,9 @@ class TargetB200(_Base):
         # for -- one sweep per frame instead of one per trace, equal to the reference's "pure delay 0" ordering.
         self.eager_trace = bool(eager_trace)
         self._pending = set()
+        # SE / LE from the brightest pixel of the PSF core with a three-point fit, as the reference's
+        # comp_strehl(do_fit=True) default; False: the on-axis pixel (cheaper sweep)
+        self.peak_fit = True
         # target i looks through the mirrors of the geometric controller when its dms are that controller's
         # (parameter layout "geo": target 1 <-> DMs [1, 3] <-> controller 1)
         geo = next((c for c in config.p_controllers if getattr(c, "type", "") == "geo"), None)
@@ -355,14 +359,15 @@ class TargetB200(_Base):
         self._flags[index] = (a, d)
         if self.eager_trace:
             lam = float(self._config.p_targets[index].Lambda)
-            self._sim.comp_strehl(lam, atmos=a, dms=d, geo=self._is_geo(index), phase="trace")
+            self._sim.comp_strehl(lam, atmos=a, dms=d, geo=self._is_geo(index), phase="trace", peak=self.peak_fit)
             self._pending.add(index)
 
     def comp_tar_image(self, tarNum, *, puponly=0, compLE=True):
         lam = float(self._config.p_targets[tarNum].Lambda)
         a, d = self._flags.get(tarNum, (False, False))
         phase = "publish" if (self.eager_trace and tarNum in self._pending) else "both"
-        self._sim.comp_strehl(lam, atmos=a, dms=d, accumulate=bool(compLE), geo=self._is_geo(tarNum), phase=phase)
+        self._sim.comp_strehl(lam, atmos=a, dms=d, accumulate=bool(compLE), geo=self._is_geo(tarNum), phase=phase,
+                              peak=self.peak_fit)
 
     def comp_strehl(self, tarNum, *, do_fit=True):
         pass
@@ -377,8 +382,28 @@ class TargetB200(_Base):
             return [float(x) for x in s[0].cpu()]
         return [s[:, i] for i in range(4)]
 
-    def get_tar_image(self, tar_index, *, expo_type="se"):
-        raise NotImplementedError("the focal-plane PSF is outside the hot-path scope (SURVEY.md 8(f) rank 1)")
+    def get_tar_image(self, tar_index, *, expo_type="se", envs=None):
+        """Short-exposure PSF on the reference's Nfft x Nfft focal grid, centred (np.fft.fftshift of sutra's d_image_se,
+        targetCompass.py:69-87), in units of the diffraction-limited peak.  An on-demand getter for plots and checks, not
+        part of the step: the phase of the selected environments (default: the first) is materialised and transformed
+        with torch.fft.  The long-exposure image is not kept -- only its 3 x 3 core feeds the LE Strehl."""
+        if expo_type != "se":
+            raise NotImplementedError("only the 3 x 3 core of the long-exposure image is accumulated (LE Strehl)")
+        import torch
+        sim = self._sim
+        a, d = self._flags.get(tar_index, (True, True))
+        envs = [0] if envs is None else list(envs)
+        g = self._config.p_geom
+        pd = int(g.pupdiam)
+        off = (int(g._n) - pd) // 2
+        ph = sim.raytrace_wfs(atmos=a, dms=d)[envs, off:off + pd, off:off + pd].double()
+        pup = torch.as_tensor(np.asarray(g._spupil) > 0, device=ph.device)
+        k = 2 * np.pi / float(self._config.p_targets[tar_index].Lambda)
+        field = torch.polar(pup.double().expand_as(ph), k * ph)
+        nf = sim.psf_nfft
+        img = torch.fft.fft2(field, s=(nf, nf)).abs().square() / float(pup.sum()) ** 2
+        img = torch.fft.fftshift(img, dim=(-2, -1)).float()
+        return img[0].cpu().numpy() if (sim.n_env == 1 or len(envs) == 1) else img
 
     def get_tar_phase(self, tar_index, *, pupil=False):
         a, d = self._flags.get(tar_index, (False, False))

@@ -83,6 +83,8 @@ def parse():
     ap.add_argument("--wfs-path", default=None,
                     choices=["umma", "umma_fast", "simt", "tensor", "tensor_fast", "tensor_reg"],
                     help="Shack-Hartmann frame kernel (default: the library's product path)")
+    ap.add_argument("--strehl-peak", action="store_true",
+                    help="with --strehl: SE / LE from the fitted peak of the 3 x 3 PSF core instead of the on-axis pixel")
     ap.add_argument("--strehl", action="store_true",
                     help="evaluate the target Strehl inside every timed step, as the reference's next_part_two does by "
                          "default (compute_tar_psf=True, rlSupervisor.py:944-947); without the flag the figure is still "
@@ -316,6 +318,17 @@ def measure_variants(args, sim, t, rl, E, dist, barrier, ev):
         b.record()
         barrier()
         out["strehl_ms"] = a.elapsed_time(b) / k
+        sim.strehl_from_peak(True)                  # fitted PSF-core peak (comp_strehl(do_fit=True)) instead of the on-axis pixel
+        sim.step(mode=0)
+        barrier()
+        a, b = ev(enable_timing=True), ev(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            sim.step(mode=0)
+        b.record()
+        barrier()
+        out["strehl_peak_ms"] = a.elapsed_time(b) / k
+        sim.strehl_from_peak(False)
         sim.step_with_strehl(False)
     if rl.n_agents:
         from ao_marl_b200.env.trainer import StepLearner
@@ -377,6 +390,11 @@ def format_variants(v, args, E, world, ms):
             "note": "aom_step with AOM_OPT_STREHL: target Strehl (pupil sums, no focal-plane image) evaluated after "
                     "apply_control on every frame, as the reference's default next_part_two does (rlSupervisor.py:944-947); "
                     "the turbulence update then cannot run beside the actor GEMMs"}
+    if "strehl_peak_ms" in v:
+        out["with_peak_strehl_every_frame"] = {
+            "ms_per_step": v["strehl_peak_ms"], "value": E * world / (v["strehl_peak_ms"] * 1e-3), "unit": "env-steps/s",
+            "note": "the same with the 3 x 3 PSF core of the reference's focal grid summed in the sweep and the fitted "
+                    "peak as SE / LE (comp_strehl(do_fit=True), targetCompass.py:139-196)"}
     if "learn_step_ms" in v:
         out["learn"] = {
             "config": "config 5: %d agents, batch %d, one SAC update of every agent per env-step, gradients "
@@ -414,6 +432,7 @@ def run_ours(args):
         sim.set_wfs_path(args.wfs_path)
     if args.strehl:
         sim.step_with_strehl(True, 1.65)
+        sim.strehl_from_peak(bool(args.strehl_peak))
     if args.denoise:
         from ao_marl_b200.denoiser import Autoencoder
         Autoencoder(dict(type="cnn_single_subaperture", path="autoencoder_M9_rms_3"), device="cuda", sim=sim)

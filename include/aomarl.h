@@ -166,6 +166,8 @@ typedef enum aom_option {
                            2: re-traced after apply_control (modification_online / "pure delay 0", rlSupervisor.py:936-940) */
   AOM_OPT_STREHL_LAMBDA_NM, /* target wavelength in nanometres for AOM_OPT_STREHL (default 1650) */
   AOM_OPT_EXTRUDE_PATH, /* which contraction serves the screen extrusion (aom_move_atmos / aom_reset) */
+  AOM_OPT_STREHL_PEAK,  /* != 0: every aom_comp_strehl (and AOM_OPT_STREHL inside aom_step) behaves as with AOM_TAR_PEAK */
+  AOM_OPT_PSF_NFFT,     /* size of the target's zero-padded focal grid (p_geom._ipupil: 2^ceil(log2(pupdiam) + 1)) */
   AOM_OPT_COUNT
 } aom_option;
 enum {
@@ -252,6 +254,10 @@ int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream);
  * The 2048^2 focal-plane PSF is not computed. */
 #define AOM_TAR_GEO 0x100   /* flags bit: the target behind the geometric controller's mirrors (reads AOM_B_GEO_VOLTS,
                                writes AOM_B_STREHL_GEO) instead of the main ones */
+#define AOM_TAR_PEAK 0x800  /* flags bit: Strehl from the brightest pixel of the PSF core (3 x 3 pixels of the reference's
+                               Nfft focal grid, AOM_OPT_PSF_NFFT) with a three-point fit per axis, as comp_strehl(do_fit=True)
+                               (targetCompass.py:139-196), instead of the on-axis pixel; the long exposure is the fit of
+                               the accumulated core */
 #define AOM_TAR_TRACE 0x200 /* flags bit: TargetCompass.raytrace only -- sweep the pupil now (current screens and voltages) and
                                keep the sums pending; nothing is published */
 #define AOM_TAR_PUBLISH 0x400 /* flags bit: comp_tar_image / comp_strehl only -- publish (and accumulate) the pending sums of

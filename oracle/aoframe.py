@@ -261,3 +261,34 @@ def cog(cube, w):
         gx = np.where(tot > 0, sx / tot, offset)
         gy = np.where(tot > 0, sy / tot, offset)
     return np.concatenate([(gx - offset) * scale, (gy - offset) * scale]).astype(F32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# (f-1) target image and Strehl -- TargetCompass.comp_tar_image / comp_strehl, targetCompass.py:139-196; the
+# arithmetic is sutra's (un-vendored): zero-padded FFT of pupil * exp(i k phi) on the Nfft grid of p_geom._ipupil,
+# |.|^2, maximum pixel, optional sub-pixel fit, normalised by the same figure of a flat wavefront.  [S] the fit is
+# restated as a three-point Gaussian (parabola through the logarithms) per axis around the brightest pixel.
+def psf_image(phase, pupil, lam, nfft):
+    """|FFT|^2 of the pupil field, in units of the diffraction-limited peak, zero frequency at [0, 0]."""
+    pup = np.asarray(pupil) > 0
+    f = pup * np.exp(1j * (2 * np.pi / lam) * np.asarray(phase, np.float64))
+    return np.abs(np.fft.fft2(f, s=(nfft, nfft))) ** 2 / float(pup.sum()) ** 2
+
+
+def fit_peak(img):
+    """Brightest pixel refined by a three-point Gaussian fit along each axis (periodic neighbours)."""
+    j, i = np.unravel_index(np.argmax(img), img.shape)
+    pk = img[j, i]
+    lg = np.log(pk)
+    for m1, p1 in ((img[j - 1, i], img[(j + 1) % img.shape[0], i]), (img[j, i - 1], img[j, (i + 1) % img.shape[1]])):
+        if m1 > 0 and p1 > 0:
+            a = 0.5 * (np.log(m1) + np.log(p1)) - np.log(pk)
+            b = 0.5 * (np.log(p1) - np.log(m1))
+            if a < 0:
+                lg += -b * b / (4 * a)
+    return float(np.exp(lg))
+
+
+def psf_peak(phase, pupil, lam, nfft, do_fit=True):
+    img = psf_image(phase, pupil, lam, nfft)
+    return fit_peak(img) if do_fit else float(img.max())

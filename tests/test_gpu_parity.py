@@ -673,6 +673,54 @@ def test_strehl_kernel_matches_the_materialised_phase(sim10, static10, torch):
     sim10.check_device()
 
 
+def test_psf_core_strehl_against_oracle(system10, static10, torch):
+    """Peak Strehl (comp_strehl(do_fit=True), targetCompass.py:139-196): the 3 x 3 PSF core summed directly in the pupil
+    sweep + the three-point fit, against the oracle's full zero-padded FFT image (oracle.aoframe.psf_image / fit_peak) of
+    the same phase; short exposure per frame, long exposure = fit of the accumulated image; both sweep forms; and the
+    on-demand image getter.  Closed loop with the integrator so that the peak sits within a pixel of the axis."""
+    from oracle import aoframe as af
+    from ao_marl_b200.supervisor.components import TargetB200
+    sim, t, rl = system10
+    g = t.config.p_geom
+    pd, off = int(g.pupdiam), (int(g._n) - int(g.pupdiam)) // 2
+    sp = np.asarray(g._spupil) > 0
+    nfft = sim.psf_nfft
+    assert nfft == np.asarray(g._ipupil).shape[0] == 512
+    lam = 1.65
+    sim.reset(np.array([21, 22, 23], dtype=np.int64))
+    sim.reset_strehl()
+    for _ in range(25):                                        # let the integrator converge
+        sim.move_atmos(); sim.comp_wfs_image(); sim.do_centroids(); sim.do_control(); sim.apply_control()
+    le_img = [np.zeros((nfft, nfft)) for _ in range(3)]
+    worst = 0.0
+    try:
+        for it in range(4):
+            sim.set_pupil_path("pixel" if it & 1 else "sweep")
+            sim.move_atmos(); sim.comp_wfs_image(); sim.do_centroids(); sim.do_control(); sim.apply_control()
+            s = sim.comp_strehl(lam, peak=True).cpu().numpy()
+            on_axis = sim.comp_strehl(lam, accumulate=False).cpu().numpy()[:, 0]
+            ph = sim.raytrace_wfs().cpu().numpy()[:, off:off + pd, off:off + pd]
+            for e in range(3):
+                img = af.psf_image(ph[e], sp, lam, nfft)
+                le_img[e] += img
+                se, le = af.fit_peak(img), af.fit_peak(le_img[e] / (it + 1))
+                assert np.unravel_index(np.argmax(img), img.shape) == (0, 0)     # closed loop: brightest pixel on axis
+                assert se > 0.3 and se >= img[0, 0] and abs(on_axis[e] - img[0, 0]) < 1e-5
+                worst = max(worst, abs(s[e, 0] - se), abs(s[e, 1] - le))
+                assert abs(s[e, 0] - se) < 2e-5 and abs(s[e, 1] - le) < 2e-5, (it, e, s[e], se, le)
+    finally:
+        sim.set_pupil_path("sweep")
+    print("peak Strehl vs oracle FFT image, worst abs error:", worst)
+    # the image getter against the oracle image (centred)
+    tar = TargetB200(sim, t.config, t)
+    tar.raytrace(0, atm=type("A", (), {"is_enable": True})(), dms=object())
+    img = tar.get_tar_image(0, envs=[1])
+    ref = np.fft.fftshift(af.psf_image(ph[1], sp, lam, nfft))
+    assert img.shape == (nfft, nfft) and np.abs(img - ref).max() < 1e-5
+    sim.reset_strehl()
+    sim.check_device()
+
+
 def test_strehl_ordering_in_the_fused_step(system10, torch):
     """AOM_OPT_STREHL inside aom_step: value 1 publishes the phase as traced in the previous next_part_one, i.e. with the
     voltages that were on the mirrors before this step's apply_control (rlSupervisor.py:964-965 then 944-947); value 2

@@ -176,3 +176,23 @@ def test_closed_loop_statistics(oracle_tab10, oracle_imat10, static10):
     norm, _ = load_normalization("production_sh_10x10_2m.py")
     ref = float(norm["wfs"]["std"].mean())
     assert abs(np.mean(rms) / ref - 1) < 0.25
+
+
+def test_psf_peak_fit_known_answers():
+    """oracle.aoframe.psf_image / fit_peak: flat wavefront -> peak 1 on axis; a pure tilt of a fraction of a pixel leaves
+    the fitted peak within 1 % of 1 while the brightest pixel drops; a Gaussian image is fitted exactly."""
+    from oracle import aoframe as af
+    n, nfft = 64, 256
+    yy, xx = np.mgrid[0:n, 0:n] - (n - 1) / 2.0
+    pup = (xx ** 2 + yy ** 2) <= (n / 2.0) ** 2
+    img = af.psf_image(np.zeros((n, n)), pup, 1.65, nfft)
+    assert abs(img[0, 0] - 1.0) < 1e-12 and abs(af.fit_peak(img) - 1.0) < 1e-9
+    lam = 1.65
+    for shift in (0.2, 0.4):                                   # focal shift in pixels of the nfft grid
+        tilt = lam * shift * xx / nfft                          # k * tilt = 2 pi shift x / nfft
+        img = af.psf_image(tilt, pup, lam, nfft)
+        assert img.max() < 1.0 - 0.02 * shift
+        assert abs(af.fit_peak(img) - 1.0) < 0.01
+    jj, ii = np.mgrid[0:32, 0:32]
+    gimg = 0.7 * np.exp(-((jj - 10.3) ** 2 + (ii - 20.6) ** 2) / 8.0)
+    assert abs(af.fit_peak(gimg) - 0.7) < 1e-12
