@@ -19,6 +19,7 @@
 #include "geo_kernels.cuh"
 #include "pupil_sweep.cuh"
 #include "denoise_kernels.cuh"
+#include "denoise_tc_host.h"
 
 static char g_create_error[512] = "";
 
@@ -78,6 +79,8 @@ struct aom_ctx {
   int closed;
   uint32_t frame;
   int opt[AOM_OPT_COUNT];
+  long long* dn_dbg;
+  float dn_prm[DT_NPARAM];    // float parameters of the tensor-core denoiser (head of AOM_T_DENOISER_TC)
   int tar_peak, geo_tar_peak; // whether the pending target sums hold the PSF core (AOM_TAR_PEAK)
   int* d_err;                 // device error word raised by bounded waits (gemm_tc.cuh)
   // RL
@@ -212,6 +215,7 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
   CU(dalloc(&ctx->strehl, E * 4));
   CU(dalloc(&ctx->tar_mom, E * 2 * PSW_MOM2));     // main target, then the geometric controller's
   CU(dalloc(&ctx->tar_acc, E * TAR_ACC));
+  CU(cudaMalloc((void**)&ctx->dn_dbg, 16 * sizeof(long long)));
   if (cfg->nmodes > 0) {
     CU(dalloc(&ctx->modes, E * ctx->ldm));
     CU(dalloc(&ctx->modes_before, E * ctx->ldm));
@@ -312,6 +316,7 @@ static size_t table_expected_bytes(const aom_ctx* ctx, int t, int index) {
     case AOM_T_GEO_PROJ: return (size_t)c.nactu * AOM_LD(c.nactu) * 4;
     case AOM_T_GEO_SIFN: return (size_t)c.nactu * 4;
     case AOM_T_DENOISER: return (size_t)DN_PARAM_FLOATS * 4;
+    case AOM_T_DENOISER_TC: return (size_t)DT_NPARAM * 4 + DT_WBLOB_BYTES;
   }
   return 0;
 }
@@ -359,6 +364,7 @@ extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* hos
     ctx->umma_state = 0;
   }
   if (table == AOM_T_MPUPIL || table == AOM_T_TT_PLANES) ctx->sweep_state = 0;
+  if (table == AOM_T_DENOISER_TC) memcpy(ctx->dn_prm, host, (size_t)DT_NPARAM * 4);   // float parameters travel as kernel arguments
   if (table == AOM_T_AB) {
     // digit planes of [A | B] for the exact integer extrusion
     const aom_config& c = ctx->cfg;
@@ -1394,7 +1400,24 @@ extern "C" int aom_denoise(aom_ctx* ctx, const float* din, float* dout, long lon
     if (din != ctx->bincube) return fail(ctx, AOM_ERR_INVALID, "in-place denoising needs the context's detector cube as input");
     dout = ctx->bincube;
   }
-  if (n_spots > 0) {
+  if (n_spots > 0 && ctx->opt[AOM_OPT_DENOISE_PATH] == AOM_DENOISE_TCGEN05 && ctx->tab[AOM_T_DENOISER_TC][0]) {
+    DnTcParams P;
+    P.in = din; P.out = dout; P.n_spots = n_spots;
+    P.wblob = (const uint8_t*)ctx->tab[AOM_T_DENOISER_TC][0] + (size_t)DT_NPARAM * 4;
+    P.err = ctx->d_err;
+    P.dbg = getenv("AOM_DN_TIMING") ? ctx->dn_dbg : nullptr;
+    memcpy(P.prm, ctx->dn_prm, sizeof(P.prm));
+    CU(denoise_tc_launch(P, ctx->num_sms, (cudaStream_t)stream));
+    ctx->launches += 1;
+    if (P.dbg) {   // development: per-phase clock totals of CTA 0
+      long long h[12];
+      CU(cudaStreamSynchronize((cudaStream_t)stream));
+      CU(cudaMemcpy(h, ctx->dn_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+      const char* nm[9] = {"load+e1", "e2 mma", "e2 epi", "e3 mma", "e3 epi", "d1 mma", "d1 epi", "d2 mma", "d2 epi+d3+store"};
+      const double passes = (double)((n_spots + DT_G - 1) / DT_G + ctx->num_sms - 1) / ctx->num_sms;
+      for (int i = 0; i < 9; ++i) fprintf(stderr, "denoise_tc %-16s %9.0f cycles per pass\n", nm[i], (double)h[i] / passes);
+    }
+  } else if (n_spots > 0) {
     CU(cudaFuncSetAttribute(denoise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_SMEM_BYTES));
     const long long batches = (n_spots + DN_G - 1) / DN_G;
     const int grid = (int)(batches < ctx->num_sms ? batches : ctx->num_sms);

@@ -1,0 +1,603 @@
+// denoise_tc.cuh -- the per-subaperture CNN denoiser with its four wide layers on tcgen05 (row a-6, config 4).
+//
+// Reference: DenoisingAutoencoderCNN2DSingleSubapeture (src/autoencoder/autoencoder_models.py:130-197), applied to every
+// 16 x 16 spot of the detector cube between the sensor frame and the centroider (rlSupervisor.py:876-891, 968-979):
+//   e1 conv3x3 1->16 + relu + pool | e2 conv3x3 16->32 + relu + pool | e3 conv3x3 32->64 + relu
+//   d1 convT4x4/2 64->32 + relu    | d2 convT4x4/2 32->16 + relu     | d3 convT3x3 16->1
+// 96 % of the 3.42 MFLOP per spot are in e2, e3, d1, d2.  They run here as implicit GEMMs on `tcgen05.mma kind::f16`
+// (fp16 hi + lo operands, three products each, float32 accumulators in TMEM); e1 and d3 (K = 9 / N = 1) stay on the
+// CUDA cores, fused into the prologue and the last epilogue.  denoise_kernels.cuh keeps the float32 FFMA form
+// (cross-check, AOM_DENOISE_SIMT).
+//
+// One geometry for every layer.  A pass takes G = 5 spots.  Every feature map is stored *space-to-depth* on the 4 x 4
+// coarse grid of a spot: an 8 x 8 map as 4 phase planes, a 16 x 16 map as 16.  Coarse positions of the five spots are
+// laid out linearly with a shared zero pad column and pad row (pitch 5: q = (1 + 5 s + Y) 5 + 1 + X < 128), so
+//   * the M dimension of every GEMM is the same 128 positions = one UMMA tile = TMEM lane = one epilogue thread,
+//   * a convolution tap, a pooling phase or a transposed-convolution parity is a (phase plane, linear shift) pair, i.e.
+//     only a different *start address* of the A descriptor: activations live in shared memory as planes
+//     [channel group of 8][position][8 channels] (16 bytes per position), which is the no-swizzle K-major core-matrix
+//     order (8 consecutive positions x 16 bytes = one core matrix, SBO = 128 B, LBO = plane stride) for any shift,
+//   * max-pooling = the maximum over four accumulators (the four output phases of e2) in the epilogue thread; the four
+//     parities of a transposed convolution are four accumulators (d1) / sixteen (d2, two levels) -- no data movement.
+// Zero padding = the pad positions of the planes, zeroed once and never written.  Activations carry a factor 2^-4 (exact)
+// so that fp16 cannot overflow on bright spots; biases are pre-scaled, the last layer undoes it.
+// d3 (transposed 3 x 3, 16 -> 1) is a scatter from the d2 epilogue: the thread that holds a 4 x 4 x 16 block of d2's
+// output adds its 6 x 6 window of partial sums into the output image in shared memory.
+// Weights (256 KB as fp16 hi / lo tiles, pre-ordered by ao_marl_b200/denoiser.py::pack_weights_tc) stream through two
+// 36 KB buffers by cp.async.bulk, eight chunks per pass, prefetched one chunk ahead.
+// Warps 0-7: prologue (e1), epilogues (two warps per TMEM lane quarter split the columns); warp 8: one lane issues the
+// bulk copies and the 738 MMAs of a pass.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#define DT_G 5
+#define DT_PITCH 5
+#define DT_LEAD 8
+#define DT_NPOS 144
+#define DT_PLANE (DT_NPOS * 16)            // 2304 B: one channel group of 8 (fp16) over all positions
+#define DT_WBUF 36864
+#define DT_THREADS 288
+#define DT_TMEM_COLS 512
+#define DT_NPARAM 452
+#define DT_WBLOB_BYTES 256000
+
+// float parameters (kernel argument = constant bank): offsets
+#define DT_P_W1 0      // [16][9]
+#define DT_P_B1 144
+#define DT_P_B2 160    // scaled
+#define DT_P_B3 192
+#define DT_P_B4 256
+#define DT_P_B5 288
+#define DT_P_W6 304    // [16][9]
+#define DT_P_B6 448
+#define DT_P_S 449
+#define DT_P_INVS 450
+
+// shared memory map
+#define DT_OFF_A14 0                                  // 32 planes: A1s [phase][part][2 groups] / A4s [phase][part][4 groups]
+#define DT_OFF_A2 (32 * DT_PLANE)                     // 8 planes  [part][4 groups]
+#define DT_OFF_A3 (40 * DT_PLANE)                     // 16 planes [part][8 groups]
+#define DT_OFF_W (56 * DT_PLANE)                      // two weight buffers
+#define DT_OFF_IN (DT_OFF_W + 2 * DT_WBUF)            // [G][18][18] float, zero border
+#define DT_OFF_OUT (DT_OFF_IN + DT_G * 324 * 4)       // [G][256] float
+#define DT_OFF_BAR (DT_OFF_OUT + DT_G * 256 * 4)      // mbarriers: w0, w1, mma, cA, cB ; tmem slot
+#define DT_SMEM_BYTES (DT_OFF_BAR + 64)
+
+struct DnTcParams {
+  const float* in;          // [n_spots][256]
+  float* out;               // [n_spots][256] (may alias in)
+  long long n_spots;
+  const uint8_t* wblob;     // DT_WBLOB_BYTES, 16-byte aligned
+  int* err;
+  long long* dbg;           // optional [16]: per-phase clock totals of CTA 0 (development)
+  float prm[DT_NPARAM];
+};
+
+#ifdef DT_DEFINE_KERNELS
+#define DT_WAIT_SPINS (1u << 22)
+
+__device__ __forceinline__ uint32_t dt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool dt_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait (a nanosleep back-off cost up to 0.5 us of wake-up latency per phase here: nine warps, nothing to yield to);
+// on expiry the error word is raised and the kernel traps
+__device__ __forceinline__ void dt_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < DT_WAIT_SPINS; ++it)
+    if (dt_mbar_try(bar, parity)) return;        // try_wait itself suspends the thread for a bounded time
+  atomicExch(err, 5);
+  __threadfence_system();
+  __trap();
+}
+__device__ __forceinline__ bool dt_elect() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+// one weight chunk as 4 KB bulk copies on the same mbarrier: a single 36 KB copy streamed at ~6 B per cycle
+__device__ __forceinline__ void dt_bulk(uint32_t dst, const uint8_t* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#pragma unroll 1
+  for (uint32_t o = 0; o < bytes; o += 4096u) {
+    const uint32_t n = bytes - o < 4096u ? bytes - o : 4096u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst + o), "l"(src + o), "r"(n), "r"(bar) : "memory");
+  }
+}
+__device__ __forceinline__ uint64_t dt_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+__device__ __forceinline__ void dt_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+// The same with the descriptors given as their low words (start address >> 4 | LBO >> 4 << 16); the high word is the
+// constant (SBO = 128 B) >> 4 | version 1 << 14.  A tap / phase / K step is then one add on the low word.
+__device__ __forceinline__ void dt_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, {%6, %6, %6, %6}, p;\n\t}"
+      :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(0x4008u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void dt_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void dt_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void dt_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void dt_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// eight consecutive channels of one position -> the hi and lo planes of their channel group
+__device__ __forceinline__ void dt_store8(uint32_t hi_addr, uint32_t lo_addr, const float* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dt_split2(v[2 * j], v[2 * j + 1], h[j], l[j]);
+  dt_sts128(hi_addr, h[0], h[1], h[2], h[3]);
+  dt_sts128(lo_addr, l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ constexpr int dt_floor2(int a) { return (a + 4) / 2 - 2; }    // floor(a / 2), a >= -4
+// stride-2 4 x 4 transposed convolution, output parity p, tap t: kernel index and input offset
+__device__ __forceinline__ constexpr int dt_ct_k(int p, int t) { return p == 0 ? (t == 0 ? 1 : 3) : (t == 0 ? 0 : 2); }
+__device__ __forceinline__ constexpr int dt_ct_d(int p, int t) { return p == 0 ? (t == 0 ? 0 : -1) : (t == 0 ? 1 : 0); }
+
+// e1 on the CUDA cores: conv3x3 1 -> 16 + relu + pool for this thread's coarse position and channel half, written as
+// the four phase planes of the 8 x 8 map
+template <int H>
+__device__ __forceinline__ void dt_layer1(const DnTcParams& P, const float* img, int Y, int X, uint32_t a1_pos) {
+  float win[6][6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = 0; b < 6; ++b) win[a][b] = img[(4 * Y + a) * 18 + 4 * X + b];
+  float res[4][8];
+  const float S = P.prm[DT_P_S];
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    const int c = 8 * H + cc;
+    float cv[4][4];
+#pragma unroll
+    for (int fy = 0; fy < 4; ++fy)
+#pragma unroll
+      for (int fx = 0; fx < 4; ++fx) cv[fy][fx] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float w = P.prm[DT_P_W1 + c * 9 + ky * 3 + kx];        // one fetch, sixteen independent FMAs
+#pragma unroll
+        for (int fy = 0; fy < 4; ++fy)
+#pragma unroll
+          for (int fx = 0; fx < 4; ++fx) cv[fy][fx] = fmaf(w, win[fy + ky][fx + kx], cv[fy][fx]);
+      }
+    const float b = P.prm[DT_P_B1 + c];
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const float m = fmaxf(fmaxf(cv[2 * py][2 * px], cv[2 * py][2 * px + 1]), fmaxf(cv[2 * py + 1][2 * px], cv[2 * py + 1][2 * px + 1]));
+        res[py * 2 + px][cc] = fmaxf(m + b, 0.f) * S;
+      }
+  }
+#pragma unroll
+  for (int ph = 0; ph < 4; ++ph)
+    dt_store8(a1_pos + ((ph * 2 + 0) * 2 + H) * DT_PLANE, a1_pos + ((ph * 2 + 1) * 2 + H) * DT_PLANE, res[ph]);
+}
+
+// epilogue of e2: max over the four phase accumulators (= 2 x 2 pooling), bias, relu -> A2; this half's 16 channels
+template <int H>
+__device__ __forceinline__ void dt_epi2(const DnTcParams& P, uint32_t tlane, bool real, uint32_t a2_pos) {
+  float m[16], v[16];
+  dt_ld16(tlane + 0 * 32 + 16 * H, m);
+#pragma unroll
+  for (int ph = 1; ph < 4; ++ph) {
+    dt_ld16(tlane + ph * 32 + 16 * H, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], v[j]);
+  }
+  if (real) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j] + P.prm[DT_P_B2 + 16 * H + j], 0.f);
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+      dt_store8(a2_pos + (0 * 4 + 2 * H + g) * DT_PLANE, a2_pos + (1 * 4 + 2 * H + g) * DT_PLANE, m + 8 * g);
+  }
+}
+
+// epilogue of e3: bias, relu -> A3; this half's 32 channels
+template <int H>
+__device__ __forceinline__ void dt_epi3(const DnTcParams& P, uint32_t tlane, bool real, uint32_t a3_pos) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float v[16];
+    dt_ld16(tlane + 128 + 32 * H + 16 * q, v);
+    if (real) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + P.prm[DT_P_B3 + 32 * H + 16 * q + j], 0.f);
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        dt_store8(a3_pos + (0 * 8 + 4 * H + 2 * q + g) * DT_PLANE, a3_pos + (1 * 8 + 4 * H + 2 * q + g) * DT_PLANE, v + 8 * g);
+    }
+  }
+}
+
+// epilogue of d1: the four parity classes are the four phase planes of the 8 x 8 map; this half's two classes
+template <int H>
+__device__ __forceinline__ void dt_epi4(const DnTcParams& P, uint32_t tlane, bool real, uint32_t a4_pos) {
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int cl = 2 * H + cc;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float v[16];
+      dt_ld16(tlane + 192 + cl * 32 + 16 * q, v);
+      if (real) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + P.prm[DT_P_B4 + 16 * q + j], 0.f);
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          dt_store8(a4_pos + ((cl * 2 + 0) * 4 + 2 * q + g) * DT_PLANE, a4_pos + ((cl * 2 + 1) * 4 + 2 * q + g) * DT_PLANE, v + 8 * g);
+      }
+    }
+  }
+}
+
+// epilogue of d2 + d3: this half holds the fine rows fy = 2 H, 2 H + 1 of its 4 x 4 block (8 fine pixels x 16 channels);
+// every fine pixel adds its nine taps of the transposed 3 x 3 convolution into a 4 x 6 window of partial sums, which is
+// then added to the output image of the spot
+template <int H>
+__device__ __forceinline__ void dt_epi5(const DnTcParams& P, uint32_t tlane, bool real, float* out_img, int Y, int X) {
+  // all eight fine pixels first (128 values), then every d3 weight is fetched once and feeds eight independent FMAs
+  // (the first form walked the pixels one by one: 1152 constant loads per thread, each at the head of a dependent chain)
+  float v[8][16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dt_ld16(tlane + (H * 8 + i) * 16, v[i]);       // i = (px, qy, qx)
+  if (!real) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[i][j] = fmaxf(v[i][j] + P.prm[DT_P_B5 + j], 0.f);
+  float wnd[4][6];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 6; ++b) wnd[a][b] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float w = P.prm[DT_P_W6 + j * 9 + ky * 3 + kx];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i][j], w, acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int px = i >> 2, qy = (i >> 1) & 1, qx = i & 1;
+        wnd[qy + ky][2 * px + qx + kx] += acc[i];
+      }
+    }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int row = 4 * Y + 2 * H + a - 1;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      const int col = 4 * X + b - 1;
+      if (row >= 0 && row < 16 && col >= 0 && col < 16) atomicAdd(out_img + row * 16 + col, wnd[a][b]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_constant__ DnTcParams P) {
+  extern __shared__ __align__(128) uint8_t dt_sm[];
+  const uint32_t sb = dt_smem_u32(dt_sm);
+  // warp index through a shuffle and the issuing lane through elect.sync: the compiler then knows the control path is
+  // warp-uniform and keeps the UMMA descriptors in uniform registers (UTCHMMA back to back); with `lane == 0` every MMA
+  // sat in a per-thread waterfall loop (ELECT / R2UR / BRA.U.ANY, ~13 instructions and ~160 cycles per MMA)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = tid & 31;
+  const uint32_t bar_w0 = sb + DT_OFF_BAR, bar_w1 = bar_w0 + 8, bar_mma = bar_w0 + 16, bar_ca = bar_w0 + 24, bar_cb = bar_w0 + 32;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(dt_sm + DT_OFF_BAR + 40);
+
+  for (int i = tid; i < DT_OFF_W / 16; i += DT_THREADS) reinterpret_cast<uint4*>(dt_sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < (DT_OFF_BAR - DT_OFF_IN) / 4; i += DT_THREADS) reinterpret_cast<float*>(dt_sm + DT_OFF_IN)[i] = 0.f;
+  if (tid == 0) {
+    for (int b = 0; b < 5; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_w0 + 8 * b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + DT_OFF_BAR + 40), "r"((uint32_t)DT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const long long n_pass = (P.n_spots + DT_G - 1) / DT_G;
+  const bool w8 = warp == 8;      // the issuing lane is re-elected at every control block (see above)
+  const uint32_t wb0 = sb + DT_OFF_W, wb1 = wb0 + DT_WBUF;
+  // mbarrier phases: each weight buffer completes four chunks per pass and bar_ca two, so their parities are fixed per
+  // use; bar_cb completes once per pass, bar_mma four times (tracked by every thread)
+  uint32_t pm = 0, pcb = 0;
+
+  // this thread's coarse position (epilogue warps): TMEM lane m = UMMA row = linear position q
+  const int m = 32 * (warp & 3) + lane, half = (warp >> 2) & 1;
+  const int r = m / DT_PITCH, c = m - r * DT_PITCH;
+  const int s = r >= 1 ? (r - 1) / 5 : 0, Y = r >= 1 ? (r - 1) % 5 : 4, X = c - 1;
+  const bool is_pos = warp < 8 && r >= 1 && c >= 1 && Y < 4 && s < DT_G;
+  const uint32_t tlane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+  const uint32_t pos_off = (uint32_t)(DT_LEAD + m) * 16;
+  float* img_in = reinterpret_cast<float*>(dt_sm + DT_OFF_IN);
+  float* img_out = reinterpret_cast<float*>(dt_sm + DT_OFF_OUT);
+
+  if (w8 && (long long)blockIdx.x < n_pass && dt_elect()) {
+    dt_bulk(wb0, P.wblob + 0, 18432, bar_w0);
+    dt_bulk(wb1, P.wblob + 18432, 36864, bar_w1);
+  }
+
+  const uint32_t ID16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t ID32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t ID64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+  // descriptor low words in 16-byte units, warp-uniform: start address >> 4 | LBO >> 4 << 16.  Position shift s = +s,
+  // plane p = +p * PQ, weight offset o bytes = +o / 16.
+  const uint32_t sbq = __shfl_sync(0xffffffffu, sb >> 4, 0);
+  constexpr uint32_t PQ = DT_PLANE >> 4;
+  const uint32_t A14 = sbq + (DT_OFF_A14 >> 4) + DT_LEAD + (PQ << 16);
+  const uint32_t A2 = sbq + (DT_OFF_A2 >> 4) + DT_LEAD + (PQ << 16);
+  const uint32_t A3 = sbq + (DT_OFF_A3 >> 4) + DT_LEAD + (PQ << 16);
+  const uint32_t wq0 = sbq + (DT_OFF_W >> 4), wq1 = wq0 + (DT_WBUF >> 4);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+
+  long long tacc[12], tprev = 0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) tacc[i] = 0;
+#define DT_TICK(i) if (P.dbg) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
+#pragma unroll 1
+  for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+    if (P.dbg) tprev = clock64();
+    const long long spot0 = pass * DT_G;
+    const int ns = (int)((P.n_spots - spot0) < DT_G ? (P.n_spots - spot0) : DT_G);
+    const bool has_next = pass + gridDim.x < n_pass;
+    const bool real = is_pos && s < ns;
+
+    // ---- input spots -> padded images; e1 -> A1s
+    if (warp < 8) {
+      for (int i = tid; i < ns * 256; i += 256) {
+        const int sp = i >> 8, px = i & 255;
+        img_in[sp * 324 + (1 + (px >> 4)) * 18 + 1 + (px & 15)] = __ldg(P.in + (spot0 + sp) * 256 + px);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (real) {
+        if (half == 0) dt_layer1<0>(P, img_in + s * 324, Y, X, sb + DT_OFF_A14 + pos_off);
+        else dt_layer1<1>(P, img_in + s * 324, Y, X, sb + DT_OFF_A14 + pos_off);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DT_TICK(0)
+
+    // ---- e2: four output phases x nine taps, K = 16
+    if (w8 && dt_elect()) {
+      dt_mbar_wait(bar_w0, 0u, P.err);
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const int iph = ((py + dy) & 1) * 2 + ((px + dx) & 1);
+          const int sh = dt_floor2(py + dy) * DT_PITCH + dt_floor2(px + dx);
+          const uint32_t a_hi = A14 + ((iph * 2 + 0) * 2) * PQ + sh, a_lo = A14 + ((iph * 2 + 1) * 2) * PQ + sh;
+          const uint32_t b_hi = wq0 + tap * 128 + (32u << 16), b_lo = b_hi + 64;
+          const uint32_t d = tmem_u + ph * 32;
+          dt_mma2(d, a_hi, b_hi, ID32, tap ? 1u : 0u);
+          dt_mma2(d, a_lo, b_hi, ID32, 1u);
+          dt_mma2(d, a_hi, b_lo, ID32, 1u);
+        }
+      }
+      dt_commit(bar_mma);
+    }
+    dt_mbar_wait(bar_mma, pm, P.err);
+    pm ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DT_TICK(1)
+    if (w8 && dt_elect()) dt_bulk(wb0, P.wblob + 55296, 36864, bar_w0);                  // e3 low parts
+    if (warp < 8) {
+      if (half == 0) dt_epi2<0>(P, tlane, real, sb + DT_OFF_A2 + pos_off);
+      else dt_epi2<1>(P, tlane, real, sb + DT_OFF_A2 + pos_off);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DT_TICK(2)
+
+    // ---- e3: nine taps, K = 32; high weight parts from buffer 1, low parts from buffer 0
+    if (w8 && dt_elect()) {
+      dt_mbar_wait(bar_w1, 0u, P.err);
+      const uint32_t d = tmem_u + 128;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int sh = (tap / 3 - 1) * DT_PITCH + tap % 3 - 1;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint32_t a_hi = A2 + (0 * 4 + 2 * ks) * PQ + sh, a_lo = A2 + (1 * 4 + 2 * ks) * PQ + sh;
+          const uint32_t b = wq1 + tap * 256 + ks * 128 + (64u << 16);
+          dt_mma2(d, a_hi, b, ID64, (tap | ks) ? 1u : 0u);
+          dt_mma2(d, a_lo, b, ID64, 1u);
+        }
+      }
+      dt_mbar_wait(bar_w0, 1u, P.err);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int sh = (tap / 3 - 1) * DT_PITCH + tap % 3 - 1;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          dt_mma2(d, A2 + (2 * ks) * PQ + sh, wq0 + tap * 256 + ks * 128 + (64u << 16), ID64, 1u);
+      }
+      dt_commit(bar_mma);
+    }
+    dt_mbar_wait(bar_mma, pm, P.err);
+    pm ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DT_TICK(3)
+    if (w8 && dt_elect()) {
+      dt_bulk(wb1, P.wblob + 92160, 32768, bar_w1);                           // d1 class 0
+      dt_bulk(wb0, P.wblob + 124928, 32768, bar_w0);                          // d1 class 1
+    }
+    if (warp < 8) {
+      if (half == 0) dt_epi3<0>(P, tlane, real, sb + DT_OFF_A3 + pos_off);
+      else dt_epi3<1>(P, tlane, real, sb + DT_OFF_A3 + pos_off);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DT_TICK(4)
+
+    // ---- d1: four parity classes x four taps, K = 64; one weight chunk per class
+    if (w8 && dt_elect()) {
+#pragma unroll
+      for (int cl = 0; cl < 4; ++cl) {
+        const int py = cl >> 1, px = cl & 1;
+        const uint32_t wq = (cl & 1) ? wq0 : wq1;
+        dt_mbar_wait((cl & 1) ? bar_w0 : bar_w1, (cl & 1) ? (uint32_t)(cl >> 1) : (uint32_t)(1 - (cl >> 1)), P.err);
+        const uint32_t d = tmem_u + 192 + cl * 32;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int sh = dt_ct_d(py, t >> 1) * DT_PITCH + dt_ct_d(px, t & 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a_hi = A3 + (0 * 8 + 2 * ks) * PQ + sh, a_lo = A3 + (1 * 8 + 2 * ks) * PQ + sh;
+            const uint32_t b_hi = wq + t * 512 + ks * 64 + (32u << 16), b_lo = b_hi + 256;
+            dt_mma2(d, a_hi, b_hi, ID32, (t | ks) ? 1u : 0u);
+            dt_mma2(d, a_lo, b_hi, ID32, 1u);
+            dt_mma2(d, a_hi, b_lo, ID32, 1u);
+          }
+        }
+        if (cl == 0) dt_commit(bar_ca);
+        if (cl == 1) {
+          dt_commit(bar_cb);
+          dt_mbar_wait(bar_ca, 0u, P.err);
+          dt_bulk(wb1, P.wblob + 157696, 32768, bar_w1);                      // class 2
+          dt_mbar_wait(bar_cb, pcb, P.err);
+          dt_bulk(wb0, P.wblob + 190464, 32768, bar_w0);                      // class 3
+        }
+        if (cl == 2) dt_commit(bar_ca);
+        if (cl == 3) {
+          dt_commit(bar_mma);
+          dt_mbar_wait(bar_ca, 1u, P.err);
+          dt_bulk(wb1, P.wblob + 223232, 32768, bar_w1);                      // d2
+        }
+      }
+    }
+    dt_mbar_wait(bar_mma, pm, P.err);
+    pm ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    pcb ^= 1;
+    DT_TICK(5)
+    if (w8 && has_next && dt_elect()) dt_bulk(wb0, P.wblob + 0, 18432, bar_w0);           // next pass: e2
+    if (warp < 8) {
+      if (half == 0) dt_epi4<0>(P, tlane, real, sb + DT_OFF_A14 + pos_off);
+      else dt_epi4<1>(P, tlane, real, sb + DT_OFF_A14 + pos_off);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DT_TICK(6)
+
+    // ---- d2: sixteen (input phase, output parity) classes x four taps, K = 32
+    if (w8 && dt_elect()) {
+      dt_mbar_wait(bar_w1, 1u, P.err);
+#pragma unroll
+      for (int sc = 0; sc < 16; ++sc) {
+        const int py = sc >> 3, px = (sc >> 2) & 1, qy = (sc >> 1) & 1, qx = sc & 1;
+        const uint32_t d = tmem_u + sc * 16;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int ky = dt_ct_k(qy, t >> 1), dy = dt_ct_d(qy, t >> 1), kx = dt_ct_k(qx, t & 1), dx = dt_ct_d(qx, t & 1);
+          const int iph = ((py + dy) & 1) * 2 + ((px + dx) & 1);
+          const int sh = dt_floor2(py + dy) * DT_PITCH + dt_floor2(px + dx);
+          const uint32_t bt = wq1 + (ky * 4 + kx) * 128 + (16u << 16);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t a_hi = A14 + ((iph * 2 + 0) * 4 + 2 * ks) * PQ + sh, a_lo = A14 + ((iph * 2 + 1) * 4 + 2 * ks) * PQ + sh;
+            const uint32_t b_hi = bt + ks * 32, b_lo = b_hi + 64;
+            dt_mma2(d, a_hi, b_hi, ID16, (t | ks) ? 1u : 0u);
+            dt_mma2(d, a_lo, b_hi, ID16, 1u);
+            dt_mma2(d, a_hi, b_lo, ID16, 1u);
+          }
+        }
+      }
+      dt_commit(bar_mma);
+    }
+    dt_mbar_wait(bar_mma, pm, P.err);
+    pm ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DT_TICK(7)
+    if (w8 && has_next && dt_elect()) dt_bulk(wb1, P.wblob + 18432, 36864, bar_w1);       // next pass: e3 high parts
+    if (warp < 8) {
+      if (half == 0) dt_epi5<0>(P, tlane, real, img_out + s * 256, Y, X);
+      else dt_epi5<1>(P, tlane, real, img_out + s * 256, Y, X);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float invs = P.prm[DT_P_INVS], b6 = P.prm[DT_P_B6];
+      for (int i = tid; i < ns * 256; i += 256) {
+        const float v = img_out[i];
+        img_out[i] = 0.f;
+        P.out[spot0 * 256 + i] = fmaf(v, invs, b6);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DT_TICK(8)
+  }
+  if (P.dbg && blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 12; ++i) P.dbg[i] = tacc[i];
+
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)DT_TMEM_COLS) : "memory");
+}
+#endif  // DT_DEFINE_KERNELS

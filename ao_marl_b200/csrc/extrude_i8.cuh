@@ -278,6 +278,26 @@ __device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
   return d;
 }
 
+// one lane of a converged warp.  With the warp index taken through a shuffle and the lane through elect.sync the compiler
+// knows the issuing path is warp-uniform and keeps descriptors in uniform registers; under `lane == 0` every MMA sat in a
+// per-thread waterfall loop (ELECT / R2UR / BRA.U.ANY, ~13 instructions per MMA; measured on the denoiser kernel).
+__device__ __forceinline__ bool oz_elect() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
+// descriptors given as low words (start address >> 4 | LBO 128 B >> 4 << 16); high word = SBO 256 B >> 4 | version
+__device__ __forceinline__ void oz_mma_i8_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, {%6, %6, %6, %6}, p;\n\t}"
+      :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"((256u >> 4) | (1u << 14)), "r"(0u) : "memory");
+}
+
 __device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -297,7 +317,7 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
 template <int EPI>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) {
   extern __shared__ __align__(1024) uint8_t oz_smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = tid & 31;
   const int nt = blockIdx.x, mt = blockIdx.y;
   uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + OZ_STAGES * OZ_STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * OZ_STAGES + 1);
@@ -316,10 +336,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (oz_elect()) {
       const uint8_t* za = p.Zs + (size_t)mt * p.KB * OZ_SLICES * OZ_A_TILE;
       const uint8_t* ab = p.ABs + (size_t)nt * p.KB * OZ_SLICES_B * OZ_B_TILE;
       for (int kb = 0; kb < p.KB; ++kb) {
@@ -336,7 +356,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (oz_elect()) {
       // int8 x int8 -> int32: c_format S32 (2), a / b format signed 8 bit (1), K-major operands, N 96, M 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
       uint32_t used = 0;                                      // bit g: accumulator g has been written
@@ -345,15 +365,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) 
         const uint32_t round = (uint32_t)(kb / OZ_STAGES);
         oz_mbar_wait(full0 + 8 * s, round & 1u, p.err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = oz_smem_u32(oz_smem + (size_t)s * OZ_STAGE_BYTES), b0 = a0 + OZ_SLICES * OZ_A_TILE;
+        const uint32_t a0 = ((oz_smem_u32(oz_smem) + (uint32_t)s * OZ_STAGE_BYTES) >> 4) | ((128u >> 4) << 16);
+        const uint32_t b0 = a0 + (OZ_SLICES * OZ_A_TILE >> 4);
 #pragma unroll
         for (int g = 0; g < OZ_LEVELS; ++g)
 #pragma unroll
           for (int sa = 0; sa < OZ_SLICES; ++sa) {
             const int sb = g - sa;
             if (sb < 0 || sb >= OZ_SLICES_B || sa >= OZ_SLICES) continue;
-            oz_mma_i8(tmem_base + (uint32_t)(g * OZ_BN), oz_desc(a0 + sa * OZ_A_TILE), oz_desc(b0 + sb * OZ_B_TILE), idesc,
-                      (used >> g) & 1u);
+            oz_mma_i8_lo(tmem_base + (uint32_t)(g * OZ_BN), a0 + sa * (OZ_A_TILE >> 4), b0 + sb * (OZ_B_TILE >> 4), idesc,
+                         (used >> g) & 1u);
             used |= 1u << g;
           }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s) : "memory");

@@ -88,6 +88,23 @@ __device__ __forceinline__ void gtc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, u
       : "memory");
 }
 
+// descriptors as low words (start >> 4 | LBO 128 B >> 4 << 16); high word = SBO 512 B >> 4 | version.  Together with
+// elect.sync on a shuffled warp index this keeps the issue path in uniform registers (no per-MMA waterfall loop).
+__device__ __forceinline__ void gtc_mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, {%6, %6, %6, %6}, p;\n\t}"
+      :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"((512u >> 4) | (1u << 14)), "r"(0u) : "memory");
+}
+__device__ __forceinline__ bool gtc_elect() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
 __device__ __forceinline__ void gtc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -110,7 +127,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
   constexpr int B_ITERS = (BN + 31) / 32;
   constexpr uint32_t TMEM_COLS = BN <= 128 ? 128u : 256u;
   extern __shared__ __align__(1024) uint8_t gtc_smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = tid & 31;
   const int bz = blockIdx.z;
   const float* __restrict__ A = p.A + (long long)bz * p.sA;
   const float* __restrict__ B = p.B + (long long)bz * p.sB;
@@ -141,7 +158,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp < 4) {
     // ===== loaders =====
@@ -252,8 +269,8 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else if (lane == 0) {
-    // ===== MMA issuer (one thread) =====
+  } else if (gtc_elect()) {
+    // ===== MMA issuer (one elected lane of warp 4) =====
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(GTC_BM >> 4) << 24);
     for (int kb = 0; kb < nkb; ++kb) {
@@ -261,15 +278,15 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
       const uint32_t round = (uint32_t)(kb / GTC_STAGES);
       gtc_mbar_wait(full0 + 8 * s, round & 1u, err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t base = gtc_smem_u32(tiles + (size_t)s * STAGE_BYTES);
+      const uint32_t base = ((gtc_smem_u32(tiles) + (uint32_t)s * STAGE_BYTES) >> 4) | ((128u >> 4) << 16);
 #pragma unroll
       for (int k8 = 0; k8 < GTC_BK / 8; ++k8) {
-        const uint32_t ko = (uint32_t)k8 * 256u;                 // two 16-byte chunks = 8 tf32 values
-        const uint64_t a_hi = gtc_desc(base + ko), a_lo = gtc_desc(base + GTC_TILE_BYTES + ko);
-        const uint64_t b_hi = gtc_desc(base + B_OFF + ko), b_lo = gtc_desc(base + B_OFF + GTC_BTILE_BYTES(BN) + ko);
-        gtc_mma_tf32(tmem_base, a_hi, b_hi, idesc, (kb | k8) ? 1u : 0u);
-        gtc_mma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-        gtc_mma_tf32(tmem_base, a_lo, b_hi, idesc, 1u);
+        const uint32_t ko = (uint32_t)k8 * 16u;                  // two 16-byte chunks = 8 tf32 values
+        const uint32_t a_hi = base + ko, a_lo = base + (GTC_TILE_BYTES >> 4) + ko;
+        const uint32_t b_hi = base + (B_OFF >> 4) + ko, b_lo = base + ((B_OFF + GTC_BTILE_BYTES(BN)) >> 4) + ko;
+        gtc_mma_tf32_lo(tmem_base, a_hi, b_hi, idesc, (kb | k8) ? 1u : 0u);
+        gtc_mma_tf32_lo(tmem_base, a_hi, b_lo, idesc, 1u);
+        gtc_mma_tf32_lo(tmem_base, a_lo, b_hi, idesc, 1u);
       }
       gtc_commit(empty0 + 8 * s);                                // stage reusable once these MMAs have read it
     }

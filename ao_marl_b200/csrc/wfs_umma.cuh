@@ -135,6 +135,31 @@ __device__ __forceinline__ void wu_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       : "memory");
 }
 
+// the same with descriptor low words (start >> 4 | LBO >> 4 << 16) and the constant high word (SBO >> 4 | version) apart
+__device__ __forceinline__ void wu_mma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, {%6, %6, %6, %6}, p;\n\t}"
+      :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi), "r"(0u) : "memory");
+}
+// separate high words for A and B (the MN-major stage-2 operand has its own stride field)
+__device__ __forceinline__ void wu_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, {%7, %7, %7, %7}, p;\n\t}"
+      :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(b_hi), "r"(0u) : "memory");
+}
+__device__ __forceinline__ bool wu_elect() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void wu_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -248,7 +273,7 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = s_cnt[2];
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_cnt[2], 0);
 
   unsigned char* my_tiles = s_tiles + (size_t)warp * NLS * WU_TILE_STRIDE;
   const uint32_t my_tiles_u32 = wu_smem_u32(my_tiles);
@@ -385,48 +410,53 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
   // ---- lane 0 of the last warp to arrive issues the tensor-core work of the group ----
   const uint32_t idesc1 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
   const uint32_t idesc2 = idesc1 | (1u << 15);                                                      // A operand MN-major
+  // The arrival count is broadcast through a shuffle and the issuing lane chosen by elect.sync, so that the issue path is
+  // warp-uniform for the compiler (descriptors in uniform registers, UTCHMMA back to back; under `lane == 0` every MMA
+  // sat in a per-thread waterfall loop of ~13 instructions).
+  const uint32_t q_a1 = __shfl_sync(0xffffffffu, wu_smem_u32(s_a1) >> 4, 0), q_b1 = __shfl_sync(0xffffffffu, wu_smem_u32(s_b1) >> 4, 0);
+  const uint32_t q_a2 = __shfl_sync(0xffffffffu, wu_smem_u32(s_a2) >> 4, 0), q_b2 = __shfl_sync(0xffffffffu, wu_smem_u32(s_b2) >> 4, 0);
   auto arrive_and_issue = [&](int which) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
+    uint32_t old = 0;
     if (lane == 0) {
       __threadfence_block();
-      const uint32_t old = atomicAdd(&s_cnt[which], 1u);
-      if ((old & (WU_WARPS - 1)) == WU_WARPS - 1) {
+      old = atomicAdd(&s_cnt[which], 1u);
+    }
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if ((old & (WU_WARPS - 1)) == WU_WARPS - 1) {
+      if (wu_elect()) {
         __threadfence_block();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        constexpr uint32_t KM = (128u >> 4) << 16, HI = (512u >> 4) | (1u << 14);     // K-major: LBO 128, SBO 512
         if (which == 0) {
-          const uint32_t a_hi = wu_smem_u32(s_a1), a_lo = a_hi + WU_A_BYTES;
-          const uint32_t b_hi = wu_smem_u32(s_b1), b_lo = b_hi + WU_B_BYTES;
+          const uint32_t a_hi = q_a1 + KM, a_lo = a_hi + (WU_A_BYTES >> 4);
+          const uint32_t b_hi = q_b1 + KM, b_lo = b_hi + (WU_B_BYTES >> 4);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            wu_mma_f16(tmem_base, wu_desc(a_hi + ks * 256, 128, 512), wu_desc(b_hi + ks * 256, 128, 512), idesc1, ks ? 1u : 0u);
+          for (int ks = 0; ks < 2; ++ks) wu_mma_f16_lo(tmem_base, a_hi + ks * 16, b_hi + ks * 16, HI, idesc1, ks ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            wu_mma_f16(tmem_base, wu_desc(a_lo + ks * 256, 128, 512), wu_desc(b_hi + ks * 256, 128, 512), idesc1, 1u);
+          for (int ks = 0; ks < 2; ++ks) wu_mma_f16_lo(tmem_base, a_lo + ks * 16, b_hi + ks * 16, HI, idesc1, 1u);
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            wu_mma_f16(tmem_base, wu_desc(a_hi + ks * 256, 128, 512), wu_desc(b_lo + ks * 256, 128, 512), idesc1, 1u);
+          for (int ks = 0; ks < 2; ++ks) wu_mma_f16_lo(tmem_base, a_hi + ks * 16, b_lo + ks * 16, HI, idesc1, 1u);
           wu_commit(mma1_bar);
         } else {
-          const uint32_t b_hi = wu_smem_u32(s_b2), b_lo = b_hi + WU_B_BYTES;
+          const uint32_t b_hi = q_b2 + KM, b_lo = b_hi + (WU_B_BYTES >> 4);
           const uint32_t lbo = f.a2_swap ? 512u : 128u, sbo = f.a2_swap ? 128u : 512u;
+          const uint32_t am = (lbo >> 4) << 16, hia = (sbo >> 4) | (1u << 14);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const uint32_t a_hi = wu_smem_u32(s_a2) + j * 2 * WU_A_BYTES, a_lo = a_hi + WU_A_BYTES;
+            const uint32_t a_hi = q_a2 + j * (2 * WU_A_BYTES >> 4) + am, a_lo = a_hi + (WU_A_BYTES >> 4);
             const uint32_t d = tmem_base + 64u + 64u * j;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              wu_mma_f16(d, wu_desc(a_hi + ks * 256, lbo, sbo), wu_desc(b_hi + ks * 256, 128, 512), idesc2, ks ? 1u : 0u);
+            for (int ks = 0; ks < 2; ++ks) wu_mma2(d, a_hi + ks * 16, hia, b_hi + ks * 16, HI, idesc2, ks ? 1u : 0u);
             if (FULL) {
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks)
-                wu_mma_f16(d, wu_desc(a_lo + ks * 256, lbo, sbo), wu_desc(b_hi + ks * 256, 128, 512), idesc2, 1u);
+              for (int ks = 0; ks < 2; ++ks) wu_mma2(d, a_lo + ks * 16, hia, b_hi + ks * 16, HI, idesc2, 1u);
             }
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              wu_mma_f16(d, wu_desc(a_hi + ks * 256, lbo, sbo), wu_desc(b_lo + ks * 256, 128, 512), idesc2, 1u);
+            for (int ks = 0; ks < 2; ++ks) wu_mma2(d, a_hi + ks * 16, hia, b_lo + ks * 16, HI, idesc2, 1u);
           }
           wu_commit(mma2_bar);
         }

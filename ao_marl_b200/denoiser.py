@@ -69,6 +69,61 @@ def pack_weights(state_dict):
     return out
 
 
+# ---- tensor-core form of the same network (csrc/denoise_tc.cuh) -------------------------------------------------------
+# Geometry shared with the kernel: G spots per pass on a 4 x 4 coarse grid with a shared pad row / column (pitch 5), every
+# finer map stored space-to-depth on that grid; activations scaled by SCALE (a power of two: exact) so that fp16 hi / lo
+# operands cannot overflow on bright spots.  CT_TAPS[parity] = the two (kernel index, input offset) pairs a stride-2
+# 4 x 4 transposed convolution uses for an output row / column of that parity.
+DT = dict(G=5, PITCH=5, LEAD=8, NPOS=144, SCALE=2.0 ** -4, CT_TAPS=(((1, 0), (3, -1)), ((0, 1), (2, 0))),
+          CHUNKS=(0, 18432, 55296, 92160, 124928, 157696, 190464, 223232, 256000), NPARAM=452)
+
+
+def _tile_f16(w_nk):
+    """[N][K] float -> (hi, lo) fp16 tiles in the UMMA K-major core-matrix order [K / 8][N][8]."""
+    w = np.asarray(w_nk, np.float32)
+    hi = w.astype(np.float16)
+    lo = (w - hi.astype(np.float32)).astype(np.float16)
+    n, k = w.shape
+    order = lambda t: np.ascontiguousarray(t.reshape(n, k // 8, 8).transpose(1, 0, 2)).reshape(-1)
+    return order(hi), order(lo)
+
+
+def pack_weights_tc(state_dict, as_float=False):
+    """Weight tiles of the four tensor-core layers in the order the kernel streams them, and the float parameters of the
+    two SIMT layers + the (scaled) biases.  as_float: float64 tiles as a dict (profiles/dev/denoise_tc_model.py)."""
+    sd = {k: np.asarray(v.detach().cpu() if hasattr(v, "detach") else v, dtype=np.float32) for k, v in state_dict.items()}
+    S, ct = DT["SCALE"], DT["CT_TAPS"]
+    e2, e3, d1, d2 = sd["encoder2.weight"], sd["encoder3.weight"], sd["decoder1.weight"], sd["decoder2.weight"]
+    L2 = [e2[:, :, ky, kx] for ky in range(3) for kx in range(3)]                       # [n = co][k = ci]
+    L3 = [e3[:, :, ky, kx] for ky in range(3) for kx in range(3)]
+    L4 = [[d1[:, :, ct[py][ty][0], ct[px][tx][0]].T for ty in range(2) for tx in range(2)]
+          for py in range(2) for px in range(2)]                                        # ConvTranspose2d: [ci][co] -> [co][ci]
+    L5 = [d2[:, :, ky, kx].T for ky in range(4) for kx in range(4)]
+    if as_float:
+        f = lambda t: np.asarray(t, np.float64)
+        return dict(L2=[f(t) for t in L2], L3=[f(t) for t in L3], L4=[[f(t) for t in c] for c in L4], L5=[f(t) for t in L5],
+                    b2=f(sd["encoder2.bias"]) * S, b3=f(sd["encoder3.bias"]) * S, b4=f(sd["decoder1.bias"]) * S,
+                    b5=f(sd["decoder2.bias"]) * S)
+    parts = []
+    for t in L2:
+        parts += list(_tile_f16(t))
+    parts += [_tile_f16(t)[0] for t in L3] + [_tile_f16(t)[1] for t in L3]
+    for c in L4:
+        for t in c:
+            parts += list(_tile_f16(t))
+    for t in L5:
+        parts += list(_tile_f16(t))
+    blob = np.concatenate(parts)
+    assert blob.nbytes == DT["CHUNKS"][-1], blob.nbytes
+    prm = np.concatenate([sd["encoder1.weight"].reshape(16, 9).reshape(-1), sd["encoder1.bias"],
+                          sd["encoder2.bias"] * S, sd["encoder3.bias"] * S, sd["decoder1.bias"] * S, sd["decoder2.bias"] * S,
+                          sd["decoder3.weight"].reshape(16, 9).reshape(-1), sd["decoder3.bias"].reshape(1),
+                          np.array([S, 1.0 / S], np.float32)]).astype(np.float32)
+    out = np.zeros(DT["NPARAM"], np.float32)
+    out[:prm.size] = prm
+    return blob.view(np.uint16), out
+
+
 def load_weights(name_or_path):
     """state_dict from a reference checkpoint (torch.save of model.state_dict()) or a shipped .npz export."""
     path = name_or_path
@@ -100,7 +155,7 @@ class Autoencoder:
 
     def attach(self, sim):
         """Route `predict` through the fused CUDA kernel of this simulator context (uploads the packed parameters)."""
-        sim.set_denoiser(pack_weights(self.model.state_dict()))
+        sim.set_denoiser(pack_weights(self.model.state_dict()), pack_weights_tc(self.model.state_dict()))
         self.sim = sim
 
     @torch.no_grad()

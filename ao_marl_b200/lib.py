@@ -41,13 +41,13 @@ class AomConfig(ctypes.Structure):
 TABLES = ["AB", "STENCIL", "MPUPIL", "HALFXY", "SUB_X0", "SUB_Y0", "FLUX", "STAMP1D", "ACT_MAP", "TT_PLANES",
           "CMAT", "V2M", "M2V", "FREEDOM", "ACTION_MAP", "STATE_MAP", "NORM_DM_MEAN", "NORM_DM_STD",
           "NORM_RES_MEAN", "NORM_RES_STD", "AGENT_IDX", "AGENT_ACT", "AGENT_REWARD", "ACTOR_W1", "ACTOR_B1",
-          "ACTOR_W2", "ACTOR_B2", "ACTOR_WH", "ACTOR_BH", "GEO_PROJ", "GEO_SIFN", "DENOISER"]
+          "ACTOR_W2", "ACTOR_B2", "ACTOR_WH", "ACTOR_BH", "GEO_PROJ", "GEO_SIFN", "DENOISER", "DENOISER_TC"]
 T = {name: i for i, name in enumerate(TABLES)}
 BUFFERS = ["SCREEN", "RING_OX", "RING_OY", "SLOPES", "ERR", "COM", "VOLTS", "BINCUBE", "PHASE", "MODES",
            "RES_MODES", "STATE", "REWARD", "ACTION", "ACTION_MEAN", "STREHL", "GEO_COM", "GEO_VOLTS", "STREHL_GEO", "GEO_PROJ"]
 B = {name: i for i, name in enumerate(BUFFERS)}
 _INT_BUFFERS = {"RING_OX", "RING_OY"}
-OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH", "KEEP_IMAGE", "STREHL", "STREHL_LAMBDA_NM", "EXTRUDE_PATH", "STREHL_PEAK", "PSF_NFFT"]
+OPTIONS = ["WFS_PATH", "GEMM_PATH", "TIME_WFS", "GEO", "DENOISE", "PUPIL_PATH", "KEEP_IMAGE", "STREHL", "STREHL_LAMBDA_NM", "EXTRUDE_PATH", "STREHL_PEAK", "PSF_NFFT", "DENOISE_PATH"]
 O = {name: i for i, name in enumerate(OPTIONS)}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
@@ -453,9 +453,18 @@ class Simulator:
     def reset_strehl(self):
         self._check(self.lib.aom_reset_strehl(self._ctx, self.stream), "aom_reset_strehl")
 
-    def set_denoiser(self, packed):
-        """Upload the denoiser's parameters (ao_marl_b200.denoiser.pack_weights)."""
+    def set_denoiser(self, packed, packed_tc=None):
+        """Upload the denoiser's parameters (ao_marl_b200.denoiser.pack_weights; packed_tc = pack_weights_tc's
+        (weight tiles, float parameters) for the tensor-core kernel)."""
         self.set_table("DENOISER", np.asarray(packed, dtype=np.float32))
+        if packed_tc is not None:
+            tiles, prm = packed_tc
+            blob = np.concatenate([np.asarray(prm, np.float32).view(np.uint8), np.asarray(tiles, np.uint16).view(np.uint8)])
+            self.set_table("DENOISER_TC", blob)
+
+    def set_denoise_path(self, name):
+        """'tcgen05' (default) or 'simt' (float32 FFMA cross-check kernel)."""
+        self._check(self.lib.aom_set_option(self._ctx, O["DENOISE_PATH"], {"tcgen05": 0, "simt": 1}[name]), "aom_set_option")
 
     def denoise(self, cube=None, out=None):
         """Fused CNN denoiser.  cube None: the last frame's detector cube, in place, feeding the next do_centroids;

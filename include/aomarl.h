@@ -119,6 +119,9 @@ typedef enum aom_table {
   AOM_T_GEO_SIFN,      /* float [nactu]        pupil sum of each influence row / number of pupil points           */
   AOM_T_DENOISER,      /* float [64452]        parameters of the per-subaperture denoiser, packed per layer as
                                                [input channel][tap][output channel] + bias (autoencoder_models.py:130-197) */
+  AOM_T_DENOISER_TC,   /* [452 float][256000 B] the same denoiser for the tensor-core kernel: float parameters of the two
+                                               CUDA-core layers and the scaled biases, then the fp16 hi / lo weight tiles of
+                                               the four tcgen05 layers in streaming order (denoiser.py::pack_weights_tc) */
   AOM_T_COUNT
 } aom_table;
 
@@ -168,12 +171,18 @@ typedef enum aom_option {
   AOM_OPT_EXTRUDE_PATH, /* which contraction serves the screen extrusion (aom_move_atmos / aom_reset) */
   AOM_OPT_STREHL_PEAK,  /* != 0: every aom_comp_strehl (and AOM_OPT_STREHL inside aom_step) behaves as with AOM_TAR_PEAK */
   AOM_OPT_PSF_NFFT,     /* size of the target's zero-padded focal grid (p_geom._ipupil: 2^ceil(log2(pupdiam) + 1)) */
+  AOM_OPT_DENOISE_PATH, /* AOM_DENOISE_TCGEN05 (default when AOM_T_DENOISER_TC is uploaded) or AOM_DENOISE_SIMT */
   AOM_OPT_COUNT
 } aom_option;
 enum {
   AOM_EXTRUDE_I8 = 0,      /* exact integer contraction on tcgen05 (int8 digit planes, int32 accumulators, one rounding to
                               float32 per new pixel; default; extrude_i8.cuh) */
   AOM_EXTRUDE_FFMA = 1     /* float32 FFMA accumulation with round-to-nearest (round-1 kernel, cross-check path) */
+};
+enum {
+  AOM_DENOISE_TCGEN05 = 0, /* e2, e3, d1, d2 as implicit GEMMs on tcgen05 (fp16 hi / lo operands, three products each), e1 and
+                              d3 fused on the CUDA cores (denoise_tc.cuh); needs AOM_T_DENOISER_TC, else the next one runs */
+  AOM_DENOISE_SIMT = 1     /* float32 FFMA kernel (denoise_kernels.cuh; cross-check path) */
 };
 enum {
   AOM_PUPIL_SWEEP = 0,     /* staged screen rows, one warp per strip of pupil rows (pitch-16 lattices; default; other
