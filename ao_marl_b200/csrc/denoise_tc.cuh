@@ -287,43 +287,53 @@ __device__ __forceinline__ void dt_epi5(const DnTcParams& P, uint32_t tlane, boo
   float v[8][16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dt_ld16(tlane + (H * 8 + i) * 16, v[i]);       // i = (px, qy, qx)
-  if (!real) return;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[i][j] = fmaxf(v[i][j] + P.prm[DT_P_B5 + j], 0.f);
   float wnd[4][6];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 6; ++b) wnd[a][b] = 0.f;
+  if (real) {
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      float acc[8];
+      for (int j = 0; j < 16; ++j) v[i][j] = fmaxf(v[i][j] + P.prm[DT_P_B5 + j], 0.f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float w = P.prm[DT_P_W6 + j * 9 + ky * 3 + kx];
+      for (int kx = 0; kx < 3; ++kx) {
+        float acc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i][j], w, acc[i]);
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float w = P.prm[DT_P_W6 + j * 9 + ky * 3 + kx];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i][j], w, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int px = i >> 2, qy = (i >> 1) & 1, qx = i & 1;
+          wnd[qy + ky][2 * px + qx + kx] += acc[i];
+        }
       }
+  }
+  // the windows of neighbouring threads overlap: eight colours (half, parity of Y, parity of X) whose windows are disjoint
+  // add in turn, so that the sum order -- and with it every output bit -- is the same in every run and batch split
+  const int colour = H * 4 + (Y & 1) * 2 + (X & 1);
+#pragma unroll 1
+  for (int ph = 0; ph < 8; ++ph) {
+    if (real && ph == colour) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int px = i >> 2, qy = (i >> 1) & 1, qx = i & 1;
-        wnd[qy + ky][2 * px + qx + kx] += acc[i];
+      for (int a = 0; a < 4; ++a) {
+        const int row = 4 * Y + 2 * H + a - 1;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          const int col = 4 * X + b - 1;
+          if (row >= 0 && row < 16 && col >= 0 && col < 16) out_img[row * 16 + col] += wnd[a][b];
+        }
       }
     }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int row = 4 * Y + 2 * H + a - 1;
-#pragma unroll
-    for (int b = 0; b < 6; ++b) {
-      const int col = 4 * X + b - 1;
-      if (row >= 0 && row < 16 && col >= 0 && col < 16) atomicAdd(out_img + row * 16 + col, wnd[a][b]);
-    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   }
 }
 
@@ -582,7 +592,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
     if (warp < 8) {
       if (half == 0) dt_epi5<0>(P, tlane, real, img_out + s * 256, Y, X);
       else dt_epi5<1>(P, tlane, real, img_out + s * 256, Y, X);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
       const float invs = P.prm[DT_P_INVS], b6 = P.prm[DT_P_B6];
       for (int i = tid; i < ns * 256; i += 256) {
         const float v = img_out[i];

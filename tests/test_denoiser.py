@@ -58,19 +58,27 @@ def test_fused_kernel_matches_the_reference_module(static10):
     sim = Simulator(static10, 2, rl=None)
     try:
         ae = Autoencoder(dict(type="cnn_single_subaperture", path="autoencoder_M9_rms_3"), device="cuda", sim=sim)
-        y = ae.predict(torch.from_numpy(g["x"]).cuda()).cpu().numpy()
-        sim.check_device()
-        assert y.shape == g["y"].shape
-        assert np.abs(y - g["y"]).max() < 2e-5 * np.abs(g["y"]).max()
         ref = Autoencoder(dict(type="cnn_single_subaperture", path="autoencoder_M9_rms_3"), device="cpu")
-        gen = torch.Generator().manual_seed(3)
-        for n in (1, 3, 4, 5, 1027):
-            x = torch.poisson(torch.rand((n, 16, 16), generator=gen) * 30, generator=gen) + \
-                torch.randn((n, 16, 16), generator=gen) * 3
-            want = ref.predict(x).numpy()
-            got = ae.predict(x.cuda()).cpu().numpy()
-            assert got.shape == want.shape
-            assert np.abs(got - want).max() < 2e-5 * np.abs(want).max(), n
+        # both kernels: the tensor-core one (default: four layers as implicit GEMMs on tcgen05, fp16 hi / lo operands) and
+        # the float32 FFMA one; same tolerance
+        for path in ("tcgen05", "simt"):
+            sim.set_denoise_path(path)
+            y = ae.predict(torch.from_numpy(g["x"]).cuda()).cpu().numpy()
+            sim.check_device()
+            assert y.shape == g["y"].shape
+            assert np.abs(y - g["y"]).max() < 2e-5 * np.abs(g["y"]).max(), path
+            gen = torch.Generator().manual_seed(3)
+            for n in (1, 3, 4, 5, 6, 1027):
+                for scale in (30.0, 3000.0):                   # faint and bright spots (fp16 operand range)
+                    x = torch.poisson(torch.rand((n, 16, 16), generator=gen) * scale, generator=gen) + \
+                        torch.randn((n, 16, 16), generator=gen) * 3
+                    want = ref.predict(x).numpy()
+                    got = ae.predict(x.cuda()).cpu().numpy()
+                    assert got.shape == want.shape
+                    assert np.abs(got - want).max() < 2e-5 * np.abs(want).max(), (path, n, scale)
+                    again = ae.predict(x.cuda()).cpu().numpy()
+                    assert np.array_equal(got, again), (path, n)      # run-to-run reproducible
+        sim.set_denoise_path("tcgen05")
         sim.check_device()
     finally:
         sim.close()
