@@ -215,7 +215,7 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
   CU(dalloc(&ctx->strehl, E * 4));
   CU(dalloc(&ctx->tar_mom, E * 2 * PSW_MOM2));     // main target, then the geometric controller's
   CU(dalloc(&ctx->tar_acc, E * TAR_ACC));
-  CU(cudaMalloc((void**)&ctx->dn_dbg, 16 * sizeof(long long)));
+  CU(cudaMalloc((void**)&ctx->dn_dbg, 32 * sizeof(long long)));
   if (cfg->nmodes > 0) {
     CU(dalloc(&ctx->modes, E * ctx->ldm));
     CU(dalloc(&ctx->modes_before, E * ctx->ldm));
@@ -1410,12 +1410,15 @@ extern "C" int aom_denoise(aom_ctx* ctx, const float* din, float* dout, long lon
     CU(denoise_tc_launch(P, ctx->num_sms, (cudaStream_t)stream));
     ctx->launches += 1;
     if (P.dbg) {   // development: per-phase clock totals of CTA 0
-      long long h[12];
+      long long h[32];
       CU(cudaStreamSynchronize((cudaStream_t)stream));
       CU(cudaMemcpy(h, ctx->dn_dbg, sizeof(h), cudaMemcpyDeviceToHost));
       const char* nm[9] = {"load+e1", "e2 mma", "e2 epi", "e3 mma", "e3 epi", "d1 mma", "d1 epi", "d2 mma", "d2 epi+d3+store"};
       const double passes = (double)((n_spots + DT_G - 1) / DT_G + ctx->num_sms - 1) / ctx->num_sms;
       for (int i = 0; i < 9; ++i) fprintf(stderr, "denoise_tc %-16s %9.0f cycles per pass\n", nm[i], (double)h[i] / passes);
+      const char* cn[15] = {"e2 wait w", "e2 issue", "e2 complete", "e3 wait w hi", "e3 issue hi", "e3 wait w lo", "e3 issue lo", "e3 complete",
+                            "d1 wait w (4x)", "d1 issue (4x)", "d1 wait class + reload (2x)", "d1 complete", "d2 wait w", "d2 issue", "d2 complete"};
+      for (int i = 0; i < 15; ++i) fprintf(stderr, "denoise_tc issuing lane: %-28s %9.0f cycles per pass\n", cn[i], (double)h[16 + i] / passes);
     }
   } else if (n_spots > 0) {
     CU(cudaFuncSetAttribute(denoise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_SMEM_BYTES));

@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <type_traits>
 
 #define DT_G 5
 #define DT_PITCH 5
@@ -71,7 +72,7 @@ struct DnTcParams {
   long long n_spots;
   const uint8_t* wblob;     // DT_WBLOB_BYTES, 16-byte aligned
   int* err;
-  long long* dbg;           // optional [16]: per-phase clock totals of CTA 0 (development)
+  long long* dbg;           // optional [32]: per-phase clock totals of CTA 0: [0..8] an epilogue thread, [16..30] the issuing lane
   float prm[DT_NPARAM];
 };
 
@@ -138,6 +139,32 @@ __device__ __forceinline__ void dt_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t
       "mov.b64 db, {%2, %5};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, {%6, %6, %6, %6}, p;\n\t}"
       :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(0x4008u), "r"(0u) : "memory");
+}
+// Fully immediate form: the descriptor low words are assembler constants (shared-window offset of the dynamic array
+// >> 4, plus template offsets), built next to the instruction.  With run-time (even uniform) low words the compiler CSE'd
+// and hoisted hundreds of descriptor values out of the unrolled issue loops and then spilled uniform registers
+// (R2UR / MOV.SPILL chains: 63-98 cycles per MMA instead of the 40 the tensor pipe needs, profiles/dev/umma_rate_probe.cu).
+template <uint32_t AQ, uint32_t BQ, uint32_t ACC>
+__device__ __forceinline__ void dt_mma_c(uint32_t d_tmem, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 sa, ta, tb;\n\t.reg .b64 da, db;\n\t"
+      "mov.u32 sa, dt_sm;\n\t"
+      "shr.u32 sa, sa, 4;\n\t"
+      "and.b32 sa, sa, 0x3FFF;\n\t"
+      "add.u32 ta, sa, %2;\n\t"
+      "add.u32 tb, sa, %3;\n\t"
+      "mov.b64 da, {ta, %4};\n\t"
+      "mov.b64 db, {tb, %4};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %1, {%6, %6, %6, %6}, p;\n\t}"
+      :: "r"(d_tmem), "r"(idesc), "n"(AQ), "n"(BQ), "n"(0x4008), "n"(ACC), "r"(0u) : "memory");
+}
+template <int I, int N, class F>
+__device__ __forceinline__ void dt_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    dt_for<I + 1, N>(f);
+  }
 }
 __device__ __forceinline__ void dt_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -337,6 +364,85 @@ __device__ __forceinline__ void dt_epi5(const DnTcParams& P, uint32_t tlane, boo
   }
 }
 
+// ---- MMA issue groups.  Each group is its own (non-inlined) function: with the 738 MMAs of a pass in one body ptxas hoisted
+// the descriptor constants of the whole pass and spilled uniform registers between every pair of UTCHMMA. ----
+constexpr uint32_t DT_PQ = DT_PLANE >> 4;
+constexpr uint32_t DT_QA14 = (DT_OFF_A14 >> 4) + DT_LEAD + (DT_PQ << 16);
+constexpr uint32_t DT_QA2 = (DT_OFF_A2 >> 4) + DT_LEAD + (DT_PQ << 16);
+constexpr uint32_t DT_QA3 = (DT_OFF_A3 >> 4) + DT_LEAD + (DT_PQ << 16);
+constexpr uint32_t DT_QW0 = (DT_OFF_W >> 4), DT_QW1 = DT_QW0 + (DT_WBUF >> 4);
+constexpr uint32_t DT_ID16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t DT_ID32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t DT_ID64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// e2, output phase PH: nine taps, K = 16, weights in buffer 0
+template <int PH>
+__device__ __noinline__ void dt_issue_e2(uint32_t tmem_u) {
+  constexpr int py = PH >> 1, px = PH & 1;
+  const uint32_t d = tmem_u + PH * 32;
+  dt_for<0, 9>([&](auto tc) {
+    constexpr int tap = decltype(tc)::value, dy = tap / 3 - 1, dx = tap % 3 - 1;
+    constexpr int iph = ((py + dy) & 1) * 2 + ((px + dx) & 1);
+    constexpr int sh = dt_floor2(py + dy) * DT_PITCH + dt_floor2(px + dx);
+    constexpr uint32_t a_hi = DT_QA14 + ((iph * 2 + 0) * 2) * DT_PQ + sh, a_lo = DT_QA14 + ((iph * 2 + 1) * 2) * DT_PQ + sh;
+    constexpr uint32_t b_hi = DT_QW0 + tap * 128 + (32u << 16), b_lo = b_hi + 64;
+    dt_mma_c<a_hi, b_hi, (tap ? 1u : 0u)>(d, DT_ID32);
+    dt_mma_c<a_lo, b_hi, 1u>(d, DT_ID32);
+    dt_mma_c<a_hi, b_lo, 1u>(d, DT_ID32);
+  });
+}
+// e3, taps T0 .. T0 + 2: high weight parts from buffer 1 (LO = 0: two products) or low parts from buffer 0 (LO = 1)
+template <int T0, int LO>
+__device__ __noinline__ void dt_issue_e3(uint32_t tmem_u) {
+  const uint32_t d = tmem_u + 128;
+  dt_for<0, 6>([&](auto ic) {
+    constexpr int tap = T0 + (decltype(ic)::value >> 1), ks = decltype(ic)::value & 1;
+    constexpr int sh = (tap / 3 - 1) * DT_PITCH + tap % 3 - 1;
+    constexpr uint32_t a_hi = DT_QA2 + (0 * 4 + 2 * ks) * DT_PQ + sh, a_lo = DT_QA2 + (1 * 4 + 2 * ks) * DT_PQ + sh;
+    constexpr uint32_t b = (LO ? DT_QW0 : DT_QW1) + tap * 256 + ks * 128 + (64u << 16);
+    if constexpr (LO == 0) {
+      dt_mma_c<a_hi, b, ((tap | ks) ? 1u : 0u)>(d, DT_ID64);
+      dt_mma_c<a_lo, b, 1u>(d, DT_ID64);
+    } else {
+      dt_mma_c<a_hi, b, 1u>(d, DT_ID64);
+    }
+  });
+}
+// d1, parity class CL, tap T: K = 64
+template <int CL, int T>
+__device__ __noinline__ void dt_issue_d1(uint32_t tmem_u) {
+  constexpr int py = CL >> 1, px = CL & 1;
+  constexpr uint32_t wq = (CL & 1) ? DT_QW0 : DT_QW1;
+  const uint32_t d = tmem_u + 192 + CL * 32;
+  constexpr int sh = dt_ct_d(py, T >> 1) * DT_PITCH + dt_ct_d(px, T & 1);
+  dt_for<0, 4>([&](auto kc) {
+    constexpr int ks = decltype(kc)::value;
+    constexpr uint32_t a_hi = DT_QA3 + (0 * 8 + 2 * ks) * DT_PQ + sh, a_lo = DT_QA3 + (1 * 8 + 2 * ks) * DT_PQ + sh;
+    constexpr uint32_t b_hi = wq + T * 512 + ks * 64 + (32u << 16), b_lo = b_hi + 256;
+    dt_mma_c<a_hi, b_hi, ((T | ks) ? 1u : 0u)>(d, DT_ID32);
+    dt_mma_c<a_lo, b_hi, 1u>(d, DT_ID32);
+    dt_mma_c<a_hi, b_lo, 1u>(d, DT_ID32);
+  });
+}
+// d2, (input phase, output parity) class SC: four taps, K = 32, weights in buffer 1
+template <int SC>
+__device__ __noinline__ void dt_issue_d2(uint32_t tmem_u) {
+  constexpr int py = SC >> 3, px = (SC >> 2) & 1, qy = (SC >> 1) & 1, qx = SC & 1;
+  const uint32_t d = tmem_u + SC * 16;
+  dt_for<0, 8>([&](auto ic) {
+    constexpr int t = decltype(ic)::value >> 1, ks = decltype(ic)::value & 1;
+    constexpr int ky = dt_ct_k(qy, t >> 1), dy = dt_ct_d(qy, t >> 1), kx = dt_ct_k(qx, t & 1), dx = dt_ct_d(qx, t & 1);
+    constexpr int iph = ((py + dy) & 1) * 2 + ((px + dx) & 1);
+    constexpr int sh = dt_floor2(py + dy) * DT_PITCH + dt_floor2(px + dx);
+    constexpr uint32_t bt = DT_QW1 + (ky * 4 + kx) * 128 + (16u << 16);
+    constexpr uint32_t a_hi = DT_QA14 + ((iph * 2 + 0) * 4 + 2 * ks) * DT_PQ + sh, a_lo = DT_QA14 + ((iph * 2 + 1) * 4 + 2 * ks) * DT_PQ + sh;
+    constexpr uint32_t b_hi = bt + ks * 32, b_lo = b_hi + 64;
+    dt_mma_c<a_hi, b_hi, ((t | ks) ? 1u : 0u)>(d, DT_ID16);
+    dt_mma_c<a_lo, b_hi, 1u>(d, DT_ID16);
+    dt_mma_c<a_hi, b_lo, 1u>(d, DT_ID16);
+  });
+}
+
 __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_constant__ DnTcParams P) {
   extern __shared__ __align__(128) uint8_t dt_sm[];
   const uint32_t sb = dt_smem_u32(dt_sm);
@@ -385,23 +491,21 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
     dt_bulk(wb1, P.wblob + 18432, 36864, bar_w1);
   }
 
-  const uint32_t ID16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-  const uint32_t ID32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-  const uint32_t ID64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
   // descriptor low words in 16-byte units, warp-uniform: start address >> 4 | LBO >> 4 << 16.  Position shift s = +s,
   // plane p = +p * PQ, weight offset o bytes = +o / 16.
-  const uint32_t sbq = __shfl_sync(0xffffffffu, sb >> 4, 0);
-  constexpr uint32_t PQ = DT_PLANE >> 4;
-  const uint32_t A14 = sbq + (DT_OFF_A14 >> 4) + DT_LEAD + (PQ << 16);
-  const uint32_t A2 = sbq + (DT_OFF_A2 >> 4) + DT_LEAD + (PQ << 16);
-  const uint32_t A3 = sbq + (DT_OFF_A3 >> 4) + DT_LEAD + (PQ << 16);
-  const uint32_t wq0 = sbq + (DT_OFF_W >> 4), wq1 = wq0 + (DT_WBUF >> 4);
+  // (the masked shared-window offset is a compile-time constant for the compiler -- no shuffle here, it would hide that --
+  // so every descriptor low word folds to an immediate)
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
   long long tacc[12], tprev = 0;
 #pragma unroll
   for (int i = 0; i < 12; ++i) tacc[i] = 0;
 #define DT_TICK(i) if (P.dbg) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
+  long long cacc[15], cprev = 0;
+#pragma unroll
+  for (int i = 0; i < 15; ++i) cacc[i] = 0;
+#define DT_CT0 if (P.dbg) cprev = clock64();
+#define DT_CT(i) if (P.dbg) { const long long tn = clock64(); cacc[i] += tn - cprev; cprev = tn; }
 #pragma unroll 1
   for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
     if (P.dbg) tprev = clock64();
@@ -430,24 +534,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
 
     // ---- e2: four output phases x nine taps, K = 16
     if (w8 && dt_elect()) {
+      DT_CT0
       dt_mbar_wait(bar_w0, 0u, P.err);
-#pragma unroll
-      for (int ph = 0; ph < 4; ++ph) {
-        const int py = ph >> 1, px = ph & 1;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          const int iph = ((py + dy) & 1) * 2 + ((px + dx) & 1);
-          const int sh = dt_floor2(py + dy) * DT_PITCH + dt_floor2(px + dx);
-          const uint32_t a_hi = A14 + ((iph * 2 + 0) * 2) * PQ + sh, a_lo = A14 + ((iph * 2 + 1) * 2) * PQ + sh;
-          const uint32_t b_hi = wq0 + tap * 128 + (32u << 16), b_lo = b_hi + 64;
-          const uint32_t d = tmem_u + ph * 32;
-          dt_mma2(d, a_hi, b_hi, ID32, tap ? 1u : 0u);
-          dt_mma2(d, a_lo, b_hi, ID32, 1u);
-          dt_mma2(d, a_hi, b_lo, ID32, 1u);
-        }
-      }
+      DT_CT(0)
+      dt_issue_e2<0>(tmem_u); dt_issue_e2<1>(tmem_u); dt_issue_e2<2>(tmem_u); dt_issue_e2<3>(tmem_u);
       dt_commit(bar_mma);
+      DT_CT(1)
+      dt_mbar_wait(bar_mma, pm, P.err);
+      DT_CT(2)
     }
     dt_mbar_wait(bar_mma, pm, P.err);
     pm ^= 1;
@@ -466,28 +560,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
 
     // ---- e3: nine taps, K = 32; high weight parts from buffer 1, low parts from buffer 0
     if (w8 && dt_elect()) {
+      DT_CT0
       dt_mbar_wait(bar_w1, 0u, P.err);
-      const uint32_t d = tmem_u + 128;
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int sh = (tap / 3 - 1) * DT_PITCH + tap % 3 - 1;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint32_t a_hi = A2 + (0 * 4 + 2 * ks) * PQ + sh, a_lo = A2 + (1 * 4 + 2 * ks) * PQ + sh;
-          const uint32_t b = wq1 + tap * 256 + ks * 128 + (64u << 16);
-          dt_mma2(d, a_hi, b, ID64, (tap | ks) ? 1u : 0u);
-          dt_mma2(d, a_lo, b, ID64, 1u);
-        }
-      }
+      DT_CT(3)
+      dt_issue_e3<0, 0>(tmem_u); dt_issue_e3<3, 0>(tmem_u); dt_issue_e3<6, 0>(tmem_u);
+      DT_CT(4)
       dt_mbar_wait(bar_w0, 1u, P.err);
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int sh = (tap / 3 - 1) * DT_PITCH + tap % 3 - 1;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          dt_mma2(d, A2 + (2 * ks) * PQ + sh, wq0 + tap * 256 + ks * 128 + (64u << 16), ID64, 1u);
-      }
+      DT_CT(5)
+      dt_issue_e3<0, 1>(tmem_u); dt_issue_e3<3, 1>(tmem_u); dt_issue_e3<6, 1>(tmem_u);
       dt_commit(bar_mma);
+      DT_CT(6)
+      dt_mbar_wait(bar_mma, pm, P.err);
+      DT_CT(7)
     }
     dt_mbar_wait(bar_mma, pm, P.err);
     pm ^= 1;
@@ -509,24 +593,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
 
     // ---- d1: four parity classes x four taps, K = 64; one weight chunk per class
     if (w8 && dt_elect()) {
-#pragma unroll
-      for (int cl = 0; cl < 4; ++cl) {
-        const int py = cl >> 1, px = cl & 1;
-        const uint32_t wq = (cl & 1) ? wq0 : wq1;
+      dt_for<0, 4>([&](auto clc) {
+        constexpr int cl = decltype(clc)::value;
+        DT_CT0
         dt_mbar_wait((cl & 1) ? bar_w0 : bar_w1, (cl & 1) ? (uint32_t)(cl >> 1) : (uint32_t)(1 - (cl >> 1)), P.err);
-        const uint32_t d = tmem_u + 192 + cl * 32;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int sh = dt_ct_d(py, t >> 1) * DT_PITCH + dt_ct_d(px, t & 1);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t a_hi = A3 + (0 * 8 + 2 * ks) * PQ + sh, a_lo = A3 + (1 * 8 + 2 * ks) * PQ + sh;
-            const uint32_t b_hi = wq + t * 512 + ks * 64 + (32u << 16), b_lo = b_hi + 256;
-            dt_mma2(d, a_hi, b_hi, ID32, (t | ks) ? 1u : 0u);
-            dt_mma2(d, a_lo, b_hi, ID32, 1u);
-            dt_mma2(d, a_hi, b_lo, ID32, 1u);
-          }
-        }
+        DT_CT(8)
+        dt_issue_d1<cl, 0>(tmem_u); dt_issue_d1<cl, 1>(tmem_u); dt_issue_d1<cl, 2>(tmem_u); dt_issue_d1<cl, 3>(tmem_u);
+        DT_CT(9)
         if (cl == 0) dt_commit(bar_ca);
         if (cl == 1) {
           dt_commit(bar_cb);
@@ -534,14 +607,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
           dt_bulk(wb1, P.wblob + 157696, 32768, bar_w1);                      // class 2
           dt_mbar_wait(bar_cb, pcb, P.err);
           dt_bulk(wb0, P.wblob + 190464, 32768, bar_w0);                      // class 3
+          DT_CT(10)
         }
         if (cl == 2) dt_commit(bar_ca);
         if (cl == 3) {
           dt_commit(bar_mma);
           dt_mbar_wait(bar_ca, 1u, P.err);
           dt_bulk(wb1, P.wblob + 223232, 32768, bar_w1);                      // d2
+          DT_CT(10)
+          dt_mbar_wait(bar_mma, pm, P.err);
+          DT_CT(11)
         }
-      }
+      });
     }
     dt_mbar_wait(bar_mma, pm, P.err);
     pm ^= 1;
@@ -561,28 +638,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
 
     // ---- d2: sixteen (input phase, output parity) classes x four taps, K = 32
     if (w8 && dt_elect()) {
+      DT_CT0
       dt_mbar_wait(bar_w1, 1u, P.err);
-#pragma unroll
-      for (int sc = 0; sc < 16; ++sc) {
-        const int py = sc >> 3, px = (sc >> 2) & 1, qy = (sc >> 1) & 1, qx = sc & 1;
-        const uint32_t d = tmem_u + sc * 16;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int ky = dt_ct_k(qy, t >> 1), dy = dt_ct_d(qy, t >> 1), kx = dt_ct_k(qx, t & 1), dx = dt_ct_d(qx, t & 1);
-          const int iph = ((py + dy) & 1) * 2 + ((px + dx) & 1);
-          const int sh = dt_floor2(py + dy) * DT_PITCH + dt_floor2(px + dx);
-          const uint32_t bt = wq1 + (ky * 4 + kx) * 128 + (16u << 16);
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t a_hi = A14 + ((iph * 2 + 0) * 4 + 2 * ks) * PQ + sh, a_lo = A14 + ((iph * 2 + 1) * 4 + 2 * ks) * PQ + sh;
-            const uint32_t b_hi = bt + ks * 32, b_lo = b_hi + 64;
-            dt_mma2(d, a_hi, b_hi, ID16, (t | ks) ? 1u : 0u);
-            dt_mma2(d, a_lo, b_hi, ID16, 1u);
-            dt_mma2(d, a_hi, b_lo, ID16, 1u);
-          }
-        }
-      }
+      DT_CT(12)
+      dt_for<0, 16>([&](auto scc) { dt_issue_d2<decltype(scc)::value>(tmem_u); });
       dt_commit(bar_mma);
+      DT_CT(13)
+      dt_mbar_wait(bar_mma, pm, P.err);
+      DT_CT(14)
     }
     dt_mbar_wait(bar_mma, pm, P.err);
     pm ^= 1;
@@ -606,6 +669,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
   }
   if (P.dbg && blockIdx.x == 0 && tid == 0)
     for (int i = 0; i < 12; ++i) P.dbg[i] = tacc[i];
+  if (P.dbg && blockIdx.x == 0 && w8 && dt_elect())
+    for (int i = 0; i < 15; ++i) P.dbg[16 + i] = cacc[i];
 
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)DT_TMEM_COLS) : "memory");
 }

@@ -1,3 +1,4 @@
+// (second half: effect of a start address that is not 128-byte aligned)
 // Issue-to-completion time of back-to-back tcgen05.mma kind::f16 (M = 128, K = 16) for several N: how small an MMA may be
 // before the tensor pipe stops scaling.  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate_probe umma_rate_probe.cu
 #include <cuda_runtime.h>
@@ -12,7 +13,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t a_lo, uint32_t b_lo, ui
       :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(0x4008u), "r"(0u) : "memory");
 }
 template <int N, int REP>
-__global__ void k(long long* out) {
+__global__ void k(long long* out, uint32_t a_shift, uint32_t n_acc) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint64_t bar; __shared__ uint32_t slot;
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sm);
@@ -37,7 +38,7 @@ __global__ void k(long long* out) {
     for (int r = 0; r < REP; ++r) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        mma(tmem + (j & 1) * 256, sbq + j * 16 + (144u << 16), sbq + 2048 + j * 8 + ((uint32_t)(N * 16 >> 4) << 16), idesc, j > 1 ? 1u : 0u);
+        mma(tmem + (j % n_acc) * 64, sbq + 8 + a_shift + j * 16 + (144u << 16), sbq + 2048 + j * 8 + ((uint32_t)(N * 16 >> 4) << 16), idesc, 1u);
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(barp) : "memory");
     const long long t1 = clock64();
@@ -49,17 +50,21 @@ __global__ void k(long long* out) {
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
-template <int N> void run(long long* d) {
+template <int N> void run(long long* d, unsigned a_shift = 0, unsigned n_acc = 2) {
   const int REP = 64;
   cudaFuncSetAttribute(k<N, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  k<N, REP><<<1, 128, 65536>>>(d); cudaDeviceSynchronize();
-  k<N, REP><<<1, 128, 65536>>>(d);
+  k<N, REP><<<1, 128, 65536>>>(d, a_shift, n_acc); cudaDeviceSynchronize();
+  k<N, REP><<<1, 128, 65536>>>(d, a_shift, n_acc);
   long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-  printf("N=%3d: issue %.1f cycles/MMA, complete %.1f cycles/MMA (%d MMAs, M=128 K=16 f16) -> %.0f MAC/clk   %s\n", N, h[0] / (16.0 * REP), h[1] / (16.0 * REP),
+  printf("A start + %u x 16 B, %u accumulator(s) in turn  N=%3d: issue %.1f cycles/MMA, complete %.1f cycles/MMA (%d MMAs, M=128 K=16 f16) -> %.0f MAC/clk   %s\n", a_shift, n_acc, N, h[0] / (16.0 * REP), h[1] / (16.0 * REP),
          16 * REP, 128.0 * N * 16 / (h[1] / (16.0 * REP)), cudaGetErrorString(cudaGetLastError()));
 }
 int main() {
   long long* d; cudaMalloc(&d, 16);
   run<16>(d); run<32>(d); run<64>(d); run<128>(d); run<256>(d);
+  // the same with the A tile starting 1, 3, 4 positions (16 B each) off a 128-byte boundary: shifted implicit-GEMM taps
+  // dependent chains: every MMA accumulates into the same TMEM columns (1), or 2 / 4 accumulators in turn
+  run<16>(d, 0, 1); run<32>(d, 0, 1); run<64>(d, 0, 1); run<32>(d, 0, 4); run<64>(d, 0, 4);
+  run<16>(d, 1); run<32>(d, 1); run<32>(d, 3); run<32>(d, 4); run<64>(d, 1); run<128>(d, 1);
   return 0;
 }
