@@ -5,7 +5,7 @@
 //   e1 conv3x3 1->16 + relu + pool | e2 conv3x3 16->32 + relu + pool | e3 conv3x3 32->64 + relu
 //   d1 convT4x4/2 64->32 + relu    | d2 convT4x4/2 32->16 + relu     | d3 convT3x3 16->1
 // 96 % of the 3.42 MFLOP per spot are in e2, e3, d1, d2.  They run here as implicit GEMMs on `tcgen05.mma kind::f16`
-// (fp16 hi + lo operands, three products each, float32 accumulators in TMEM); e1 and d3 (K = 9 / N = 1) stay on the
+// (fp16 hi + lo operands, three products each -- two instructions, see the issue groups -- float32 accumulators in TMEM); e1 and d3 (K = 9 / N = 1) stay on the
 // CUDA cores, fused into the prologue and the last epilogue.  denoise_kernels.cuh keeps the float32 FFMA form
 // (cross-check, AOM_DENOISE_SIMT).
 //
@@ -25,8 +25,8 @@
 // output adds its 6 x 6 window of partial sums into the output image in shared memory.
 // Weights (256 KB as fp16 hi / lo tiles, pre-ordered by ao_marl_b200/denoiser.py::pack_weights_tc) stream through two
 // 36 KB buffers by cp.async.bulk, eight chunks per pass, prefetched one chunk ahead.
-// Warps 0-7: prologue (e1), epilogues (two warps per TMEM lane quarter split the columns); warp 8: one lane issues the
-// bulk copies and the 738 MMAs of a pass.
+// Warps 0-15: prologue (e1), epilogues (four warps per TMEM lane quarter split the columns); warp 16: one elected lane
+// issues the bulk copies and the 510 MMAs of a pass.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -39,7 +39,8 @@
 #define DT_NPOS 144
 #define DT_PLANE (DT_NPOS * 16)            // 2304 B: one channel group of 8 (fp16) over all positions
 #define DT_WBUF 36864
-#define DT_THREADS 288
+#define DT_EPI_WARPS 16
+#define DT_THREADS (32 * DT_EPI_WARPS + 32)
 #define DT_TMEM_COLS 512
 #define DT_NPARAM 452
 #define DT_WBLOB_BYTES 256000
@@ -62,9 +63,11 @@
 #define DT_OFF_A3 (40 * DT_PLANE)                     // 16 planes [part][8 groups]
 #define DT_OFF_W (56 * DT_PLANE)                      // two weight buffers
 #define DT_OFF_IN (DT_OFF_W + 2 * DT_WBUF)            // [G][18][18] float, zero border
-#define DT_OFF_OUT (DT_OFF_IN + DT_G * 324 * 4)       // [G][256] float
-#define DT_OFF_BAR (DT_OFF_OUT + DT_G * 256 * 4)      // mbarriers: w0, w1, mma, cA, cB ; tmem slot
-#define DT_SMEM_BYTES (DT_OFF_BAR + 64)
+#define DT_OFF_OUT (DT_OFF_IN + DT_G * 324 * 4)       // d3 windows [G][16 cells][4 quarters][4][4] float
+#define DT_OFF_BAR (DT_OFF_OUT + DT_G * 1024 * 4)     // mbarriers: w0, w1, mma, cA, cB ; tmem slot
+#define DT_OFF_SPRM (DT_OFF_BAR + 64)                 // CUDA-core weights as vector-register operands: w1 [16][12], w6 [9][16]
+#define DT_SPRM_FLOATS (16 * 12 + 9 * 16)
+#define DT_SMEM_BYTES (DT_OFF_SPRM + DT_SPRM_FLOATS * 4)
 
 struct DnTcParams {
   const float* in;          // [n_spots][256]
@@ -180,6 +183,15 @@ __device__ __forceinline__ void dt_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
+__device__ __forceinline__ void dt_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
 __device__ __forceinline__ void dt_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 f = __half22float2(h);
@@ -203,30 +215,40 @@ __device__ __forceinline__ constexpr int dt_floor2(int a) { return (a + 4) / 2 -
 __device__ __forceinline__ constexpr int dt_ct_k(int p, int t) { return p == 0 ? (t == 0 ? 1 : 3) : (t == 0 ? 0 : 2); }
 __device__ __forceinline__ constexpr int dt_ct_d(int p, int t) { return p == 0 ? (t == 0 ? 0 : -1) : (t == 0 ? 1 : 0); }
 
-// e1 on the CUDA cores: conv3x3 1 -> 16 + relu + pool for this thread's coarse position and channel half, written as
-// the four phase planes of the 8 x 8 map
-template <int H>
-__device__ __forceinline__ void dt_layer1(const DnTcParams& P, const float* img, int Y, int X, uint32_t a1_pos) {
+// Sixteen epilogue warps: TMEM lane quarter = warp & 3 (the position), column quarter Q = warp >> 2 (which quarter of the
+// channels / classes of that position).  With eight warps (two column halves) the CUDA-core phases ran at 0.25 instructions
+// per cycle and scheduler: two warps per scheduler cannot hide their own LDS / LDTM / constant-load latencies.
+
+// e1 on the CUDA cores: conv3x3 1 -> 16 + relu + pool for this thread's coarse position and four channels, written as
+// the four phase planes of the 8 x 8 map (8-byte halves of the 16-byte channel group)
+template <int Q>
+__device__ __forceinline__ void dt_layer1(const DnTcParams& P, const float* sprm, const float* img, int Y, int X, uint32_t a1_pos) {
   float win[6][6];
 #pragma unroll
   for (int a = 0; a < 6; ++a)
 #pragma unroll
     for (int b = 0; b < 6; ++b) win[a][b] = img[(4 * Y + a) * 18 + 4 * X + b];
-  float res[4][8];
+  float res[4][4];
   const float S = P.prm[DT_P_S];
 #pragma unroll
-  for (int cc = 0; cc < 8; ++cc) {
-    const int c = 8 * H + cc;
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = 4 * Q + cc;
     float cv[4][4];
 #pragma unroll
     for (int fy = 0; fy < 4; ++fy)
 #pragma unroll
       for (int fx = 0; fx < 4; ++fx) cv[fy][fx] = 0.f;
+    float wk[12];
+#pragma unroll
+    for (int q4 = 0; q4 < 3; ++q4) {
+      const float4 t = *reinterpret_cast<const float4*>(sprm + c * 12 + 4 * q4);
+      wk[4 * q4] = t.x; wk[4 * q4 + 1] = t.y; wk[4 * q4 + 2] = t.z; wk[4 * q4 + 3] = t.w;
+    }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const float w = P.prm[DT_P_W1 + c * 9 + ky * 3 + kx];        // one fetch, sixteen independent FMAs
+        const float w = wk[ky * 3 + kx];                             // one fetch, sixteen independent FMAs
 #pragma unroll
         for (int fy = 0; fy < 4; ++fy)
 #pragma unroll
@@ -242,125 +264,121 @@ __device__ __forceinline__ void dt_layer1(const DnTcParams& P, const float* img,
       }
   }
 #pragma unroll
-  for (int ph = 0; ph < 4; ++ph)
-    dt_store8(a1_pos + ((ph * 2 + 0) * 2 + H) * DT_PLANE, a1_pos + ((ph * 2 + 1) * 2 + H) * DT_PLANE, res[ph]);
+  for (int ph = 0; ph < 4; ++ph) {
+    uint32_t h0, l0, h1, l1;
+    dt_split2(res[ph][0], res[ph][1], h0, l0);
+    dt_split2(res[ph][2], res[ph][3], h1, l1);
+    const uint32_t hi = a1_pos + ((ph * 2 + 0) * 2 + (Q >> 1)) * DT_PLANE + (Q & 1) * 8;
+    const uint32_t lo = a1_pos + ((ph * 2 + 1) * 2 + (Q >> 1)) * DT_PLANE + (Q & 1) * 8;
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(hi), "r"(h0), "r"(h1) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(lo), "r"(l0), "r"(l1) : "memory");
+  }
 }
 
-// epilogue of e2: max over the four phase accumulators (= 2 x 2 pooling), bias, relu -> A2; this half's 16 channels
-template <int H>
+// epilogue of e2: max over the four phase accumulators (= 2 x 2 pooling), bias, relu -> A2; this quarter's 8 channels
+template <int Q>
 __device__ __forceinline__ void dt_epi2(const DnTcParams& P, uint32_t tlane, bool real, uint32_t a2_pos) {
-  float m[16], v[16];
-  dt_ld16(tlane + 0 * 32 + 16 * H, m);
+  float m[8], v[8], u[8];
+  dt_ld8(tlane + 0 * 64 + 8 * Q, m);
+  dt_ld8(tlane + 0 * 64 + 32 + 8 * Q, u);                     // the A_hi W_lo half of the accumulator
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] += u[j];
 #pragma unroll
   for (int ph = 1; ph < 4; ++ph) {
-    dt_ld16(tlane + ph * 32 + 16 * H, v);
+    dt_ld8(tlane + ph * 64 + 8 * Q, v);
+    dt_ld8(tlane + ph * 64 + 32 + 8 * Q, u);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], v[j]);
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j] + u[j]);
   }
   if (real) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j] + P.prm[DT_P_B2 + 16 * H + j], 0.f);
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j] + P.prm[DT_P_B2 + 8 * Q + j], 0.f);
+    dt_store8(a2_pos + (0 * 4 + Q) * DT_PLANE, a2_pos + (1 * 4 + Q) * DT_PLANE, m);
+  }
+}
+
+// epilogue of e3: bias, relu -> A3; this quarter's 16 channels
+template <int Q>
+__device__ __forceinline__ void dt_epi3(const DnTcParams& P, uint32_t tlane, bool real, uint32_t a3_pos) {
+  float v[16];
+  dt_ld16(tlane + 256 + 16 * Q, v);
+  if (real) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + P.prm[DT_P_B3 + 16 * Q + j], 0.f);
 #pragma unroll
     for (int g = 0; g < 2; ++g)
-      dt_store8(a2_pos + (0 * 4 + 2 * H + g) * DT_PLANE, a2_pos + (1 * 4 + 2 * H + g) * DT_PLANE, m + 8 * g);
+      dt_store8(a3_pos + (0 * 8 + 2 * Q + g) * DT_PLANE, a3_pos + (1 * 8 + 2 * Q + g) * DT_PLANE, v + 8 * g);
   }
 }
 
-// epilogue of e3: bias, relu -> A3; this half's 32 channels
-template <int H>
-__device__ __forceinline__ void dt_epi3(const DnTcParams& P, uint32_t tlane, bool real, uint32_t a3_pos) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    float v[16];
-    dt_ld16(tlane + 128 + 32 * H + 16 * q, v);
-    if (real) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + P.prm[DT_P_B3 + 32 * H + 16 * q + j], 0.f);
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        dt_store8(a3_pos + (0 * 8 + 4 * H + 2 * q + g) * DT_PLANE, a3_pos + (1 * 8 + 4 * H + 2 * q + g) * DT_PLANE, v + 8 * g);
-    }
-  }
-}
-
-// epilogue of d1: the four parity classes are the four phase planes of the 8 x 8 map; this half's two classes
-template <int H>
+// epilogue of d1: the four parity classes are the four phase planes of the 8 x 8 map; this quarter's class
+template <int Q>
 __device__ __forceinline__ void dt_epi4(const DnTcParams& P, uint32_t tlane, bool real, uint32_t a4_pos) {
 #pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int cl = 2 * H + cc;
+  for (int q = 0; q < 2; ++q) {
+    float v[16], u[16];
+    dt_ld16(tlane + Q * 64 + 16 * q, v);
+    dt_ld16(tlane + Q * 64 + 32 + 16 * q, u);
+    if (real) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      float v[16];
-      dt_ld16(tlane + 192 + cl * 32 + 16 * q, v);
-      if (real) {
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + u[j] + P.prm[DT_P_B4 + 16 * q + j], 0.f);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + P.prm[DT_P_B4 + 16 * q + j], 0.f);
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-          dt_store8(a4_pos + ((cl * 2 + 0) * 4 + 2 * q + g) * DT_PLANE, a4_pos + ((cl * 2 + 1) * 4 + 2 * q + g) * DT_PLANE, v + 8 * g);
-      }
+      for (int g = 0; g < 2; ++g)
+        dt_store8(a4_pos + ((Q * 2 + 0) * 4 + 2 * q + g) * DT_PLANE, a4_pos + ((Q * 2 + 1) * 4 + 2 * q + g) * DT_PLANE, v + 8 * g);
     }
   }
 }
 
-// epilogue of d2 + d3: this half holds the fine rows fy = 2 H, 2 H + 1 of its 4 x 4 block (8 fine pixels x 16 channels);
-// every fine pixel adds its nine taps of the transposed 3 x 3 convolution into a 4 x 6 window of partial sums, which is
-// then added to the output image of the spot
-template <int H>
-__device__ __forceinline__ void dt_epi5(const DnTcParams& P, uint32_t tlane, bool real, float* out_img, int Y, int X) {
-  // all eight fine pixels first (128 values), then every d3 weight is fetched once and feeds eight independent FMAs
-  // (the first form walked the pixels one by one: 1152 constant loads per thread, each at the head of a dependent chain)
-  float v[8][16];
+// epilogue of d2 + d3: this quarter Q = (py, px) holds the 2 x 2 fine pixels fy = 2 py + qy, fx = 2 px + qx of its 4 x 4
+// block (x 16 channels); every fine pixel adds its nine taps of the transposed 3 x 3 convolution into a 4 x 4 window of
+// partial sums, which is then added to the output image of the spot
+template <int Q>
+__device__ __forceinline__ void dt_epi5(const DnTcParams& P, const float* sprm, uint32_t tlane, bool real, float* out_img, int Y, int X) {
+  // all four fine pixels first, then every d3 weight is fetched once and feeds four independent FMAs
+  float v[4][16];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) dt_ld16(tlane + (H * 8 + i) * 16, v[i]);       // i = (px, qy, qx)
-  float wnd[4][6];
+  for (int i = 0; i < 4; ++i) {                                               // i = (qy, qx)
+    float u[16];
+    dt_ld16(tlane + (Q * 4 + i) * 32, v[i]);
+    dt_ld16(tlane + (Q * 4 + i) * 32 + 16, u);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[i][j] += u[j];
+  }
+  float wnd[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 6; ++b) wnd[a][b] = 0.f;
+    for (int b = 0; b < 4; ++b) wnd[a][b] = 0.f;
   if (real) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[i][j] = fmaxf(v[i][j] + P.prm[DT_P_B5 + j], 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        float acc[8];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 t = *reinterpret_cast<const float4*>(sprm + 192 + (ky * 3 + kx) * 16 + 4 * j4);
+          const float w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float w = P.prm[DT_P_W6 + j * 9 + ky * 3 + kx];
+          for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i][j], w, acc[i]);
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i][4 * j4 + jj], w[jj], acc[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int px = i >> 2, qy = (i >> 1) & 1, qx = i & 1;
-          wnd[qy + ky][2 * px + qx + kx] += acc[i];
-        }
+        for (int i = 0; i < 4; ++i) wnd[(i >> 1) + ky][(i & 1) + kx] += acc[i];
       }
   }
-  // the windows of neighbouring threads overlap: eight colours (half, parity of Y, parity of X) whose windows are disjoint
-  // add in turn, so that the sum order -- and with it every output bit -- is the same in every run and batch split
-  const int colour = H * 4 + (Y & 1) * 2 + (X & 1);
-#pragma unroll 1
-  for (int ph = 0; ph < 8; ++ph) {
-    if (real && ph == colour) {
+  // the windows of neighbouring threads overlap: each thread parks its own in shared memory, and every output pixel then
+  // sums its (at most four, one per quarter) contributions in a fixed order -- reproducible bit for bit, one barrier
+  // (a first form added the windows in 16 colour phases separated by barriers: ~5 k cycles per pass)
+  if (real) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int row = 4 * Y + 2 * H + a - 1;
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-          const int col = 4 * X + b - 1;
-          if (row >= 0 && row < 16 && col >= 0 && col < 16) out_img[row * 16 + col] += wnd[a][b];
-        }
-      }
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int a = 0; a < 4; ++a)
+      *reinterpret_cast<float4*>(out_img + ((Y * 4 + X) * 4 + Q) * 16 + 4 * a) = make_float4(wnd[a][0], wnd[a][1], wnd[a][2], wnd[a][3]);
   }
 }
 
@@ -375,26 +393,29 @@ constexpr uint32_t DT_ID16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24
 constexpr uint32_t DT_ID32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t DT_ID64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
-// e2, output phase PH: nine taps, K = 16, weights in buffer 0
+// Weight tiles of e2, d1, d2 hold the hi rows and the lo rows of W side by side (2N rows): A_hi x tile gives A_hi W_hi and
+// A_hi W_lo in ONE instruction of width 2N (columns [0, N) and [N, 2N) of the accumulator), A_lo x its first N rows adds
+// A_lo W_hi to [0, N) -- two MMAs per product instead of three at the same ~40-cycle floor; the epilogue adds the halves.
+
+// e2, output phase PH: nine taps, K = 16, weights in buffer 0; accumulator columns PH * 64 .. + 63
 template <int PH>
 __device__ __noinline__ void dt_issue_e2(uint32_t tmem_u) {
   constexpr int py = PH >> 1, px = PH & 1;
-  const uint32_t d = tmem_u + PH * 32;
+  const uint32_t d = tmem_u + PH * 64;
   dt_for<0, 9>([&](auto tc) {
     constexpr int tap = decltype(tc)::value, dy = tap / 3 - 1, dx = tap % 3 - 1;
     constexpr int iph = ((py + dy) & 1) * 2 + ((px + dx) & 1);
     constexpr int sh = dt_floor2(py + dy) * DT_PITCH + dt_floor2(px + dx);
     constexpr uint32_t a_hi = DT_QA14 + ((iph * 2 + 0) * 2) * DT_PQ + sh, a_lo = DT_QA14 + ((iph * 2 + 1) * 2) * DT_PQ + sh;
-    constexpr uint32_t b_hi = DT_QW0 + tap * 128 + (32u << 16), b_lo = b_hi + 64;
-    dt_mma_c<a_hi, b_hi, (tap ? 1u : 0u)>(d, DT_ID32);
-    dt_mma_c<a_lo, b_hi, 1u>(d, DT_ID32);
-    dt_mma_c<a_hi, b_lo, 1u>(d, DT_ID32);
+    constexpr uint32_t b = DT_QW0 + tap * 128 + (64u << 16);
+    dt_mma_c<a_hi, b, (tap ? 1u : 0u)>(d, DT_ID64);
+    dt_mma_c<a_lo, b, 1u>(d, DT_ID32);
   });
 }
 // e3, taps T0 .. T0 + 2: high weight parts from buffer 1 (LO = 0: two products) or low parts from buffer 0 (LO = 1)
 template <int T0, int LO>
 __device__ __noinline__ void dt_issue_e3(uint32_t tmem_u) {
-  const uint32_t d = tmem_u + 128;
+  const uint32_t d = tmem_u + 256;
   dt_for<0, 6>([&](auto ic) {
     constexpr int tap = T0 + (decltype(ic)::value >> 1), ks = decltype(ic)::value & 1;
     constexpr int sh = (tap / 3 - 1) * DT_PITCH + tap % 3 - 1;
@@ -408,39 +429,48 @@ __device__ __noinline__ void dt_issue_e3(uint32_t tmem_u) {
     }
   });
 }
-// d1, parity class CL, tap T: K = 64
+// d1, parity class CL, tap T: K = 64; accumulator columns CL * 64 .. + 63
 template <int CL, int T>
 __device__ __noinline__ void dt_issue_d1(uint32_t tmem_u) {
   constexpr int py = CL >> 1, px = CL & 1;
   constexpr uint32_t wq = (CL & 1) ? DT_QW0 : DT_QW1;
-  const uint32_t d = tmem_u + 192 + CL * 32;
+  const uint32_t d = tmem_u + CL * 64;
   constexpr int sh = dt_ct_d(py, T >> 1) * DT_PITCH + dt_ct_d(px, T & 1);
   dt_for<0, 4>([&](auto kc) {
     constexpr int ks = decltype(kc)::value;
     constexpr uint32_t a_hi = DT_QA3 + (0 * 8 + 2 * ks) * DT_PQ + sh, a_lo = DT_QA3 + (1 * 8 + 2 * ks) * DT_PQ + sh;
-    constexpr uint32_t b_hi = wq + T * 512 + ks * 64 + (32u << 16), b_lo = b_hi + 256;
-    dt_mma_c<a_hi, b_hi, ((T | ks) ? 1u : 0u)>(d, DT_ID32);
-    dt_mma_c<a_lo, b_hi, 1u>(d, DT_ID32);
-    dt_mma_c<a_hi, b_lo, 1u>(d, DT_ID32);
+    constexpr uint32_t b = wq + T * 512 + ks * 128 + (64u << 16);
+    dt_mma_c<a_hi, b, ((T | ks) ? 1u : 0u)>(d, DT_ID64);
+    dt_mma_c<a_lo, b, 1u>(d, DT_ID32);
   });
 }
-// d2, (input phase, output parity) class SC: four taps, K = 32, weights in buffer 1
+// d2, (input phase, output parity) class SC: four taps, K = 32, weights in buffer 1; accumulator columns SC * 32 .. + 31
 template <int SC>
 __device__ __noinline__ void dt_issue_d2(uint32_t tmem_u) {
   constexpr int py = SC >> 3, px = (SC >> 2) & 1, qy = (SC >> 1) & 1, qx = SC & 1;
-  const uint32_t d = tmem_u + SC * 16;
+  const uint32_t d = tmem_u + SC * 32;
   dt_for<0, 8>([&](auto ic) {
     constexpr int t = decltype(ic)::value >> 1, ks = decltype(ic)::value & 1;
     constexpr int ky = dt_ct_k(qy, t >> 1), dy = dt_ct_d(qy, t >> 1), kx = dt_ct_k(qx, t & 1), dx = dt_ct_d(qx, t & 1);
     constexpr int iph = ((py + dy) & 1) * 2 + ((px + dx) & 1);
     constexpr int sh = dt_floor2(py + dy) * DT_PITCH + dt_floor2(px + dx);
-    constexpr uint32_t bt = DT_QW1 + (ky * 4 + kx) * 128 + (16u << 16);
+    constexpr uint32_t b = DT_QW1 + (ky * 4 + kx) * 128 + ks * 64 + (32u << 16);
     constexpr uint32_t a_hi = DT_QA14 + ((iph * 2 + 0) * 4 + 2 * ks) * DT_PQ + sh, a_lo = DT_QA14 + ((iph * 2 + 1) * 4 + 2 * ks) * DT_PQ + sh;
-    constexpr uint32_t b_hi = bt + ks * 32, b_lo = b_hi + 64;
-    dt_mma_c<a_hi, b_hi, ((t | ks) ? 1u : 0u)>(d, DT_ID16);
-    dt_mma_c<a_lo, b_hi, 1u>(d, DT_ID16);
-    dt_mma_c<a_hi, b_lo, 1u>(d, DT_ID16);
+    dt_mma_c<a_hi, b, ((t | ks) ? 1u : 0u)>(d, DT_ID32);
+    dt_mma_c<a_lo, b, 1u>(d, DT_ID16);
   });
+}
+
+// the spots of pass `pass` into the padded input images, asynchronously (cp.async): HBM latency hides behind a whole pass
+__device__ __forceinline__ void dt_fetch_input(const DnTcParams& P, long long pass, int tid, uint32_t img_u32) {
+  const long long spot0 = pass * DT_G;
+  const int ns = (int)((P.n_spots - spot0) < DT_G ? (P.n_spots - spot0) : DT_G);
+  for (int i = tid; i < ns * 256; i += 32 * DT_EPI_WARPS) {
+    const int sp = i >> 8, px = i & 255;
+    const uint32_t dst = img_u32 + 4u * (uint32_t)(sp * 324 + (1 + (px >> 4)) * 18 + 1 + (px & 15));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(P.in + (spot0 + sp) * 256 + px) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_constant__ DnTcParams P) {
@@ -455,11 +485,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
 
   for (int i = tid; i < DT_OFF_W / 16; i += DT_THREADS) reinterpret_cast<uint4*>(dt_sm)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < (DT_OFF_BAR - DT_OFF_IN) / 4; i += DT_THREADS) reinterpret_cast<float*>(dt_sm + DT_OFF_IN)[i] = 0.f;
+  // e1 / d3 weights into shared memory: as kernel-argument constants they became uniform-register operands, and FFMA with
+  // a uniform operand issued at a quarter of the rate (both phases took 9 k cycles for 2.3 k FFMA per scheduler)
+  {
+    float* sp = reinterpret_cast<float*>(dt_sm + DT_OFF_SPRM);
+    for (int i = tid; i < 16 * 12; i += DT_THREADS) sp[i] = (i % 12) < 9 ? P.prm[DT_P_W1 + (i / 12) * 9 + i % 12] : 0.f;
+    for (int i = tid; i < 9 * 16; i += DT_THREADS) sp[192 + i] = P.prm[DT_P_W6 + (i % 16) * 9 + i / 16];
+  }
   if (tid == 0) {
     for (int b = 0; b < 5; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_w0 + 8 * b) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == DT_EPI_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + DT_OFF_BAR + 40), "r"((uint32_t)DT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -470,21 +507,22 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
   const uint32_t tmem = *tmem_slot;
 
   const long long n_pass = (P.n_spots + DT_G - 1) / DT_G;
-  const bool w8 = warp == 8;      // the issuing lane is re-elected at every control block (see above)
+  const bool w8 = warp == DT_EPI_WARPS;      // the issuing lane is re-elected at every control block (see above)
   const uint32_t wb0 = sb + DT_OFF_W, wb1 = wb0 + DT_WBUF;
   // mbarrier phases: each weight buffer completes four chunks per pass and bar_ca two, so their parities are fixed per
   // use; bar_cb completes once per pass, bar_mma four times (tracked by every thread)
   uint32_t pm = 0, pcb = 0;
 
   // this thread's coarse position (epilogue warps): TMEM lane m = UMMA row = linear position q
-  const int m = 32 * (warp & 3) + lane, half = (warp >> 2) & 1;
+  const int m = 32 * (warp & 3) + lane, quarter = (warp >> 2) & 3;
   const int r = m / DT_PITCH, c = m - r * DT_PITCH;
   const int s = r >= 1 ? (r - 1) / 5 : 0, Y = r >= 1 ? (r - 1) % 5 : 4, X = c - 1;
-  const bool is_pos = warp < 8 && r >= 1 && c >= 1 && Y < 4 && s < DT_G;
+  const bool is_pos = warp < DT_EPI_WARPS && r >= 1 && c >= 1 && Y < 4 && s < DT_G;
   const uint32_t tlane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
   const uint32_t pos_off = (uint32_t)(DT_LEAD + m) * 16;
   float* img_in = reinterpret_cast<float*>(dt_sm + DT_OFF_IN);
   float* img_out = reinterpret_cast<float*>(dt_sm + DT_OFF_OUT);
+  const float* sprm = reinterpret_cast<const float*>(dt_sm + DT_OFF_SPRM);
 
   if (w8 && (long long)blockIdx.x < n_pass && dt_elect()) {
     dt_bulk(wb0, P.wblob + 0, 18432, bar_w0);
@@ -506,6 +544,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
   for (int i = 0; i < 15; ++i) cacc[i] = 0;
 #define DT_CT0 if (P.dbg) cprev = clock64();
 #define DT_CT(i) if (P.dbg) { const long long tn = clock64(); cacc[i] += tn - cprev; cprev = tn; }
+  if (warp < DT_EPI_WARPS && (long long)blockIdx.x < n_pass) dt_fetch_input(P, blockIdx.x, tid, sb + DT_OFF_IN);
 #pragma unroll 1
   for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
     if (P.dbg) tprev = clock64();
@@ -515,15 +554,16 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
     const bool real = is_pos && s < ns;
 
     // ---- input spots -> padded images; e1 -> A1s
-    if (warp < 8) {
-      for (int i = tid; i < ns * 256; i += 256) {
-        const int sp = i >> 8, px = i & 255;
-        img_in[sp * 324 + (1 + (px >> 4)) * 18 + 1 + (px & 15)] = __ldg(P.in + (spot0 + sp) * 256 + px);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (warp < DT_EPI_WARPS) {
+      asm volatile("cp.async.wait_all;" ::: "memory");        // this pass's spots, requested a pass ago (dt_fetch_input)
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       if (real) {
-        if (half == 0) dt_layer1<0>(P, img_in + s * 324, Y, X, sb + DT_OFF_A14 + pos_off);
-        else dt_layer1<1>(P, img_in + s * 324, Y, X, sb + DT_OFF_A14 + pos_off);
+        switch (quarter) {
+          case 0: dt_layer1<0>(P, sprm, img_in + s * 324, Y, X, sb + DT_OFF_A14 + pos_off); break;
+          case 1: dt_layer1<1>(P, sprm, img_in + s * 324, Y, X, sb + DT_OFF_A14 + pos_off); break;
+          case 2: dt_layer1<2>(P, sprm, img_in + s * 324, Y, X, sb + DT_OFF_A14 + pos_off); break;
+          default: dt_layer1<3>(P, sprm, img_in + s * 324, Y, X, sb + DT_OFF_A14 + pos_off); break;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -531,6 +571,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     DT_TICK(0)
+    if (warp < DT_EPI_WARPS && has_next) dt_fetch_input(P, pass + gridDim.x, tid, sb + DT_OFF_IN);   // e1 has read this pass's images
 
     // ---- e2: four output phases x nine taps, K = 16
     if (w8 && dt_elect()) {
@@ -548,9 +589,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     DT_TICK(1)
     if (w8 && dt_elect()) dt_bulk(wb0, P.wblob + 55296, 36864, bar_w0);                  // e3 low parts
-    if (warp < 8) {
-      if (half == 0) dt_epi2<0>(P, tlane, real, sb + DT_OFF_A2 + pos_off);
-      else dt_epi2<1>(P, tlane, real, sb + DT_OFF_A2 + pos_off);
+    if (warp < DT_EPI_WARPS) {
+      switch (quarter) {
+        case 0: dt_epi2<0>(P, tlane, real, sb + DT_OFF_A2 + pos_off); break;
+        case 1: dt_epi2<1>(P, tlane, real, sb + DT_OFF_A2 + pos_off); break;
+        case 2: dt_epi2<2>(P, tlane, real, sb + DT_OFF_A2 + pos_off); break;
+        default: dt_epi2<3>(P, tlane, real, sb + DT_OFF_A2 + pos_off); break;
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -581,9 +626,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
       dt_bulk(wb1, P.wblob + 92160, 32768, bar_w1);                           // d1 class 0
       dt_bulk(wb0, P.wblob + 124928, 32768, bar_w0);                          // d1 class 1
     }
-    if (warp < 8) {
-      if (half == 0) dt_epi3<0>(P, tlane, real, sb + DT_OFF_A3 + pos_off);
-      else dt_epi3<1>(P, tlane, real, sb + DT_OFF_A3 + pos_off);
+    if (warp < DT_EPI_WARPS) {
+      switch (quarter) {
+        case 0: dt_epi3<0>(P, tlane, real, sb + DT_OFF_A3 + pos_off); break;
+        case 1: dt_epi3<1>(P, tlane, real, sb + DT_OFF_A3 + pos_off); break;
+        case 2: dt_epi3<2>(P, tlane, real, sb + DT_OFF_A3 + pos_off); break;
+        default: dt_epi3<3>(P, tlane, real, sb + DT_OFF_A3 + pos_off); break;
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -626,9 +675,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
     pcb ^= 1;
     DT_TICK(5)
     if (w8 && has_next && dt_elect()) dt_bulk(wb0, P.wblob + 0, 18432, bar_w0);           // next pass: e2
-    if (warp < 8) {
-      if (half == 0) dt_epi4<0>(P, tlane, real, sb + DT_OFF_A14 + pos_off);
-      else dt_epi4<1>(P, tlane, real, sb + DT_OFF_A14 + pos_off);
+    if (warp < DT_EPI_WARPS) {
+      switch (quarter) {
+        case 0: dt_epi4<0>(P, tlane, real, sb + DT_OFF_A14 + pos_off); break;
+        case 1: dt_epi4<1>(P, tlane, real, sb + DT_OFF_A14 + pos_off); break;
+        case 2: dt_epi4<2>(P, tlane, real, sb + DT_OFF_A14 + pos_off); break;
+        default: dt_epi4<3>(P, tlane, real, sb + DT_OFF_A14 + pos_off); break;
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -652,14 +705,25 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     DT_TICK(7)
     if (w8 && has_next && dt_elect()) dt_bulk(wb1, P.wblob + 18432, 36864, bar_w1);       // next pass: e3 high parts
-    if (warp < 8) {
-      if (half == 0) dt_epi5<0>(P, tlane, real, img_out + s * 256, Y, X);
-      else dt_epi5<1>(P, tlane, real, img_out + s * 256, Y, X);
+    if (warp < DT_EPI_WARPS) {
+      switch (quarter) {
+        case 0: dt_epi5<0>(P, sprm, tlane, real, img_out + s * 1024, Y, X); break;
+        case 1: dt_epi5<1>(P, sprm, tlane, real, img_out + s * 1024, Y, X); break;
+        case 2: dt_epi5<2>(P, sprm, tlane, real, img_out + s * 1024, Y, X); break;
+        default: dt_epi5<3>(P, sprm, tlane, real, img_out + s * 1024, Y, X); break;
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       const float invs = P.prm[DT_P_INVS], b6 = P.prm[DT_P_B6];
-      for (int i = tid; i < ns * 256; i += 256) {
-        const float v = img_out[i];
-        img_out[i] = 0.f;
-        P.out[spot0 * 256 + i] = fmaf(v, invs, b6);
+      for (int i = tid; i < ns * 256; i += 32 * DT_EPI_WARPS) {
+        const int sp = i >> 8, row = (i >> 4) & 15, col = i & 15;
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                          // window row a of cell Yc, quarter (py, px): row = 4 Yc + 2 py + a - 1
+          const int ty = row + 1 - 2 * (q >> 1), tx = col + 1 - 2 * (q & 1);
+          if (ty >= 0 && tx >= 0 && ty < 16 && tx < 16)
+            sum += img_out[sp * 1024 + (((ty >> 2) * 4 + (tx >> 2)) * 4 + q) * 16 + (ty & 3) * 4 + (tx & 3)];
+        }
+        P.out[spot0 * 256 + i] = fmaf(sum, invs, b6);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -672,6 +736,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) denoise_tc_kernel(const __grid_
   if (P.dbg && blockIdx.x == 0 && w8 && dt_elect())
     for (int i = 0; i < 15; ++i) P.dbg[16 + i] = cacc[i];
 
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)DT_TMEM_COLS) : "memory");
+  if (warp == DT_EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)DT_TMEM_COLS) : "memory");
 }
 #endif  // DT_DEFINE_KERNELS

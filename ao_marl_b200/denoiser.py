@@ -88,6 +88,17 @@ def _tile_f16(w_nk):
     return order(hi), order(lo)
 
 
+def _tile_f16_merged(w_nk):
+    """[N][K] float -> one fp16 tile of 2N rows, hi rows then lo rows, in the UMMA K-major order [K / 8][2N][8]: A_hi times
+    the whole tile gives A_hi W_hi and A_hi W_lo side by side in one instruction, A_lo times its first N rows A_lo W_hi."""
+    w = np.asarray(w_nk, np.float32)
+    hi = w.astype(np.float16)
+    lo = (w - hi.astype(np.float32)).astype(np.float16)
+    both = np.concatenate([hi, lo], axis=0)
+    n2, k = both.shape
+    return np.ascontiguousarray(both.reshape(n2, k // 8, 8).transpose(1, 0, 2)).reshape(-1)
+
+
 def pack_weights_tc(state_dict, as_float=False):
     """Weight tiles of the four tensor-core layers in the order the kernel streams them, and the float parameters of the
     two SIMT layers + the (scaled) biases.  as_float: float64 tiles as a dict (profiles/dev/denoise_tc_model.py)."""
@@ -104,15 +115,11 @@ def pack_weights_tc(state_dict, as_float=False):
         return dict(L2=[f(t) for t in L2], L3=[f(t) for t in L3], L4=[[f(t) for t in c] for c in L4], L5=[f(t) for t in L5],
                     b2=f(sd["encoder2.bias"]) * S, b3=f(sd["encoder3.bias"]) * S, b4=f(sd["decoder1.bias"]) * S,
                     b5=f(sd["decoder2.bias"]) * S)
-    parts = []
-    for t in L2:
-        parts += list(_tile_f16(t))
-    parts += [_tile_f16(t)[0] for t in L3] + [_tile_f16(t)[1] for t in L3]
+    parts = [_tile_f16_merged(t) for t in L2]                                            # e2: hi | lo side by side
+    parts += [_tile_f16(t)[0] for t in L3] + [_tile_f16(t)[1] for t in L3]               # e3: hi chunk, lo chunk
     for c in L4:
-        for t in c:
-            parts += list(_tile_f16(t))
-    for t in L5:
-        parts += list(_tile_f16(t))
+        parts += [_tile_f16_merged(t) for t in c]                                        # d1
+    parts += [_tile_f16_merged(t) for t in L5]                                           # d2
     blob = np.concatenate(parts)
     assert blob.nbytes == DT["CHUNKS"][-1], blob.nbytes
     prm = np.concatenate([sd["encoder1.weight"].reshape(16, 9).reshape(-1), sd["encoder1.bias"],
