@@ -262,6 +262,7 @@ def system10(static10, oracle_imat10, torch):
     rl = RLLayout(t.Btt.shape[1], dict(parameters_telescope="production_sh_10x10_2m.py", n_zernike_start_end=[0, 80],
                                        n_reverse_filtered_from_cmat=5), None, world_size=3, seed=3)
     import torch as th
+    th.manual_seed(20240607)     # reproducible heads: an unseeded draw once gave a 1e-3 action outlier in 1 of ~10 runs
     with th.no_grad():           # non-trivial heads so that actions are not all zero-mean/unit-std
         for p in rl.policies:
             p.mean_linear.weight.normal_(0, 0.05)

@@ -398,6 +398,7 @@ def test_40x40_closed_loop_against_oracle(tables40, torch):
                               tables=tables40)
     try:
         import torch as th
+        th.manual_seed(20240607)     # reproducible heads: an unseeded draw once gave a 1e-3 action outlier in 1 of ~10 runs
         with th.no_grad():       # non-trivial heads (the reference zero-initialises them: every action would be noise only)
             for p in rl.policies:
                 p.mean_linear.weight.normal_(0, 0.05)
