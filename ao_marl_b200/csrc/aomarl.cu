@@ -1234,7 +1234,7 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
     CU(cudaEventRecord(ctx->wev[1][ctx->wev_n], st));
     ctx->wev_n++;
   }
-  ctx->frame++;
+  if (!(flags & 8)) ctx->frame++;        // bit3: an extra look at the same frame (ROKET's noise-free image): noise stream untouched
   ctx->cube_override = nullptr;
   return AOM_OK;
 }
@@ -1276,9 +1276,28 @@ extern "C" int aom_raytrace_wfs(aom_ctx* ctx, int flags, void* stream) {
   WfsParams p;
   int rc = fill_wfs_params(ctx, p, flags, -1.f);
   if (rc) return rc;
+  if (flags & AOM_TAR_GEO) {                       // through the geometric controller's mirrors instead of the main ones
+    rc = geo_prepare(ctx);
+    if (rc) return rc;
+    p.volts = ctx->geo_volts;
+  }
   if (!ctx->phase) CU(dalloc(&ctx->phase, (size_t)c.n_env * c.n * c.n));
   dim3 blk(32, 8), grid((c.n + 31) / 32, (c.n + 7) / 8, c.n_env);
   wfs_phase_kernel<<<grid, blk, 0, st>>>(p, ctx->phase);
+  KCHECK();
+  return AOM_OK;
+}
+
+extern "C" int aom_do_centroids_geom(aom_ctx* ctx, int flags, float alpha, void* stream) {
+  if (!ctx) return AOM_ERR_INVALID;
+  const aom_config& c = ctx->cfg;
+  if (c.pdiam != 16) return fail(ctx, AOM_ERR_UNSUPPORTED, "geometric slopes need 16-pixel subapertures");
+  int rc = aom_raytrace_wfs(ctx, flags, stream);
+  if (rc) return rc;
+  WfsParams p;
+  rc = fill_wfs_params(ctx, p, flags, -1.f);
+  if (rc) return rc;
+  slopes_geom_kernel<<<dim3(c.nvalid, c.n_env), 256, 0, (cudaStream_t)stream>>>(p, ctx->phase, ctx->slopes, ctx->lds, alpha);
   KCHECK();
   return AOM_OK;
 }

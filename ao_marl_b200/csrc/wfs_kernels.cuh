@@ -407,6 +407,38 @@ __global__ void target_strehl_kernel(const double* mom, int stride, float* streh
   }
 }
 
+// Geometric slopes of a materialised pupil phase [E][n][n] (RtcCompass.do_centroids_geom, rtcCompass.py; sutra slopes_geom,
+// un-vendored -- the convention of oracle/aoframe.py::slopes_geom and init/rtc.py::geometric_slopes, which the actuator
+// filtering of the reference's imat_geom pins): central differences inside the 16 x 16 tile, one-sided at its edge, masked
+// by the pupil, summed / pdiam / 2, times alpha = 0.206265 / subaperture size, divided by the subaperture's flux fraction.
+// grid (nvalid, E), block 256 (one thread per pixel of the tile).
+__global__ void __launch_bounds__(256) slopes_geom_kernel(WfsParams p, const float* __restrict__ phase, float* __restrict__ slopes,
+                                                          int lds, float alpha) {
+  const int k = blockIdx.x, e = blockIdx.y;
+  const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+  const int x0 = p.sub_x0[k], y0 = p.sub_y0[k];
+  const float* ph = phase + (size_t)e * p.n * p.n;
+  auto at = [&](int rr, int cc) { return ph[(size_t)(y0 + rr) * p.n + x0 + cc]; };
+  const float m = p.mpupil[(size_t)(y0 + r) * p.n + x0 + c];
+  const float gx = (c == 0) ? at(r, 1) - at(r, 0) : (c == 15) ? at(r, 15) - at(r, 14) : at(r, c + 1) - at(r, c - 1);
+  const float gy = (r == 0) ? at(1, c) - at(0, c) : (r == 15) ? at(15, c) - at(14, c) : at(r + 1, c) - at(r - 1, c);
+  float sx = gx * m, sy = gy * m;
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, sft);
+    sy += __shfl_xor_sync(0xffffffffu, sy, sft);
+  }
+  __shared__ float red[2][8];
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sx; red[1][threadIdx.x >> 5] = sy; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    slopes[(size_t)e * lds + threadIdx.x * p.nvalid + k] = t / 16.f / 2.f * alpha / p.flux[k];
+  }
+}
+
 // Centre of gravity of an externally supplied detector cube [E][nvalid][256] (denoiser path).
 __global__ void cog_kernel(const float* cube, float* slopes, int lds, int nvalid, long long total,
                            float cog_offset, float pixsize) {

@@ -15,17 +15,21 @@ from ..supervisor.rlSupervisor import RlSupervisor
 class AoEnv:
     def __init__(self, config_rl, normalization_bool=True, build_cmat_with_modes=True, initial_seed=-1,
                  geo_policy_testing=False, roket=False, n_env=1, world_size=None, tables=None, autoencoder=None):
-        if geo_policy_testing or roket:
-            raise NotImplementedError("GEO controller / ROKET drivers are outside the hot-path scope")
+        if geo_policy_testing:
+            raise NotImplementedError("the GEO policy-testing driver is outside the hot-path scope")
         if not normalization_bool:
             raise NotImplementedError("un-normalised states are outside the hot-path scope")
         self.normalization_bool = normalization_bool
         self.config_rl = config_rl
         self.n_env = int(n_env)
         config = load_config_from_file(config_rl.env_rl["parameters_telescope"])
-        self.supervisor = RlSupervisor(config, config_rl, build_cmat_with_modes=build_cmat_with_modes,
-                                       initial_seed=initial_seed, autoencoder=autoencoder, n_env=n_env,
-                                       world_size=world_size, tables=tables)
+        if roket:                      # ao_env.py:118-125: the supervisor with the error breakdown
+            from ..guardians.roket import Roket as Supervisor
+        else:
+            Supervisor = RlSupervisor
+        self.supervisor = Supervisor(config, config_rl, build_cmat_with_modes=build_cmat_with_modes,
+                                     initial_seed=initial_seed, autoencoder=autoencoder, n_env=n_env,
+                                     world_size=world_size, tables=tables)
         rl = self.supervisor.rl
         self.sim = self.supervisor.sim
         self.norm_parameters = rl.norm

@@ -52,7 +52,7 @@ O = {name: i for i, name in enumerate(OPTIONS)}
 
 EXPORTS = ["aom_config_size", "aom_create", "aom_destroy", "aom_last_error", "aom_set_table", "aom_get_buffer",
            "aom_device_count_launches", "aom_set_option", "aom_check_device", "aom_reset", "aom_move_atmos", "aom_set_layer", "aom_set_layer_amp", "aom_comp_wfs_image", "aom_wfs_kernel", "aom_wfs_time_ms", "aom_raytrace_wfs",
-           "aom_comp_strehl", "aom_reset_strehl", "aom_do_control_geo", "aom_apply_control_geo", "aom_denoise", "aom_set_bincube", "aom_do_centroids", "aom_do_control", "aom_set_command", "aom_apply_control",
+           "aom_comp_strehl", "aom_reset_strehl", "aom_do_control_geo", "aom_apply_control_geo", "aom_denoise", "aom_set_bincube", "aom_do_centroids", "aom_do_centroids_geom", "aom_do_control", "aom_set_command", "aom_apply_control",
            "aom_set_gain", "aom_set_loop", "aom_reset_dm", "aom_set_dm_volts", "aom_rl_control",
            "aom_state_begin", "aom_state_end", "aom_reward", "aom_actor_forward", "aom_step", "aom_gemm_tn",
            "aom_pixel_noise"]
@@ -100,6 +100,7 @@ def load_library():
     lib.aom_do_control_geo.argtypes = [vp, vp]
     lib.aom_apply_control_geo.argtypes = [vp, vp]
     lib.aom_denoise.argtypes = [vp, vp, vp, i64, vp]
+    lib.aom_do_centroids_geom.argtypes = [vp, i32, ctypes.c_float, vp]
     lib.aom_set_bincube.argtypes = [vp, vp, vp]
     lib.aom_do_centroids.argtypes = [vp, vp]
     lib.aom_do_control.argtypes = [vp, vp]
@@ -385,13 +386,19 @@ class Simulator:
         amp = np.ascontiguousarray(np.broadcast_to(np.asarray(amp, dtype=np.float32), (self.n_env,)))
         self._check(self.lib.aom_set_layer_amp(self._ctx, int(layer), amp.ctypes.data_as(ctypes.c_void_p)), "aom_set_layer_amp")
 
-    def comp_wfs_image(self, atmos=True, dms=True, keep_image=False, noise=None):
-        flags = (1 if atmos else 0) | (2 if dms else 0) | (4 if keep_image else 0)
+    def comp_wfs_image(self, atmos=True, dms=True, keep_image=False, noise=None, advance_frame=True):
+        flags = (1 if atmos else 0) | (2 if dms else 0) | (4 if keep_image else 0) | (0 if advance_frame else 8)
         noise = float(self.cfg.noise if noise is None else noise)
         self._check(self.lib.aom_comp_wfs_image(self._ctx, flags, noise, self.stream), "aom_comp_wfs_image")
 
-    def raytrace_wfs(self, atmos=True, dms=True):
-        flags = (1 if atmos else 0) | (2 if dms else 0)
+    def do_centroids_geom(self, atmos=True, dms=True, geo=False):
+        """Geometric slopes (mean phase gradient per subaperture) of the sensor-direction phase -> SLOPES."""
+        flags = (1 if atmos else 0) | (2 if dms else 0) | (0x100 if geo else 0)
+        alpha = 0.206265 / float(self.tables.p_wfs._subapd)
+        self._check(self.lib.aom_do_centroids_geom(self._ctx, flags, alpha, self.stream), "aom_do_centroids_geom")
+
+    def raytrace_wfs(self, atmos=True, dms=True, geo=False):
+        flags = (1 if atmos else 0) | (2 if dms else 0) | (0x100 if geo else 0)
         self._check(self.lib.aom_raytrace_wfs(self._ctx, flags, self.stream), "aom_raytrace_wfs")
         return self.buffer("PHASE").view(self.n_env, self.cfg.n, self.cfg.n)
 

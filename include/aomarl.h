@@ -238,7 +238,8 @@ int aom_set_layer(aom_ctx* ctx, int layer, float deltax, float deltay, float amp
 int aom_set_layer_amp(aom_ctx* ctx, int layer, const float* amp_host);
 
 /* WfsCompass.raytrace + compute_wfs_image fused (wfsCompass.py:334-343, sourceCompass.py:54-85).
- * flags: bit0 atmosphere, bit1 mirrors, bit2 keep image (writes AOM_B_BINCUBE). noise: sensor noise for
+ * flags: bit0 atmosphere, bit1 mirrors, bit2 keep image (writes AOM_B_BINCUBE), bit3 do not advance the frame counter
+ * of the noise streams (a second look at the same frame, e.g. d_binimg_notnoisy of roket_generalized_rl.py:197). noise: sensor noise for
  * this frame (pass cfg.noise for the configured value).  Also leaves the centre-of-gravity slopes of the
  * frame for aom_do_centroids. */
 int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* stream);
@@ -297,6 +298,10 @@ int aom_denoise(aom_ctx* ctx, const float* din, float* dout, long long n_spots, 
 
 /* RtcCompass.do_centroids / do_control / set_command / apply_control (rtcCompass.py:557-563, 527-547, 463-473, 573-582) */
 int aom_do_centroids(aom_ctx* ctx, void* stream);
+/* RtcCompass.do_centroids_geom (rtcCompass.py; used by guardians/roket_generalized_rl.py:228, 246): AOM_B_SLOPES <- the mean
+ * phase gradient per subaperture of the sensor-direction phase selected by flags (bit0 atmosphere, bit1 mirrors,
+ * AOM_TAR_GEO: the geometric controller's mirrors), alpha = 0.206265 / subaperture size [m]. */
+int aom_do_centroids_geom(aom_ctx* ctx, int flags, float alpha, void* stream);
 int aom_do_control(aom_ctx* ctx, void* stream);
 int aom_set_command(aom_ctx* ctx, const float* dcom, int ld, void* stream);
 int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream);
