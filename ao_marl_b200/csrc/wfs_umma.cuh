@@ -191,6 +191,17 @@ __device__ __forceinline__ uint32_t wu_pack(float lo_elem, float hi_elem) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ---- packed float32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of arithmetic; the kernel is
+//      bound by its instruction stream, not by the FMA pipe) ----
+typedef unsigned long long wu_f2;
+__device__ __forceinline__ wu_f2 wu_pk(float lo, float hi) { wu_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void wu_upk(wu_f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ wu_f2 wu_fma2(wu_f2 a, wu_f2 b, wu_f2 c) { wu_f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ wu_f2 wu_mul2(wu_f2 a, wu_f2 b) { wu_f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ wu_f2 wu_add2(wu_f2 a, wu_f2 b) { wu_f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ wu_f2 wu_sub2(wu_f2 a, wu_f2 b) { wu_f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ wu_f2 wu_bc(float v) { return wu_pk(v, v); }       // scalar broadcast (an operand modifier in SASS)
+
 // error-free split of a pair: hi keeps the leading 11 significant bits (exact in fp16 over |v| <= 32), lo the rest
 __device__ __forceinline__ void wu_split(float a, float b, uint32_t& hi, uint32_t& lo) {
   const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
@@ -199,34 +210,66 @@ __device__ __forceinline__ void wu_split(float a, float b, uint32_t& hi, uint32_
   lo = wu_pack(a - ah, b - bh);
 }
 
-// Bilinear sample of one staged tile at this lane's 8 pixels (row y, columns 8h .. 8h+7).  The TMA box starts at the
-// 16-byte aligned column below the tile origin, so the wanted columns begin D = origin & 3 floats into the row.
+// the same on a packed pair (one FADD2 for the two low parts)
+__device__ __forceinline__ void wu_split2(wu_f2 v, uint32_t& hi, uint32_t& lo) {
+  float a, b;
+  wu_upk(v, a, b);
+  const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  hi = wu_pack(ah, bh);
+  float la, lb;
+  wu_upk(wu_sub2(v, wu_pk(ah, bh)), la, lb);
+  lo = wu_pack(la, lb);
+}
+
+// Phase accumulators of a lane's 8 pixels (row y, columns 8h .. 8h+7): X[j] = pixels (2j, 2j+1); the taps one column to
+// the right are register pairs shifted by one pixel, so they accumulate in their own pairing Y[j] = pixels (2j+1, 2j+2)
+// plus the two end pixels as scalars, and are folded into X once after the last layer.
+struct WuPhase {
+  wu_f2 X[4];
+  wu_f2 Y[3];
+  float y0, y7;
+};
+
+// Bilinear sample of one staged tile.  The TMA box starts at the 16-byte aligned column below the tile origin (the
+// start address of a box must be 16-byte aligned: profiles/dev/tma_probe.cu), so the wanted columns begin
+// D = origin & 3 floats into the row; pixel c, tap b reads v[D + c + b].  The aligned register pairs (v[2k], v[2k+1])
+// serve the X pairing for the taps with D + b even and the Y pairing for the others.
 template <int D>
-__device__ __forceinline__ void wu_layer(const float* __restrict__ t, const WfsLayer& L, float (&ph)[8]) {
+__device__ __forceinline__ void wu_layer(const float* __restrict__ t, const WfsLayer& L, WuPhase& a) {
   float v[2][12];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    const float4 a = *reinterpret_cast<const float4*>(t + r * WU_TILE_W);
-    const float4 b = *reinterpret_cast<const float4*>(t + r * WU_TILE_W + 4);
-    v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w;
-    v[r][4] = b.x; v[r][5] = b.y; v[r][6] = b.z; v[r][7] = b.w;
+    const float4 q0 = *reinterpret_cast<const float4*>(t + r * WU_TILE_W);
+    const float4 q1 = *reinterpret_cast<const float4*>(t + r * WU_TILE_W + 4);
+    v[r][0] = q0.x; v[r][1] = q0.y; v[r][2] = q0.z; v[r][3] = q0.w;
+    v[r][4] = q1.x; v[r][5] = q1.y; v[r][6] = q1.z; v[r][7] = q1.w;
     if (D == 0) {
       v[r][8] = t[r * WU_TILE_W + 8];
     } else {
-      const float4 c = *reinterpret_cast<const float4*>(t + r * WU_TILE_W + 8);
-      v[r][8] = c.x; v[r][9] = c.y; v[r][10] = c.z; v[r][11] = c.w;
+      const float4 q2 = *reinterpret_cast<const float4*>(t + r * WU_TILE_W + 8);
+      v[r][8] = q2.x; v[r][9] = q2.y; v[r][10] = q2.z; v[r][11] = q2.w;
     }
   }
-  const float w00 = L.w00, w01 = L.w01, w10 = L.w10, w11 = L.w11;
+  constexpr int d = D >> 1;
+  // taps b = B_X feed the X pairing, taps b = 1 - B_X the Y pairing and the two end pixels
+  constexpr int B_X = D & 1;
+  const float wx0 = B_X ? L.w01 : L.w00, wx1 = B_X ? L.w11 : L.w10;       // rows 0 / 1 of the X taps
+  const float wy0 = B_X ? L.w00 : L.w01, wy1 = B_X ? L.w10 : L.w11;
+  const wu_f2 WX0 = wu_bc(wx0), WX1 = wu_bc(wx1), WY0 = wu_bc(wy0), WY1 = wu_bc(wy1);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float acc = ph[c];
-    acc = fmaf(w00, v[0][D + c], acc);
-    acc = fmaf(w01, v[0][D + c + 1], acc);
-    acc = fmaf(w10, v[1][D + c], acc);
-    acc = fmaf(w11, v[1][D + c + 1], acc);
-    ph[c] = acc;
+  for (int j = 0; j < 4; ++j) {
+    const int k = 2 * (d + j + B_X);
+    a.X[j] = wu_fma2(WX1, wu_pk(v[1][k], v[1][k + 1]), wu_fma2(WX0, wu_pk(v[0][k], v[0][k + 1]), a.X[j]));
   }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int k = 2 * (d + j + 1);
+    a.Y[j] = wu_fma2(WY1, wu_pk(v[1][k], v[1][k + 1]), wu_fma2(WY0, wu_pk(v[0][k], v[0][k + 1]), a.Y[j]));
+  }
+  // end pixels of the Y pairing: pixel 0 and pixel 7 with the tap b = 1 - B_X
+  a.y0 = fmaf(wy1, v[1][D + 1 - B_X], fmaf(wy0, v[0][D + 1 - B_X], a.y0));
+  a.y7 = fmaf(wy1, v[1][D + 8 - B_X], fmaf(wy0, v[0][D + 8 - B_X], a.y7));
 }
 
 // FULL = 1: three fp16 products in both stages (fp32-grade slopes).  0: the stage-1 result goes to stage 2 as a single
@@ -303,6 +346,7 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
   // phase in turns: t = phi / lambda - (x + y) / 128   (halfxy = pi (x + y) / 64, geom_init.py:690-701)
   const float kt = p.k2 * 0.15915494309189535f;
   const float hc0 = -(float)(y + 8 * h) * 0.0078125f;
+  const wu_f2 hc01 = wu_pk(hc0, hc0 - 0.0078125f);
 
   // A1 rows of this lane: r = 16 warp + y ; chunks (re, h) (im, h) of the hi tile, the lo tile 8 KB further
   const uint32_t a1_addr = wu_smem_u32(s_a1) + (uint32_t)((2 * warp + (y >> 3)) * 512 + (y & 7) * 16 + h * 128);
@@ -415,19 +459,19 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
   // sat in a per-thread waterfall loop of ~13 instructions).
   const uint32_t q_a1 = __shfl_sync(0xffffffffu, wu_smem_u32(s_a1) >> 4, 0), q_b1 = __shfl_sync(0xffffffffu, wu_smem_u32(s_b1) >> 4, 0);
   const uint32_t q_a2 = __shfl_sync(0xffffffffu, wu_smem_u32(s_a2) >> 4, 0), q_b2 = __shfl_sync(0xffffffffu, wu_smem_u32(s_b2) >> 4, 0);
+  const uint32_t cnt_u32 = wu_smem_u32(s_cnt);
   auto arrive_and_issue = [&](int which) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     uint32_t old = 0;
-    if (lane == 0) {
-      __threadfence_block();
-      old = atomicAdd(&s_cnt[which], 1u);
-    }
+    // one release-acquire counter update per warp (inline PTX: the compiler's atomicAdd wraps a single-lane update in
+    // its warp-aggregation sequence); the __syncwarp above orders the other lanes' stores before it
+    if (lane == 0)
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_u32 + 4u * which) : "memory");
     old = __shfl_sync(0xffffffffu, old, 0);
     if ((old & (WU_WARPS - 1)) == WU_WARPS - 1) {
       if (wu_elect()) {
-        __threadfence_block();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         constexpr uint32_t KM = (128u >> 4) << 16, HI = (512u >> 4) | (1u << 14);     // K-major: LBO 128, SBO 512
@@ -465,6 +509,7 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
     __syncwarp();
   };
 
+  const bool plain = (p.noise < 0.f) && (p.bincube == nullptr);
   // q[m]: |Y|^2 of this fx row summed over the fy pair (2m, 2m+1) -> py = 8 + m (first half) or m (second half)
   auto sq_half = [&](const uint32_t (&v)[32], float (&q)[8]) {
 #pragma unroll
@@ -475,18 +520,31 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
     }
   };
   // ---- epilogue of one subaperture: lane = kept fx index; qa / qb = the fy pairs of py 8..15 / 0..7 ----
-  auto epilogue = [&](const float (&qa)[8], const float (&qb)[8], int ie, int ik) {
+  // plain path (no noise, no image kept): the centre of gravity is scale invariant and linear in |Y|^2, so the sums
+  // over the lane's 32 values run on packed pairs straight from the accumulator: s0p = sum, syp = sum of py x value
+  auto sq_plain = [&](const uint32_t (&v)[32], float py0, wu_f2& s0p, wu_f2& syp, bool first) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const wu_f2 a = wu_pk(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]));
+      const wu_f2 b = wu_pk(__uint_as_float(v[4 * m + 2]), __uint_as_float(v[4 * m + 3]));
+      const wu_f2 t = wu_fma2(b, b, wu_mul2(a, a));
+      if (first && m == 0) {
+        s0p = t;
+        syp = wu_mul2(t, wu_bc(py0));
+      } else {
+        s0p = wu_add2(s0p, t);
+        syp = wu_fma2(t, wu_bc(py0 + (float)m), syp);
+      }
+    }
+  };
+  auto epilogue = [&](const float (&qa)[8], const float (&qb)[8], wu_f2 s0p, wu_f2 syp, int ie, int ik) {
     const int pr = lane >> 1;                                  // fx pair: kept indices 2 pr, 2 pr + 1
     const int px = (pr < 8) ? 8 + pr : pr - 8;
-    const bool plain = (p.noise < 0.f) && (p.bincube == nullptr);     // the centre of gravity is scale invariant
     float s0 = 0.f, sx = 0.f, sy = 0.f;
     if (plain) {
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        s0 += qa[m] + qb[m];
-        sy = fmaf(qa[m], (float)(8 + m), sy);
-        sy = fmaf(qb[m], (float)m, sy);
-      }
+      float a, b;
+      wu_upk(s0p, a, b); s0 = a + b;
+      wu_upk(syp, a, b); sy = a + b;
       sx = s0 * (float)px;
     } else {
       // fx half of the binning: rows 2 pr, 2 pr + 1 are lanes 2 pr, 2 pr + 1; the even lane keeps fy pairs 0..7
@@ -573,9 +631,12 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
         xy_next = sb1.x;
       }
 
-      float ph[8];
+      WuPhase acc;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) ph[c] = 0.f;
+      for (int j = 0; j < 4; ++j) acc.X[j] = 0ull;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc.Y[j] = 0ull;
+      acc.y0 = acc.y7 = 0.f;
 
       // ---- atmosphere ----
       if (NL > 0) {
@@ -587,15 +648,28 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
         for (int l = 0; l < NL; ++l) {
           const float* t = reinterpret_cast<const float*>(my_tiles + l * WU_TILE_STRIDE) + lane_off;
           switch ((c_d >> (2 * l)) & 3u) {
-            case 0: wu_layer<0>(t, p.layer[l], ph); break;
-            case 1: wu_layer<1>(t, p.layer[l], ph); break;
-            case 2: wu_layer<2>(t, p.layer[l], ph); break;
-            default: wu_layer<3>(t, p.layer[l], ph); break;
+            case 0: wu_layer<0>(t, p.layer[l], acc); break;
+            case 1: wu_layer<1>(t, p.layer[l], acc); break;
+            case 2: wu_layer<2>(t, p.layer[l], acc); break;
+            default: wu_layer<3>(t, p.layer[l], acc); break;
           }
           asm volatile("" ::: "memory");                // one layer's window in registers at a time
         }
         __syncwarp();                                   // the stage is drained: re-arm it with the next item
         if (nx_valid) issue_tiles(e, sb1);
+      }
+      // fold the right-hand taps into the pixel pairs
+      wu_f2 P[4];
+      {
+        float x0, x1, ya, yb;
+        wu_upk(acc.X[0], x0, x1); wu_upk(acc.Y[0], ya, yb);
+        P[0] = wu_pk(x0 + acc.y0, x1 + ya);
+        wu_upk(acc.X[1], x0, x1); x0 += yb; wu_upk(acc.Y[1], ya, yb);
+        P[1] = wu_pk(x0, x1 + ya);
+        wu_upk(acc.X[2], x0, x1); x0 += yb; wu_upk(acc.Y[2], ya, yb);
+        P[2] = wu_pk(x0, x1 + ya);
+        wu_upk(acc.X[3], x0, x1);
+        P[3] = wu_pk(x0 + yb, x1 + acc.y7);
       }
 
       // ---- mirrors: separable stamps of the 4 x 4 lattice neighbourhood + two tip-tilt planes ----
@@ -607,53 +681,54 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
         {
           const float4 v0 = *reinterpret_cast<const float4*>(V), v1r = *reinterpret_cast<const float4*>(V + 4);
           const float4 v2r = *reinterpret_cast<const float4*>(V + 8), v3 = *reinterpret_cast<const float4*>(V + 12);
-          u[0] = fmaf(fyv.w, v3.x, fmaf(fyv.z, v2r.x, fmaf(fyv.y, v1r.x, fyv.x * v0.x)));
-          u[1] = fmaf(fyv.w, v3.y, fmaf(fyv.z, v2r.y, fmaf(fyv.y, v1r.y, fyv.x * v0.y)));
-          u[2] = fmaf(fyv.w, v3.z, fmaf(fyv.z, v2r.z, fmaf(fyv.y, v1r.z, fyv.x * v0.z)));
-          u[3] = fmaf(fyv.w, v3.w, fmaf(fyv.z, v2r.w, fmaf(fyv.y, v1r.w, fyv.x * v0.w)));
+          wu_f2 ua = wu_mul2(wu_bc(fyv.x), wu_pk(v0.x, v0.y)), ub = wu_mul2(wu_bc(fyv.x), wu_pk(v0.z, v0.w));
+          ua = wu_fma2(wu_bc(fyv.y), wu_pk(v1r.x, v1r.y), ua); ub = wu_fma2(wu_bc(fyv.y), wu_pk(v1r.z, v1r.w), ub);
+          ua = wu_fma2(wu_bc(fyv.z), wu_pk(v2r.x, v2r.y), ua); ub = wu_fma2(wu_bc(fyv.z), wu_pk(v2r.z, v2r.w), ub);
+          ua = wu_fma2(wu_bc(fyv.w), wu_pk(v3.x, v3.y), ua);   ub = wu_fma2(wu_bc(fyv.w), wu_pk(v3.z, v3.w), ub);
+          wu_upk(ua, u[0], u[1]); wu_upk(ub, u[2], u[3]);
         }
 #pragma unroll
         for (int jx = 0; jx < WU_NG; ++jx) {
           const float4 fa = *reinterpret_cast<const float4*>(s_fx + jx * 16 + 8 * h);
           const float4 fb = *reinterpret_cast<const float4*>(s_fx + jx * 16 + 8 * h + 4);
-          ph[0] = fmaf(u[jx], fa.x, ph[0]); ph[1] = fmaf(u[jx], fa.y, ph[1]);
-          ph[2] = fmaf(u[jx], fa.z, ph[2]); ph[3] = fmaf(u[jx], fa.w, ph[3]);
-          ph[4] = fmaf(u[jx], fb.x, ph[4]); ph[5] = fmaf(u[jx], fb.y, ph[5]);
-          ph[6] = fmaf(u[jx], fb.z, ph[6]); ph[7] = fmaf(u[jx], fb.w, ph[7]);
+          const wu_f2 U = wu_bc(u[jx]);
+          P[0] = wu_fma2(U, wu_pk(fa.x, fa.y), P[0]); P[1] = wu_fma2(U, wu_pk(fa.z, fa.w), P[1]);
+          P[2] = wu_fma2(U, wu_pk(fb.x, fb.y), P[2]); P[3] = wu_fma2(U, wu_pk(fb.z, fb.w), P[3]);
         }
-        const float tt0 = V[16], tt1 = V[17];
-        ph[0] = fmaf(tt0, tta[0].x, ph[0]); ph[1] = fmaf(tt0, tta[0].y, ph[1]);
-        ph[2] = fmaf(tt0, tta[0].z, ph[2]); ph[3] = fmaf(tt0, tta[0].w, ph[3]);
-        ph[4] = fmaf(tt0, tta[1].x, ph[4]); ph[5] = fmaf(tt0, tta[1].y, ph[5]);
-        ph[6] = fmaf(tt0, tta[1].z, ph[6]); ph[7] = fmaf(tt0, tta[1].w, ph[7]);
-        ph[0] = fmaf(tt1, ttb[0].x, ph[0]); ph[1] = fmaf(tt1, ttb[0].y, ph[1]);
-        ph[2] = fmaf(tt1, ttb[0].z, ph[2]); ph[3] = fmaf(tt1, ttb[0].w, ph[3]);
-        ph[4] = fmaf(tt1, ttb[1].x, ph[4]); ph[5] = fmaf(tt1, ttb[1].y, ph[5]);
-        ph[6] = fmaf(tt1, ttb[1].z, ph[6]); ph[7] = fmaf(tt1, ttb[1].w, ph[7]);
+        const wu_f2 T0 = wu_bc(V[16]), T1 = wu_bc(V[17]);
+        P[0] = wu_fma2(T0, wu_pk(tta[0].x, tta[0].y), P[0]); P[1] = wu_fma2(T0, wu_pk(tta[0].z, tta[0].w), P[1]);
+        P[2] = wu_fma2(T0, wu_pk(tta[1].x, tta[1].y), P[2]); P[3] = wu_fma2(T0, wu_pk(tta[1].z, tta[1].w), P[3]);
+        P[0] = wu_fma2(T1, wu_pk(ttb[0].x, ttb[0].y), P[0]); P[1] = wu_fma2(T1, wu_pk(ttb[0].z, ttb[0].w), P[1]);
+        P[2] = wu_fma2(T1, wu_pk(ttb[1].x, ttb[1].y), P[2]); P[3] = wu_fma2(T1, wu_pk(ttb[1].z, ttb[1].w), P[3]);
       }
 
       // ---- complex field exp(2 pi i t), t = phi / lambda - (x + y) / 128 turns; fp16 hi / lo ----
-      float re[8], im[8];
+      wu_f2 RE[4], IM[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float t = fmaf(ph[c], kt, hc0 - (float)c * 0.0078125f);
-        const float fr = t - rintf(t);
-        const float ang = fr * 6.283185307179586f;
-        re[c] = __cosf(ang);
-        im[c] = __sinf(ang);
+      for (int c = 0; c < 4; ++c) {
+        const wu_f2 t = wu_fma2(P[c], wu_bc(kt), wu_add2(hc01, wu_bc(-(float)(2 * c) * 0.0078125f)));
+        float t0, t1;
+        wu_upk(t, t0, t1);
+        const wu_f2 ang = wu_mul2(wu_sub2(t, wu_pk(rintf(t0), rintf(t1))), wu_bc(6.283185307179586f));
+        float a0, a1;
+        wu_upk(ang, a0, a1);
+        RE[c] = wu_pk(__cosf(a0), __cosf(a1));
+        IM[c] = wu_pk(__sinf(a0), __sinf(a1));
       }
       if (c_pm != 0xffu) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const bool on = (c_pm >> c) & 1u;
-          re[c] = on ? re[c] : 0.f;
-          im[c] = on ? im[c] : 0.f;
+        for (int c = 0; c < 4; ++c) {
+          float r0, r1, i0, i1;
+          wu_upk(RE[c], r0, r1); wu_upk(IM[c], i0, i1);
+          const bool on0 = (c_pm >> (2 * c)) & 1u, on1 = (c_pm >> (2 * c + 1)) & 1u;
+          RE[c] = wu_pk(on0 ? r0 : 0.f, on1 ? r1 : 0.f);
+          IM[c] = wu_pk(on0 ? i0 : 0.f, on1 ? i1 : 0.f);
         }
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        wu_split(re[2 * c], re[2 * c + 1], re_h[c], re_l[c]);
-        wu_split(im[2 * c], im[2 * c + 1], im_h[c], im_l[c]);
+        wu_split2(RE[c], re_h[c], re_l[c]);
+        wu_split2(IM[c], im_h[c], im_l[c]);
       }
     }
 
@@ -684,7 +759,7 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float a = __uint_as_float(tv[8 * c + 2 * j]), b = __uint_as_float(tv[8 * c + 2 * j + 1]);
-          if (FULL) wu_split(a, b, hw[j], lw[j]);
+          if (FULL) wu_split2(wu_pk(a, b), hw[j], lw[j]);
           else { hw[j] = wu_pack(a, b); lw[j] = 0u; }
         }
         wu_sts128(a2_addr + c * 512, hw[0], hw[1], hw[2], hw[3]);
@@ -694,19 +769,20 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
 
     // ---- E(it-2) ----
     float qa[8], qb[8];
+    wu_f2 s0p = 0ull, syp = 0ull;
     const bool epi = it > 1;
     if (epi) {
       uint32_t yv[32];
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       wu_tmem_ld32(d2_addr, yv);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      sq_half(yv, qa);
+      if (plain) sq_plain(yv, 8.f, s0p, syp, true); else sq_half(yv, qa);
       wu_tmem_ld32(d2_addr + 32u, yv);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      sq_half(yv, qb);
+      if (plain) sq_plain(yv, 0.f, s0p, syp, false); else sq_half(yv, qb);
     }
     if (conv) arrive_and_issue(1);                    // A2(it-1) written and Y(it-2) drained by this warp
-    if (epi && it - 2 < n_mine) epilogue(qa, qb, (int)(ek2 >> 16), (int)(ek2 & 0xffffu));
+    if (epi && it - 2 < n_mine) epilogue(qa, qb, s0p, syp, (int)(ek2 >> 16), (int)(ek2 & 0xffffu));
 
     xy_cur = xy_next;
     ek2 = ek1; ek1 = ek0;
