@@ -286,13 +286,17 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
   unsigned char* s_b2 = s_b1 + 2 * WU_B_BYTES;
   unsigned char* s_tiles = s_b2 + 2 * WU_B_BYTES;                      // [warp][layer][WU_TILE_STRIDE]
   uint64_t* s_bar = (uint64_t*)(s_tiles + (size_t)WU_WARPS * NLS * WU_TILE_STRIDE);   // [0..7] tiles, [8] MMA1 done, [9] MMA2 done
-  uint32_t* s_cnt = (uint32_t*)(s_bar + 10);                           // [0] stage-1 arrivals, [1] stage-2 arrivals, [2] TMEM slot
+  uint32_t* s_cnt = (uint32_t*)(s_bar + 12);                           // [2] TMEM slot   (s_bar[10], [11]: stage-1 / stage-2 arrivals of the 8 warps)
   float* s_fx = (float*)((unsigned char*)s_bar + 128);                 // [NG][16]
   float* s_fyT = s_fx + WU_NG * 16;                                    // [16][NG]
   unsigned char* s_aux = (unsigned char*)(s_fyT + 16 * WU_NG);         // [warp][parity][WU_AUX_BYTES]
   short* s_amap = (short*)(s_aux + WU_WARPS * 2 * WU_AUX_BYTES);
 
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  // lane through a volatile read: the compiler otherwise re-derives it from S2R SR_TID.X at ~25 places of the loop body
+  // and each of those reads stalls its warp (5 % of the stall samples in profiles/r02_wfs_umma_v5)
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int y = lane & 15, h = lane >> 4;
 
   for (int i = threadIdx.x; i < 2 * WU_B_BYTES / 16; i += blockDim.x) {
@@ -303,9 +307,8 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
   for (int i = threadIdx.x; i < f.GW * f.GW; i += blockDim.x) s_amap[i] = f.amap[i];
   // operand tiles start from zeros: rows of work items that do not exist are multiplied too
   for (int i = threadIdx.x; i < 6 * WU_A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_a1)[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (threadIdx.x < 10)
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wu_smem_u32(s_bar + threadIdx.x)) : "memory");
-  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
+  if (threadIdx.x < 12)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wu_smem_u32(s_bar + threadIdx.x)), "r"(threadIdx.x < 10 ? 1u : (uint32_t)WU_WARPS) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // B tiles / zeroed A tiles are read by the tensor core
   if (warp == 0) {
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
     ttb[0] = __ldg(reinterpret_cast<const float4*>(tt_plane1 + to));
     ttb[1] = __ldg(reinterpret_cast<const float4*>(tt_plane1 + to + 4));
   };
+  const float4 fyv = *reinterpret_cast<const float4*>(s_fyT + y * WU_NG);      // y stamp factors of this lane's row (constant)
   // phase in turns: t = phi / lambda - (x + y) / 128   (halfxy = pi (x + y) / 64, geom_init.py:690-701)
   const float kt = p.k2 * 0.15915494309189535f;
   const float hc0 = -(float)(y + 8 * h) * 0.0078125f;
@@ -459,19 +463,25 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
   // sat in a per-thread waterfall loop of ~13 instructions).
   const uint32_t q_a1 = __shfl_sync(0xffffffffu, wu_smem_u32(s_a1) >> 4, 0), q_b1 = __shfl_sync(0xffffffffu, wu_smem_u32(s_b1) >> 4, 0);
   const uint32_t q_a2 = __shfl_sync(0xffffffffu, wu_smem_u32(s_a2) >> 4, 0), q_b2 = __shfl_sync(0xffffffffu, wu_smem_u32(s_b2) >> 4, 0);
-  const uint32_t cnt_u32 = wu_smem_u32(s_cnt);
-  auto arrive_and_issue = [&](int which) {
+  const uint32_t arr_bar = wu_smem_u32(s_bar + 10);
+  auto arrive_and_issue = [&](int which, uint32_t arr_parity) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
-    uint32_t old = 0;
-    // one release-acquire counter update per warp (inline PTX: the compiler's atomicAdd wraps a single-lane update in
-    // its warp-aggregation sequence); the __syncwarp above orders the other lanes' stores before it
-    if (lane == 0)
-      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_u32 + 4u * which) : "memory");
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if ((old & (WU_WARPS - 1)) == WU_WARPS - 1) {
+    // One arrival per warp on a count-8 mbarrier (release semantics, no memory barrier instruction, no atomic): the state
+    // it returns is the one before the arrival, and its pending count tells the last of the eight warps (== 1), which
+    // acquires the phase it has just completed and issues (profiles/dev/mbar_count_probe.cu; a shared-memory counter
+    // with atom.acq_rel cost a MEMBAR.ALL.CTA and the compiler's warp-aggregation sequence per arrival).
+    uint32_t pend = 0;
+    if (lane == 0) {
+      uint64_t st;
+      asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(arr_bar + 8u * which) : "memory");
+      asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pend) : "l"(st));
+    }
+    pend = __shfl_sync(0xffffffffu, pend, 0);
+    if (pend == 1u) {
       if (wu_elect()) {
+        if (!wu_mbar_try(arr_bar + 8u * which, arr_parity)) atomicExch(f.err, 4);       // acquire; complete by construction
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         constexpr uint32_t KM = (128u >> 4) << 16, HI = (512u >> 4) | (1u << 14);     // K-major: LBO 128, SBO 512
@@ -618,6 +628,17 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
     if (c_valid) {
       const uint32_t c_pm = *reinterpret_cast<const uint32_t*>(my_aux + s * WU_AUX_BYTES + 4 * lane);
       const float* V = reinterpret_cast<const float*>(my_aux + s * WU_AUX_BYTES + 128);
+      // this item's mirror inputs are requested before the bookkeeping of the next item (which is full of memory-
+      // clobbering copies the compiler cannot move loads across), so that their latency is covered by it
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1r = v0, v2r = v0, v3 = v0;
+      float vt0 = 0.f, vt1 = 0.f;
+      if (p.use_dm) {
+        load_tta(xy_cur);
+        load_ttb(xy_cur);
+        v0 = *reinterpret_cast<const float4*>(V); v1r = *reinterpret_cast<const float4*>(V + 4);
+        v2r = *reinterpret_cast<const float4*>(V + 8); v3 = *reinterpret_cast<const float4*>(V + 12);
+        vt0 = V[16]; vt1 = V[17];
+      }
       // ---- next work item of this warp: record (fetched during the previous iteration), per-lane inputs now,
       //      tiles as soon as the current ones are sampled ----
       uint2 sb1 = make_uint2(0u, 0u);
@@ -631,15 +652,50 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
         xy_next = sb1.x;
       }
 
-      WuPhase acc;
+      // ---- mirrors first (they need only the per-lane inputs that arrived by cp.async): the tip-tilt table loads are
+      //      requested at once and consumed after the stamp arithmetic, and the tiles of the atmosphere get the whole
+      //      section to land ----
+      wu_f2 P[4];
+      if (p.use_dm) {
+        float u[WU_NG];
+        {
+          wu_f2 ua = wu_mul2(wu_bc(fyv.x), wu_pk(v0.x, v0.y)), ub = wu_mul2(wu_bc(fyv.x), wu_pk(v0.z, v0.w));
+          ua = wu_fma2(wu_bc(fyv.y), wu_pk(v1r.x, v1r.y), ua); ub = wu_fma2(wu_bc(fyv.y), wu_pk(v1r.z, v1r.w), ub);
+          ua = wu_fma2(wu_bc(fyv.z), wu_pk(v2r.x, v2r.y), ua); ub = wu_fma2(wu_bc(fyv.z), wu_pk(v2r.z, v2r.w), ub);
+          ua = wu_fma2(wu_bc(fyv.w), wu_pk(v3.x, v3.y), ua);   ub = wu_fma2(wu_bc(fyv.w), wu_pk(v3.z, v3.w), ub);
+          wu_upk(ua, u[0], u[1]); wu_upk(ub, u[2], u[3]);
+        }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc.X[j] = 0ull;
+        for (int jx = 0; jx < WU_NG; ++jx) {
+          const float4 fa = *reinterpret_cast<const float4*>(s_fx + jx * 16 + 8 * h);
+          const float4 fb = *reinterpret_cast<const float4*>(s_fx + jx * 16 + 8 * h + 4);
+          const wu_f2 U = wu_bc(u[jx]);
+          if (jx == 0) {
+            P[0] = wu_mul2(U, wu_pk(fa.x, fa.y)); P[1] = wu_mul2(U, wu_pk(fa.z, fa.w));
+            P[2] = wu_mul2(U, wu_pk(fb.x, fb.y)); P[3] = wu_mul2(U, wu_pk(fb.z, fb.w));
+          } else {
+            P[0] = wu_fma2(U, wu_pk(fa.x, fa.y), P[0]); P[1] = wu_fma2(U, wu_pk(fa.z, fa.w), P[1]);
+            P[2] = wu_fma2(U, wu_pk(fb.x, fb.y), P[2]); P[3] = wu_fma2(U, wu_pk(fb.z, fb.w), P[3]);
+          }
+        }
+        const wu_f2 T0 = wu_bc(vt0), T1 = wu_bc(vt1);
+        P[0] = wu_fma2(T0, wu_pk(tta[0].x, tta[0].y), P[0]); P[1] = wu_fma2(T0, wu_pk(tta[0].z, tta[0].w), P[1]);
+        P[2] = wu_fma2(T0, wu_pk(tta[1].x, tta[1].y), P[2]); P[3] = wu_fma2(T0, wu_pk(tta[1].z, tta[1].w), P[3]);
+        P[0] = wu_fma2(T1, wu_pk(ttb[0].x, ttb[0].y), P[0]); P[1] = wu_fma2(T1, wu_pk(ttb[0].z, ttb[0].w), P[1]);
+        P[2] = wu_fma2(T1, wu_pk(ttb[1].x, ttb[1].y), P[2]); P[3] = wu_fma2(T1, wu_pk(ttb[1].z, ttb[1].w), P[3]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) acc.Y[j] = 0ull;
-      acc.y0 = acc.y7 = 0.f;
+        for (int j = 0; j < 4; ++j) P[j] = 0ull;
+      }
 
-      // ---- atmosphere ----
+      // ---- atmosphere, on top of the mirror surface ----
       if (NL > 0) {
+        WuPhase acc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc.X[j] = P[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc.Y[j] = 0ull;
+        acc.y0 = acc.y7 = 0.f;
         if (!c_seam) {
           wu_mbar_wait(my_bar_u32, tile_phase, f.err);
           tile_phase ^= 1u;
@@ -657,10 +713,7 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
         }
         __syncwarp();                                   // the stage is drained: re-arm it with the next item
         if (nx_valid) issue_tiles(e, sb1);
-      }
-      // fold the right-hand taps into the pixel pairs
-      wu_f2 P[4];
-      {
+        // fold the right-hand taps into the pixel pairs
         float x0, x1, ya, yb;
         wu_upk(acc.X[0], x0, x1); wu_upk(acc.Y[0], ya, yb);
         P[0] = wu_pk(x0 + acc.y0, x1 + ya);
@@ -670,36 +723,6 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
         P[2] = wu_pk(x0, x1 + ya);
         wu_upk(acc.X[3], x0, x1);
         P[3] = wu_pk(x0 + yb, x1 + acc.y7);
-      }
-
-      // ---- mirrors: separable stamps of the 4 x 4 lattice neighbourhood + two tip-tilt planes ----
-      if (p.use_dm) {
-        load_tta(xy_cur);
-        load_ttb(xy_cur);
-        const float4 fyv = *reinterpret_cast<const float4*>(s_fyT + y * WU_NG);
-        float u[WU_NG];
-        {
-          const float4 v0 = *reinterpret_cast<const float4*>(V), v1r = *reinterpret_cast<const float4*>(V + 4);
-          const float4 v2r = *reinterpret_cast<const float4*>(V + 8), v3 = *reinterpret_cast<const float4*>(V + 12);
-          wu_f2 ua = wu_mul2(wu_bc(fyv.x), wu_pk(v0.x, v0.y)), ub = wu_mul2(wu_bc(fyv.x), wu_pk(v0.z, v0.w));
-          ua = wu_fma2(wu_bc(fyv.y), wu_pk(v1r.x, v1r.y), ua); ub = wu_fma2(wu_bc(fyv.y), wu_pk(v1r.z, v1r.w), ub);
-          ua = wu_fma2(wu_bc(fyv.z), wu_pk(v2r.x, v2r.y), ua); ub = wu_fma2(wu_bc(fyv.z), wu_pk(v2r.z, v2r.w), ub);
-          ua = wu_fma2(wu_bc(fyv.w), wu_pk(v3.x, v3.y), ua);   ub = wu_fma2(wu_bc(fyv.w), wu_pk(v3.z, v3.w), ub);
-          wu_upk(ua, u[0], u[1]); wu_upk(ub, u[2], u[3]);
-        }
-#pragma unroll
-        for (int jx = 0; jx < WU_NG; ++jx) {
-          const float4 fa = *reinterpret_cast<const float4*>(s_fx + jx * 16 + 8 * h);
-          const float4 fb = *reinterpret_cast<const float4*>(s_fx + jx * 16 + 8 * h + 4);
-          const wu_f2 U = wu_bc(u[jx]);
-          P[0] = wu_fma2(U, wu_pk(fa.x, fa.y), P[0]); P[1] = wu_fma2(U, wu_pk(fa.z, fa.w), P[1]);
-          P[2] = wu_fma2(U, wu_pk(fb.x, fb.y), P[2]); P[3] = wu_fma2(U, wu_pk(fb.z, fb.w), P[3]);
-        }
-        const wu_f2 T0 = wu_bc(V[16]), T1 = wu_bc(V[17]);
-        P[0] = wu_fma2(T0, wu_pk(tta[0].x, tta[0].y), P[0]); P[1] = wu_fma2(T0, wu_pk(tta[0].z, tta[0].w), P[1]);
-        P[2] = wu_fma2(T0, wu_pk(tta[1].x, tta[1].y), P[2]); P[3] = wu_fma2(T0, wu_pk(tta[1].z, tta[1].w), P[3]);
-        P[0] = wu_fma2(T1, wu_pk(ttb[0].x, ttb[0].y), P[0]); P[1] = wu_fma2(T1, wu_pk(ttb[0].z, ttb[0].w), P[1]);
-        P[2] = wu_fma2(T1, wu_pk(ttb[1].x, ttb[1].y), P[2]); P[3] = wu_fma2(T1, wu_pk(ttb[1].z, ttb[1].w), P[3]);
       }
 
       // ---- complex field exp(2 pi i t), t = phi / lambda - (x + y) / 128 turns; fp16 hi / lo ----
@@ -747,7 +770,7 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
       wu_tmem_ld32(d1_addr, tv);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     }
-    if (it < n_iter) arrive_and_issue(0);             // A1(it) written and T(it-1) drained by this warp
+    if (it < n_iter) arrive_and_issue(0, (uint32_t)(it & 1));             // A1(it) written and T(it-1) drained by this warp
 
     // stage 2 of iteration it-2 is complete: A2 reusable, Y(it-2) in TMEM
     if (it > 1) wu_mbar_wait(mma2_bar, (uint32_t)((it - 2) & 1), f.err);
@@ -781,7 +804,7 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (plain) sq_plain(yv, 0.f, s0p, syp, false); else sq_half(yv, qb);
     }
-    if (conv) arrive_and_issue(1);                    // A2(it-1) written and Y(it-2) drained by this warp
+    if (conv) arrive_and_issue(1, (uint32_t)((it - 1) & 1));                    // A2(it-1) written and Y(it-2) drained by this warp
     if (epi && it - 2 < n_mine) epilogue(qa, qb, s0p, syp, (int)(ek2 >> 16), (int)(ek2 & 0xffffu));
 
     xy_cur = xy_next;
