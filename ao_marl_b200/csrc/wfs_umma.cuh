@@ -38,6 +38,9 @@
 #include "wfs_params.cuh"
 
 #define WU_WARPS 8
+#ifndef WU_EARLY_Y
+#define WU_EARLY_Y 0
+#endif
 #define WU_TILE_W 20                       // box width (floats): 17 needed + up to 3 of alignment slack; rows 80 B apart
 #define WU_TILE_H 17
 #define WU_TILE_BYTES (WU_TILE_W * WU_TILE_H * 4)            // 1360 = bytes one box delivers
@@ -625,8 +628,10 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
     const bool c_seam = n_seam;
 
     uint32_t re_h[4], re_l[4], im_h[4], im_l[4];
+    wu_f2 P[4];
+    uint32_t c_pm = 0u;
     if (c_valid) {
-      const uint32_t c_pm = *reinterpret_cast<const uint32_t*>(my_aux + s * WU_AUX_BYTES + 4 * lane);
+      c_pm = *reinterpret_cast<const uint32_t*>(my_aux + s * WU_AUX_BYTES + 4 * lane);
       const float* V = reinterpret_cast<const float*>(my_aux + s * WU_AUX_BYTES + 128);
       // this item's mirror inputs are requested before the bookkeeping of the next item (which is full of memory-
       // clobbering copies the compiler cannot move loads across), so that their latency is covered by it
@@ -655,7 +660,6 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
       // ---- mirrors first (they need only the per-lane inputs that arrived by cp.async): the tip-tilt table loads are
       //      requested at once and consumed after the stamp arithmetic, and the tiles of the atmosphere get the whole
       //      section to land ----
-      wu_f2 P[4];
       if (p.use_dm) {
         float u[WU_NG];
         {
@@ -725,6 +729,19 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
         P[3] = wu_pk(x0 + yb, x1 + acc.y7);
       }
 
+    }
+
+    // ---- stage 1 of the previous iteration is complete: A1 reusable, T(it-1) in TMEM.  Its read-out is requested here
+    //      and lands while the field below is evaluated ----
+    const bool conv = it > 0 && it <= n_iter;
+    uint32_t tv[32];
+    if (conv) {
+      wu_mbar_wait(mma1_bar, (uint32_t)((it - 1) & 1), f.err);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      wu_tmem_ld32(d1_addr, tv);
+    }
+
+    if (c_valid) {
       // ---- complex field exp(2 pi i t), t = phi / lambda - (x + y) / 128 turns; fp16 hi / lo ----
       wu_f2 RE[4], IM[4];
 #pragma unroll
@@ -755,25 +772,25 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
       }
     }
 
-    // ---- stage 1 of the previous iteration is complete: A1 reusable, T(it-1) in TMEM ----
-    const bool conv = it > 0 && it <= n_iter;
-    if (conv) wu_mbar_wait(mma1_bar, (uint32_t)((it - 1) & 1), f.err);
     if (c_valid) {
       wu_sts128(a1_addr, re_h[0], re_h[1], re_h[2], re_h[3]);
       wu_sts128(a1_addr + 256u, im_h[0], im_h[1], im_h[2], im_h[3]);
       wu_sts128(a1_addr + WU_A_BYTES, re_l[0], re_l[1], re_l[2], re_l[3]);
       wu_sts128(a1_addr + WU_A_BYTES + 256u, im_l[0], im_l[1], im_l[2], im_l[3]);
     }
-    uint32_t tv[32];
-    if (conv) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      wu_tmem_ld32(d1_addr, tv);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    }
+    if (conv) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (it < n_iter) arrive_and_issue(0, (uint32_t)(it & 1));             // A1(it) written and T(it-1) drained by this warp
 
     // stage 2 of iteration it-2 is complete: A2 reusable, Y(it-2) in TMEM
-    if (it > 1) wu_mbar_wait(mma2_bar, (uint32_t)((it - 2) & 1), f.err);
+    const bool epi = it > 1;
+    uint32_t yv[32];
+    if (epi) {
+      wu_mbar_wait(mma2_bar, (uint32_t)((it - 2) & 1), f.err);
+#if WU_EARLY_Y
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      wu_tmem_ld32(d2_addr, yv);                        // first half of Y(it-2): lands during the conversion below
+#endif
+    }
     if (conv) {
       // ---- C(it-1): T -> fp16 hi / lo -> A2 (MN-major: 8 consecutive fx per 16-byte group) ----
 #pragma unroll
@@ -793,11 +810,11 @@ __global__ void __launch_bounds__(WU_WARPS * 32, 2) wfs_frame_umma_kernel(const 
     // ---- E(it-2) ----
     float qa[8], qb[8];
     wu_f2 s0p = 0ull, syp = 0ull;
-    const bool epi = it > 1;
     if (epi) {
-      uint32_t yv[32];
+#if !WU_EARLY_Y
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       wu_tmem_ld32(d2_addr, yv);
+#endif
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (plain) sq_plain(yv, 8.f, s0p, syp, true); else sq_half(yv, qa);
       wu_tmem_ld32(d2_addr + 32u, yv);
