@@ -7,9 +7,9 @@
 static cudaError_t oz_attrs() {
   static bool attr_set = false;
   if (attr_set) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(oz_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(oz_gemm_kernel<0, OZ_LEVELS>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<1, OZ_LEVELS_PRODUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(oz_gemm_kernel<2, OZ_LEVELS_PRODUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
   attr_set = e == cudaSuccess;
   return e;
 }
@@ -20,7 +20,7 @@ cudaError_t oz_extrude_launch(const OzGatherParams& g, const OzGemmParams& m, in
   oz_gather_slice_kernel<<<g.E, 256, (size_t)g.KB * OZ_BK * sizeof(double), st>>>(g);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  oz_gemm_kernel<0><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
+  oz_gemm_kernel<0, OZ_LEVELS><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
   return cudaGetLastError();
 }
 
@@ -30,8 +30,8 @@ cudaError_t oz_product_launch(const OzSliceParams& sl, const OzGemmParams& m, in
   oz_slice_rows_kernel<<<sl.E, 256, 0, st>>>(sl);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (integrator) oz_gemm_kernel<2><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
-  else oz_gemm_kernel<1><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
+  if (integrator) oz_gemm_kernel<2, OZ_LEVELS_PRODUCT><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
+  else oz_gemm_kernel<1, OZ_LEVELS_PRODUCT><<<dim3(NT, MT), OZ_THREADS, OZ_SMEM_BYTES, st>>>(m);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,9 @@
                                                   // of the recursion and adds up coherently -- with 4 digits the 648^2 screens
                                                   // were 9.5e-5 off after a reset (measured, and reproduced in numpy)
 #define OZ_LEVELS 6                               // digit pairs kept: s + t <= 5
+#define OZ_LEVELS_PRODUCT 5                       // controller products (no recursion behind them): s + t <= 4, 15 MMAs per k
+                                                  // block (with s + t <= 3 the 40x40 closed loop moved from 1e-6 to 1e-5 .. 4e-5
+                                                  // of the oracle: measured, profiles/r02_parity_levels4.json)
 #define OZ_BM 128
 #define OZ_BN 80
 #define OZ_BK 32
@@ -314,7 +317,10 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
 //   warps 2-5  epilogue: TMEM lane quarter warp % 4 -> 32 environments, five int32 accumulators -> float64 -> float32
 // EPI 0: screen extrusion (+ zref, every column of the row written)   1: plain product (pad columns zero)
 // EPI 2: least-squares integrator: out = -product, com += gain * out when the loop is closed (rtcCompass.py:527-547)
-template <int EPI>
+// LEV: digit-pair levels kept (pairs with s + t < LEV).  6 (21 MMAs per k block) for the screen recursion, which
+// integrates any truncation; OZ_LEVELS_PRODUCT = 5 (15 MMAs) for the one-shot controller products, where the dropped
+// pairs are below 2^-35 of |x|max |W|max per term.
+template <int EPI, int LEV>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) {
   extern __shared__ __align__(1024) uint8_t oz_smem[];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = tid & 31;
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) 
         const uint32_t a0 = ((oz_smem_u32(oz_smem) + (uint32_t)s * OZ_STAGE_BYTES) >> 4) | ((128u >> 4) << 16);
         const uint32_t b0 = a0 + (OZ_SLICES * OZ_A_TILE >> 4);
 #pragma unroll
-        for (int g = 0; g < OZ_LEVELS; ++g)
+        for (int g = 0; g < LEV; ++g)
 #pragma unroll
           for (int sa = 0; sa < OZ_SLICES; ++sa) {
             const int sb = g - sa;
@@ -391,9 +397,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) 
     const double zr = (EPI == 0 && live) ? (double)p.zref[e] : 0.0;
 #pragma unroll 1
     for (int cb = 0; cb < OZ_BN / 8; ++cb) {
-      uint32_t v[OZ_LEVELS][8];
+      uint32_t v[LEV][8];
 #pragma unroll
-      for (int g = 0; g < OZ_LEVELS; ++g) {
+      for (int g = 0; g < LEV; ++g) {
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(g * OZ_BN + cb * 8);
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]), "=r"(v[g][5]), "=r"(v[g][6]), "=r"(v[g][7])
@@ -406,12 +412,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(OzGemmParams p) 
         for (int j = 0; j < 8; ++j) {
           const int n = nt * OZ_BN + cb * 8 + j;
           // sum_g acc_g 2^(-7 g) in float64 (each accumulator < 2^26; the sum spans 61 bits, rounded at 2^-53)
-          double acc = (double)(int)v[5][j];
-          acc = fma(acc, 0.0078125, (double)(int)v[4][j]);
-          acc = fma(acc, 0.0078125, (double)(int)v[3][j]);
-          acc = fma(acc, 0.0078125, (double)(int)v[2][j]);
-          acc = fma(acc, 0.0078125, (double)(int)v[1][j]);
-          acc = fma(acc, 0.0078125, (double)(int)v[0][j]);
+          double acc = (double)(int)v[LEV - 1][j];
+#pragma unroll
+          for (int g = LEV - 2; g >= 0; --g) acc = fma(acc, 0.0078125, (double)(int)v[g][j]);
           const int ex = ev + p.ea[n] - 12;
           const double sc = __longlong_as_double((long long)(1023 + ex) << 52);
           if (EPI == 0) o[j] = (float)fma(acc, sc, zr);        // pad columns get zref: harmless, the scatter reads n < N
