@@ -178,6 +178,7 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
     if (g && !strcmp(g, "simt")) ctx->opt[AOM_OPT_GEMM_PATH] = AOM_GEMM_SIMT;
     const char* w = getenv("AOM_WFS_PATH");
     if (w && !strcmp(w, "umma_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_UMMA_FAST;
+    if (w && !strcmp(w, "umma_ws")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_UMMA_WS;
     if (w && !strcmp(w, "simt")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_SIMT;
     if (w && !strcmp(w, "tensor_reg")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_MMA_REG;
     if (w && !strcmp(w, "tensor")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_MMA_STAGED;
@@ -1201,7 +1202,7 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
       if (!ctx->wev[j][ctx->wev_n]) CU(cudaEventCreate(&ctx->wev[j][ctx->wev_n]));
     CU(cudaEventRecord(ctx->wev[0][ctx->wev_n], st));
   }
-  const bool umma = (path == AOM_WFS_UMMA || path == AOM_WFS_UMMA_FAST);
+  const bool umma = (path == AOM_WFS_UMMA || path == AOM_WFS_UMMA_FAST || path == AOM_WFS_UMMA_WS);
   const bool staged = umma || path == AOM_WFS_MMA_STAGED || path == AOM_WFS_MMA_STAGED_FAST;
   const bool fast = (path == AOM_WFS_UMMA_FAST || path == AOM_WFS_MMA_STAGED_FAST);
   if (c.nfft == 64 && staged) {
@@ -1209,7 +1210,7 @@ extern "C" int aom_comp_wfs_image(aom_ctx* ctx, int flags, float noise, void* st
     if (rc) return rc;
   }
   if (c.nfft == 64 && umma && ctx->umma_state == 1) {
-    cudaError_t le = wfs_umma_launch(p, ctx->umma, ctx->num_sms, !fast, st);
+    cudaError_t le = wfs_umma_launch(p, ctx->umma, ctx->num_sms, !fast, path == AOM_WFS_UMMA_WS && p.noise < 0.f && p.bincube == nullptr, st);
     if (le != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "wfs_umma_launch: %s", cudaGetErrorString(le));
   }
   else if (c.nfft == 64 && staged && ctx->fast_state == 1) {
@@ -1259,9 +1260,9 @@ extern "C" const char* aom_wfs_kernel(aom_ctx* ctx) {
   const int path = ctx->opt[AOM_OPT_WFS_PATH];
   if (ctx->cfg.nfft != 64 || path == AOM_WFS_SIMT) return "wfs_frame_kernel";
   if (path == AOM_WFS_MMA_REG) return "wfs_frame_mma_kernel";
-  if (path == AOM_WFS_UMMA || path == AOM_WFS_UMMA_FAST) {
+  if (path == AOM_WFS_UMMA || path == AOM_WFS_UMMA_FAST || path == AOM_WFS_UMMA_WS) {
     if (wfs_umma_prepare(ctx) != AOM_OK) return "";
-    if (ctx->umma_state == 1) return "wfs_frame_umma_kernel";
+    if (ctx->umma_state == 1) return path == AOM_WFS_UMMA_WS ? "wfs_frame_ws_kernel" : "wfs_frame_umma_kernel";
   }
   if (wfs_fast_prepare(ctx) != AOM_OK) return "";
   if (ctx->fast_state == 1) return "wfs_frame_tma_kernel";
@@ -1518,7 +1519,7 @@ extern "C" int aom_apply_control(aom_ctx* ctx, int comp_voltage, void* stream) {
 extern "C" int aom_set_option(aom_ctx* ctx, int option, int value) {
   if (!ctx) return AOM_ERR_INVALID;
   if (option < 0 || option >= AOM_OPT_COUNT) return fail(ctx, AOM_ERR_INVALID, "unknown option %d", option);
-  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_MMA_STAGED_FAST))
+  if (option == AOM_OPT_WFS_PATH && (value < 0 || value > AOM_WFS_UMMA_WS))
     return fail(ctx, AOM_ERR_INVALID, "AOM_OPT_WFS_PATH: value %d out of range", value);
   if (option == AOM_OPT_TIME_WFS) ctx->wev_n = 0;
   if (option == AOM_OPT_GEMM_PATH && (value < 0 || value > AOM_GEMM_TF32))

@@ -12,4 +12,5 @@ struct WfsUmmaHost {
 
 // Launches wfs_frame_umma_kernel for the frame described by p.  full != 0: fp32-grade products in both stages.
 // Returns cudaSuccess or the error of the attribute / launch call.
-cudaError_t wfs_umma_launch(const WfsParams& p, const WfsUmmaHost& h, int num_sms, int full, cudaStream_t st);
+// ws != 0: the warp-specialised kernel (wfs_umma_ws.cuh) on the same tables.
+cudaError_t wfs_umma_launch(const WfsParams& p, const WfsUmmaHost& h, int num_sms, int full, int ws, cudaStream_t st);

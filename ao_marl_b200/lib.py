@@ -282,7 +282,7 @@ class Simulator:
         self.lib.aom_device_count_launches(self._ctx, ctypes.byref(n))
         return n.value
 
-    WFS_PATHS = {"umma": 0, "umma_fast": 1, "simt": 2, "tensor_reg": 3, "tensor": 4, "tensor_fast": 5}
+    WFS_PATHS = {"umma": 0, "umma_fast": 1, "simt": 2, "tensor_reg": 3, "tensor": 4, "tensor_fast": 5, "umma_ws": 6}
 
     def set_wfs_path(self, name):
         """Select the Shack-Hartmann frame kernel: 'umma' (default: both DFT stages on tcgen05), 'umma_fast', 'simt'

@@ -197,7 +197,9 @@ enum {
   AOM_WFS_SIMT = 2,        /* float32 shared-memory FFT on the FP32 pipe (cross-check path) */
   AOM_WFS_MMA_REG = 3,     /* round-1 generation 2: warp-level mma.sync DFT fed by plain global loads (any Nfft = 64 geometry) */
   AOM_WFS_MMA_STAGED = 4,  /* round-1 default: TMA-staged tiles + warp-level mma.sync DFT (cross-check / comparison path) */
-  AOM_WFS_MMA_STAGED_FAST = 5  /* same, twiddle low parts dropped in stage 2 */
+  AOM_WFS_MMA_STAGED_FAST = 5, /* same, twiddle low parts dropped in stage 2 */
+  AOM_WFS_UMMA_WS = 6      /* the AOM_WFS_UMMA pipeline on specialised warps: 8 field warps + 4 transform warps per CTA, two
+                              stage-1 accumulators in TMEM, register reallocation between the warp groups (wfs_umma_ws.cuh) */
 };
 
 enum {
