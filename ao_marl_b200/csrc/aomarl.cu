@@ -172,13 +172,14 @@ extern "C" int aom_create(const aom_config* cfg, aom_ctx** out) {
   ctx->cfg = *cfg;
   ctx->gain = cfg->gain;
   ctx->closed = 1;
+  ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_UMMA_WS;
   {
     // development overrides of the default kernel paths (see aom_set_option)
     const char* g = getenv("AOM_GEMM_PATH");
     if (g && !strcmp(g, "simt")) ctx->opt[AOM_OPT_GEMM_PATH] = AOM_GEMM_SIMT;
     const char* w = getenv("AOM_WFS_PATH");
     if (w && !strcmp(w, "umma_fast")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_UMMA_FAST;
-    if (w && !strcmp(w, "umma_ws")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_UMMA_WS;
+    if (w && !strcmp(w, "umma")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_UMMA;
     if (w && !strcmp(w, "simt")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_SIMT;
     if (w && !strcmp(w, "tensor_reg")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_MMA_REG;
     if (w && !strcmp(w, "tensor")) ctx->opt[AOM_OPT_WFS_PATH] = AOM_WFS_MMA_STAGED;

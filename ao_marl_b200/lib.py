@@ -282,10 +282,12 @@ class Simulator:
         self.lib.aom_device_count_launches(self._ctx, ctypes.byref(n))
         return n.value
 
+    DEFAULT_WFS_PATH = "umma_ws"
     WFS_PATHS = {"umma": 0, "umma_fast": 1, "simt": 2, "tensor_reg": 3, "tensor": 4, "tensor_fast": 5, "umma_ws": 6}
 
     def set_wfs_path(self, name):
-        """Select the Shack-Hartmann frame kernel: 'umma' (default: both DFT stages on tcgen05), 'umma_fast', 'simt'
+        """Select the Shack-Hartmann frame kernel: 'umma_ws' (default: both DFT stages on tcgen05, specialised warps), 'umma'
+        (the same pipeline fused in every warp; also serves noisy / image-keeping frames of the default), 'umma_fast', 'simt'
         (float32 FFT cross-check), 'tensor' / 'tensor_fast' / 'tensor_reg' (the round-1 mma.sync kernels)."""
         self._check(self.lib.aom_set_option(self._ctx, O["WFS_PATH"], self.WFS_PATHS[name]), "aom_set_option")
 

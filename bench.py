@@ -34,12 +34,20 @@ if ROOT not in sys.path:
 
 # DRAM bytes per environment per launch of the sensor kernel from `ncu --set full` (dram__bytes_read.sum +
 # dram__bytes_write.sum of one launch at E = 1024, divided by 1024).  Used for roofline.traffic (scaled to the E of this run).
-NCU_DRAM_BYTES_PER_ENV = {("40x40_d0_noise", "wfs_frame_umma_kernel"): (4.072948e9 + 13.814528e6) / 1024,
+NCU_DRAM_BYTES_PER_ENV = {("40x40", "wfs_frame_ws_kernel"): (4.073935e9 + 14.962176e6) / 1024,      # profiles/r02_wfs_ws_v1_E1024_*
+                          ("40x40_d0_noise", "wfs_frame_ws_kernel"): (4.072948e9 + 13.814528e6) / 1024,   # noisy frames run wfs_frame_umma_kernel
+                          ("40x40_d0_noise", "wfs_frame_umma_kernel"): (4.072948e9 + 13.814528e6) / 1024,
                           ("40x40", "wfs_frame_umma_kernel"): (4.072948e9 + 13.814528e6) / 1024,   # profiles/r02_wfs_umma_v3_E1024_*
                           ("40x40", "wfs_frame_tma_kernel"): (4.108122e9 + 13.919744e6) / 1024,    # profiles/r01_wfs_tma_E1024_*
                           ("40x40", "wfs_frame_mma_kernel"): (4.062998e9 + 18.132992e6) / 1024}
 
 ROOFLINE_NOTES = {
+    "wfs_frame_ws_kernel": "both DFT stages on tcgen05 with the phases on specialised warps (8 field + 4 transform warps per CTA, 24 "
+                           "warps per SM, UTCHMMA / LDTM / UTMALDG, packed FFMA2 arithmetic, ~915 warp instructions per subaperture): "
+                           "issue slots 52 % busy, shared-memory wavefronts of the LSU at 56 % of their peak next to the tensor "
+                           "core's operand fetch (21 % of cycles) and the TMA fills, tensor pipe 16 %, DRAM 24 %: bound by latency "
+                           "and shared-memory bandwidth of the per-subaperture pipeline, neither by HBM nor by the tensor pipe; see "
+                           "DESIGN.md section 4.1",
     "wfs_frame_umma_kernel": "both DFT stages on tcgen05 (UTCHMMA, no HMMA; tensor pipe 14 %, DRAM 21 %): bound by the CUDA-core "
                              "instruction stream around the tensor core (~1060 useful warp instructions per subaperture: bilinear "
                              "trace, mirrors, sincos, fp16 hi/lo splits of both operands, |.|^2, centroid) at ~0.5 IPC per scheduler "
@@ -81,7 +89,7 @@ def parse():
     ap.add_argument("--geo", action="store_true",
                     help="also run the parameter file's geometric controller every step (SURVEY 8(f) rank 4; off by default)")
     ap.add_argument("--wfs-path", default=None,
-                    choices=["umma", "umma_fast", "simt", "tensor", "tensor_fast", "tensor_reg"],
+                    choices=["umma_ws", "umma", "umma_fast", "simt", "tensor", "tensor_fast", "tensor_reg"],
                     help="Shack-Hartmann frame kernel (default: the library's product path)")
     ap.add_argument("--strehl-peak", action="store_true",
                     help="with --strehl: SE / LE from the fitted peak of the 3 x 3 PSF core instead of the on-axis pixel")

@@ -191,15 +191,16 @@ enum {
 };
 enum {
   AOM_WFS_UMMA = 0,        /* both stages of the pruned DFT on tcgen05 / TMEM, eight subapertures per tensor-core tile, TMA-staged
-                              screen tiles, three fp16 products per stage (fp32-grade; default; wfs_umma.cuh).  Geometries it does
-                              not cover fall back to AOM_WFS_MMA_STAGED, then AOM_WFS_MMA_REG (aom_last_error says why) */
+                              screen tiles, three fp16 products per stage (fp32-grade; wfs_umma.cuh; serves the frames with noise or
+                              a kept image under AOM_WFS_UMMA_WS too).  Geometries it does not cover fall back to
+                              AOM_WFS_MMA_STAGED, then AOM_WFS_MMA_REG (aom_last_error says why) */
   AOM_WFS_UMMA_FAST = 1,   /* same, the stage-1 result handed to stage 2 as one rounded fp16 (slopes ~3e-5 relative) */
   AOM_WFS_SIMT = 2,        /* float32 shared-memory FFT on the FP32 pipe (cross-check path) */
   AOM_WFS_MMA_REG = 3,     /* round-1 generation 2: warp-level mma.sync DFT fed by plain global loads (any Nfft = 64 geometry) */
   AOM_WFS_MMA_STAGED = 4,  /* round-1 default: TMA-staged tiles + warp-level mma.sync DFT (cross-check / comparison path) */
   AOM_WFS_MMA_STAGED_FAST = 5, /* same, twiddle low parts dropped in stage 2 */
-  AOM_WFS_UMMA_WS = 6      /* the AOM_WFS_UMMA pipeline on specialised warps: 8 field warps + 4 transform warps per CTA, two
-                              stage-1 accumulators in TMEM, register reallocation between the warp groups (wfs_umma_ws.cuh) */
+  AOM_WFS_UMMA_WS = 6      /* DEFAULT: the AOM_WFS_UMMA pipeline on specialised warps -- 8 field warps + 4 transform warps per
+                              CTA, two stage-1 accumulators in TMEM (wfs_umma_ws.cuh); bit-identical results */
 };
 
 enum {

@@ -20,10 +20,21 @@
 #pragma once
 #include "wfs_umma.cuh"
 
-#define WS_THREADS 384
+#define WS_THREADS 512
+#define WS_REGS_FIELD 80
+#define WS_REGS_XFORM 48
 #ifndef WS_MIN_BLOCKS
 #define WS_MIN_BLOCKS 2
 #endif
+
+__device__ __forceinline__ void ws_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 
 template <int NL, int FULL>
 __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel(const __grid_constant__ WfsUmmaParams P) {
@@ -62,7 +73,7 @@ __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel
   for (int i = threadIdx.x; i < 6 * WU_A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_a1)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x < 15)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wu_smem_u32(s_bar + threadIdx.x)),
-                 "r"(threadIdx.x < 11 ? 1u : threadIdx.x == 11 ? (uint32_t)WU_WARPS : 4u) : "memory");
+                 "r"(threadIdx.x < 11 ? 1u : (uint32_t)WU_WARPS) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // B tiles / zeroed A tiles are read by the tensor core
   if (warp == 0) {
@@ -95,6 +106,7 @@ __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel
   if (warp < WU_WARPS) {
 #endif
     // =============================== field warps ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_FIELD));
     unsigned char* my_tiles = s_tiles + (size_t)warp * NLS * WU_TILE_STRIDE;
     const uint32_t my_tiles_u32 = wu_smem_u32(my_tiles);
     const uint32_t my_bar_u32 = wu_smem_u32(s_bar + warp);
@@ -419,27 +431,22 @@ __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel
   } else {
 #endif
     // =============================== transform warps ===============================
-    const int q = warp - WU_WARPS;                                 // TMEM lane quarter
-    // conversion: rows 32 q .. of the stage-1 result = subapertures 2 q + h; A2 tile q >> 1, rows m = 32 s' + fx with
-    // s' = 2 (q & 1) + h, K index 16 ro + y (ro = 0: T_re columns 0..31, ro = 1: T_im columns 32..63)
-    const uint32_t d1_addr = tmem_base + ((uint32_t)(32 * q) << 16);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_XFORM));
+    const int q = (warp - WU_WARPS) & 3, ro = (warp - WU_WARPS) >> 2;   // TMEM lane quarter; half of the work of that quarter
+    // conversion: rows 32 q .. of the stage-1 result = subapertures 2 q + h, columns 32 ro .. (ro = 0: T_re, 1: T_im);
+    // A2 tile q >> 1, rows m = 32 s' + fx with s' = 2 (q & 1) + h, K index 16 ro + y
+    const uint32_t d1_addr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * ro);
     const uint32_t a2_addr = wu_smem_u32(s_a2) + (uint32_t)((q >> 1) * 2 * WU_A_BYTES + (4 * (2 * (q & 1) + h)) * 512 +
-                                                           (y >> 3) * 128 + (y & 7) * 16);
-    // epilogue: the fx rows of subaperture q (tile 0) and 4 + q (tile 1)
-    const uint32_t d2_addr = tmem_base + ((uint32_t)(32 * q) << 16) + 128u;
-    // (e, k) of the two subapertures of the group in the epilogue
-    int ee[2], kk[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      ee[t] = (int)((base + 4 * t + q) / p.nvalid);
-      kk[t] = (int)((base + 4 * t + q) % p.nvalid);
-    }
+                                                           (2 * ro + (y >> 3)) * 128 + (y & 7) * 16);
+    // epilogue: the fx rows of subaperture 4 ro + q (tile ro)
+    const uint32_t d2_addr = tmem_base + ((uint32_t)(32 * q) << 16) + 128u + 64u * (uint32_t)ro;
+    int ee = (int)((base + 4 * ro + q) / p.nvalid), kk = (int)((base + 4 * ro + q) % p.nvalid);
     // This kernel serves frames without noise and without a kept image (the host routes the others to
     // wfs_frame_umma_kernel): the centre of gravity is scale invariant and linear in |Y|^2, so the sums over the lane's 32
     // values of a half run on packed pairs straight from the accumulator: s0p = sum, syp = sum of py x value.
-    auto sq_plain = [&](const uint32_t (&v)[32], float py0, wu_f2& s0p, wu_f2& syp, bool first) {
+    auto sq_plain = [&](const uint32_t (&v)[16], float py0, wu_f2& s0p, wu_f2& syp, bool first) {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
+      for (int m = 0; m < 4; ++m) {
         const wu_f2 a = wu_pk(__uint_as_float(v[4 * m]), __uint_as_float(v[4 * m + 1]));
         const wu_f2 b = wu_pk(__uint_as_float(v[4 * m + 2]), __uint_as_float(v[4 * m + 3]));
         const wu_f2 t = wu_fma2(b, b, wu_mul2(a, a));
@@ -454,62 +461,44 @@ __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel
     };
     // lane = kept fx index; fx pair lane >> 1 -> px
     const float pxf = (float)(((lane >> 1) < 8) ? 8 + (lane >> 1) : (lane >> 1) - 8);
-    // both subapertures of the lane quarter reduced together: five shuffle rounds instead of ten in a row
-    auto epilogue2 = [&](const wu_f2 (&s0p)[2], const wu_f2 (&syp)[2], const bool (&live)[2], const int (&ie)[2], const int (&ik)[2]) {
-      float s0[2], sx[2], sy[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        float a, b;
-        wu_upk(s0p[t], a, b); s0[t] = a + b;
-        wu_upk(syp[t], a, b); sy[t] = a + b;
-        sx[t] = s0[t] * pxf;
-      }
+    auto epilogue = [&](wu_f2 s0p, wu_f2 syp, int ie, int ik) {
+      float a, b;
+      wu_upk(s0p, a, b); float s0 = a + b;
+      wu_upk(syp, a, b); float sy = a + b;
+      float sx = s0 * pxf;
 #pragma unroll
       for (int sft = 16; sft > 0; sft >>= 1) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          s0[t] += __shfl_xor_sync(0xffffffffu, s0[t], sft);
-          sx[t] += __shfl_xor_sync(0xffffffffu, sx[t], sft);
-          sy[t] += __shfl_xor_sync(0xffffffffu, sy[t], sft);
-        }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, sft);
+        sx += __shfl_xor_sync(0xffffffffu, sx, sft);
+        sy += __shfl_xor_sync(0xffffffffu, sy, sft);
       }
-      // lane t writes the slopes of subaperture t
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (lane == t && live[t]) {
-          const float inv = __frcp_rn(s0[t]);
-          const float gx = (s0[t] > 0.f) ? sx[t] * inv : p.cog_offset;
-          const float gy = (s0[t] > 0.f) ? sy[t] * inv : p.cog_offset;
-          float* sl = p.slopes + (size_t)ie[t] * p.lds;
-          sl[ik[t]] = (gx - p.cog_offset) * p.pixsize;
-          sl[p.nvalid + ik[t]] = (gy - p.cog_offset) * p.pixsize;
-        }
+      if (lane == 0) {
+        const float inv = __frcp_rn(s0);
+        const float gx = (s0 > 0.f) ? sx * inv : p.cog_offset;
+        const float gy = (s0 > 0.f) ? sy * inv : p.cog_offset;
+        float* sl = p.slopes + (size_t)ie * p.lds;
+        sl[ik] = (gx - p.cog_offset) * p.pixsize;
+        sl[p.nvalid + ik] = (gy - p.cog_offset) * p.pixsize;
       }
     };
 
     for (int j = 0; j <= n_iter; ++j) {
       const bool conv = j < n_iter, epi = j > 0;
-      uint32_t tv[32];
+      uint32_t tv[16];
       if (conv) {
         wu_mbar_wait(mma1_bar + 8u * (j & 1), (uint32_t)((j >> 1) & 1), f.err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        wu_tmem_ld32(d1_addr + 64u * (uint32_t)(j & 1), tv);
+        ws_tmem_ld16(d1_addr + 64u * (uint32_t)(j & 1), tv);
       }
       // stage 2 of the previous group is complete: A2 reusable, Y(j-1) in TMEM
       if (epi) wu_mbar_wait(mma2_bar, (uint32_t)((j - 1) & 1), f.err);
       if (conv) {
+        // ---- T -> fp16 hi / lo -> A2 (MN-major: 8 consecutive fx per 16-byte group), 16 columns at a time ----
 #pragma unroll
-        for (int ro = 0; ro < 2; ++ro) {
+        for (int half = 0; half < 2; ++half) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (ro == 1) {
-            // both halves are in registers: the accumulator buffer may be overwritten (by MMA 1 of group j + 2)
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_free + 8u * (j & 1)) : "memory");
-          }
-          // ---- T -> fp16 hi / lo -> A2 (MN-major: 8 consecutive fx per 16-byte group) ----
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -517,26 +506,28 @@ __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel
               if (FULL) wu_split2(wu_pk(a, b), hw[i], lw[i]);
               else { hw[i] = wu_pack(a, b); lw[i] = 0u; }
             }
-            wu_sts128(a2_addr + ro * 256 + c * 512, hw[0], hw[1], hw[2], hw[3]);
-            if (FULL) wu_sts128(a2_addr + WU_A_BYTES + ro * 256 + c * 512, lw[0], lw[1], lw[2], lw[3]);
+            wu_sts128(a2_addr + (2 * half + c) * 512, hw[0], hw[1], hw[2], hw[3]);
+            if (FULL) wu_sts128(a2_addr + WU_A_BYTES + (2 * half + c) * 512, lw[0], lw[1], lw[2], lw[3]);
           }
-          if (ro == 0) wu_tmem_ld32(d1_addr + 64u * (uint32_t)(j & 1) + 32u, tv);
+          if (half == 0) ws_tmem_ld16(d1_addr + 64u * (uint32_t)(j & 1) + 16u, tv);
         }
+        // this warp's part of the accumulator buffer may be overwritten (MMA 1 of group j + 2)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_free + 8u * (j & 1)) : "memory");
       }
 
-      // ---- read-out of Y(j-1): both subapertures of this lane quarter, before MMA 2 of group j overwrites them ----
-      wu_f2 s0p[2] = {0ull, 0ull}, syp[2] = {0ull, 0ull};
+      // ---- read-out of Y(j-1), before MMA 2 of group j overwrites it ----
+      wu_f2 s0p = 0ull, syp = 0ull;
       if (epi) {
+        uint32_t yv[16];
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          uint32_t yv[32];
-          wu_tmem_ld32(d2_addr + 64u * t, yv);
+        for (int part = 0; part < 4; ++part) {
+          ws_tmem_ld16(d2_addr + 16u * part, yv);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          sq_plain(yv, 8.f, s0p[t], syp[t], true);
-          wu_tmem_ld32(d2_addr + 64u * t + 32u, yv);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          sq_plain(yv, 0.f, s0p[t], syp[t], false);
+          // columns 0..31: fy pairs of py 8..15, columns 32..63: py 0..7; four fy pairs per 16 columns
+          sq_plain(yv, (part < 2 ? 8.f : 0.f) + 4.f * (float)(part & 1), s0p, syp, part == 0);
         }
       }
       if (conv) {
@@ -579,13 +570,9 @@ __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel
         __syncwarp();
       }
       if (epi) {
-        const bool live[2] = {8 * (j - 1) + q < n_cta, 8 * (j - 1) + 4 + q < n_cta};
-        epilogue2(s0p, syp, live, ee, kk);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          kk[t] += WU_WARPS;
-          if (kk[t] >= p.nvalid) { kk[t] -= p.nvalid; ee[t] += 1; }
-        }
+        if (8 * (j - 1) + 4 * ro + q < n_cta) epilogue(s0p, syp, ee, kk);
+        kk += WU_WARPS;
+        if (kk >= p.nvalid) { kk -= p.nvalid; ee += 1; }
       }
     }
   }

@@ -182,7 +182,7 @@ def test_wfs_paths_agree(sim10, static10, torch):
             out[path] = (sim10.rows("SLOPES", static10.nslopes).cpu().numpy().copy(),
                          sim10.buffer("BINCUBE").cpu().numpy().copy())
     finally:
-        sim10.set_wfs_path("umma")
+        sim10.set_wfs_path(sim10.DEFAULT_WFS_PATH)
     assert relerr(out["tensor"][1], out["simt"][1]) < 2e-5
     assert relerr(out["tensor"][0], out["simt"][0]) < 2e-5
     assert relerr(out["tensor_fast"][0], out["simt"][0]) < 5e-4
@@ -206,7 +206,7 @@ def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
             for _ in range(3):
                 sim10.move_atmos()
             res = {}
-            for path in ("simt", "tensor", "umma"):
+            for path in ("simt", "tensor", "umma", "umma_ws"):
                 sim10.set_wfs_path(path)
                 sim10.comp_wfs_image(keep_image=(it % 2 == 0), noise=-1.0)
                 sim10.do_centroids()
@@ -214,8 +214,9 @@ def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
             sim10.check_device()
             assert relerr(res["tensor"], res["simt"]) < 2e-5, it
             assert relerr(res["umma"], res["simt"]) < 2e-5, it
+            assert np.array_equal(res["umma_ws"], res["umma"]), it      # same arithmetic on specialised warps
     finally:
-        sim10.set_wfs_path("umma")
+        sim10.set_wfs_path(sim10.DEFAULT_WFS_PATH)
 
 
 def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
@@ -238,7 +239,7 @@ def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
                 ref = aoframe.sh_noise(clean[e], 3.0, int(seeds[e]), static10.wfs_index, 0)
                 assert np.array_equal(noisy[e], ref), path
     finally:
-        sim10.set_wfs_path("umma")
+        sim10.set_wfs_path(sim10.DEFAULT_WFS_PATH)
 
 
 def test_imat_matches_oracle(static10, oracle_imat10, torch):
@@ -380,7 +381,7 @@ def test_40x40_flat_and_tilt(system40, torch):
     """Flat wavefront -> zero slopes; a tip-tilt command -> the same slope on every subaperture, linear in the
     command; all on the staged kernel."""
     sim, t, rl = system40
-    assert sim.wfs_kernel() == "wfs_frame_umma_kernel", sim.lib.aom_last_error(sim._ctx)
+    assert sim.wfs_kernel() == "wfs_frame_ws_kernel", sim.lib.aom_last_error(sim._ctx)
     nv = t.p_wfs._nvalid
     sim.reset(np.arange(6, dtype=np.int64) + 500)
     sim.reset_dm()
@@ -423,7 +424,7 @@ def test_40x40_kernel_generations_agree(system40, torch):
             for _ in range(1 + 40 * it):
                 sim.move_atmos()
             res = {}
-            for path in ("simt", "tensor", "tensor_reg", "umma"):
+            for path in ("simt", "tensor", "tensor_reg", "umma", "umma_ws"):
                 sim.set_wfs_path(path)
                 sim.comp_wfs_image(noise=-1.0)
                 sim.do_centroids()
@@ -433,8 +434,9 @@ def test_40x40_kernel_generations_agree(system40, torch):
             assert relerr(res["tensor"], res["simt"]) < 2e-5, it
             assert relerr(res["tensor_reg"], res["simt"]) < 2e-5, it
             assert relerr(res["umma"], res["simt"]) < 2e-5, it
+            assert np.array_equal(res["umma_ws"], res["umma"]), it      # same arithmetic on specialised warps
     finally:
-        sim.set_wfs_path("umma")
+        sim.set_wfs_path(sim.DEFAULT_WFS_PATH)
 
 
 def test_40x40_closed_loop_properties(system40, torch):
