@@ -162,8 +162,12 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
 
   if (warp < 4) {
     // ===== loaders =====
-    const int c = tid & 3;                       // 16-byte chunk (4 k-values) of the 16-wide slab
-    const int r0 = tid >> 2;                     // rows r0, r0 + 32, r0 + 64, r0 + 96
+    // eight consecutive lanes take the same 16-byte chunk (4 k-values) of eight consecutive rows: their st.shared.v4 fill
+    // one 128-byte core matrix without bank conflicts (with chunk = tid & 3 the four chunks of a row landed 128 B apart on
+    // the same banks: 75 % of the shared-memory wavefronts were replays, profiles/r01_gemmtc_E4096_metrics.csv); the
+    // global loads of a warp still cover whole 64-byte row segments
+    const int c = (tid >> 3) & 3;
+    const int r0 = (tid >> 5) * 8 + (tid & 7);   // rows r0, r0 + 32, r0 + 64, r0 + 96
     // two slabs of global loads stay in flight (register sets 0 / 1): one slab alone left every stage waiting
     // for HBM/L2 latency longer than its three MMAs take
     float4 va[GTC_INFLIGHT][4], vb[GTC_INFLIGHT][B_ITERS];
