@@ -143,10 +143,12 @@ __global__ void __launch_bounds__(256) oz_gather_slice_kernel(OzGatherParams p) 
   const float zr = scr[(size_t)oz_wrap(rr + oy, N) * N + oz_wrap(rc + ox, N)];
   // differences and products in float64, i.e. exactly: what the oracle (and a float64 reading of iterkolmo.py:281-284) does
   double amax = 0.0;
+  const uint32_t magic = 0xFFFFFFFFu / (uint32_t)N + 1u;       // idx / N = umulhi(idx, magic) for idx < N^2 <= 2^22 (N <= 2048)
   for (int k = threadIdx.x; k < p.S; k += blockDim.x) {
     const int idx = p.stencil[k];
+    const int sr = (int)__umulhi((uint32_t)idx, magic), sc = idx - sr * N;
     int lr, lc;
-    oz_logical(idx / N, idx % N, N, p.axis, p.sign, lr, lc);
+    oz_logical(sr, sc, N, p.axis, p.sign, lr, lc);
     const double v = (double)scr[(size_t)oz_wrap(lr + oy, N) * N + oz_wrap(lc + ox, N)] - (double)zr;
     oz_v[k] = v;
     amax = fmax(amax, fabs(v));
@@ -178,24 +180,23 @@ __global__ void __launch_bounds__(256) oz_gather_slice_kernel(OzGatherParams p) 
   if (threadIdx.x == 0) { p.zref[e] = zr; p.ev[e] = ex; }
   const double scale = __longlong_as_double((long long)(1023 - ex) << 52);      // 2^-ex
   const int mt = e >> 7, r = e & 127;
-  for (int j = threadIdx.x; j < Kp / 16; j += blockDim.x) {
-    uint32_t w[OZ_SLICES][4];
+  // eight values per thread and pass: the 1984 values of a 648-pixel layer keep 248 of the 256 threads busy in one pass
+  for (int j = threadIdx.x; j < Kp / 8; j += blockDim.x) {
+    uint32_t w[OZ_SLICES][2];
 #pragma unroll
-    for (int s = 0; s < OZ_SLICES; ++s)
+    for (int s = 0; s < OZ_SLICES; ++s) w[s][0] = w[s][1] = 0u;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w[s][i] = 0u;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 8; ++i) {
       int q[OZ_SLICES];
-      oz_digits<OZ_SLICES>(oz_v[16 * j + i], scale, q);
+      oz_digits<OZ_SLICES>(oz_v[8 * j + i], scale, q);
 #pragma unroll
       for (int s = 0; s < OZ_SLICES; ++s) w[s][i >> 2] |= ((uint32_t)q[s] & 0xffu) << (8 * (i & 3));
     }
-    const int kb = j >> 1;
-    uint8_t* base = p.Zs + ((size_t)(mt * p.KB + kb) * OZ_SLICES) * OZ_A_TILE + oz_tile_offset(r, (j & 1) * 16);
+    const int kb = j >> 2;
+    uint8_t* base = p.Zs + ((size_t)(mt * p.KB + kb) * OZ_SLICES) * OZ_A_TILE + oz_tile_offset(r, (j & 3) * 8);
 #pragma unroll
     for (int s = 0; s < OZ_SLICES; ++s)
-      *reinterpret_cast<uint4*>(base + (size_t)s * OZ_A_TILE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+      *reinterpret_cast<uint2*>(base + (size_t)s * OZ_A_TILE) = make_uint2(w[s][0], w[s][1]);
   }
 }
 

@@ -19,8 +19,8 @@
 //              tcgen05.ld of their 32 TMEM lanes, bias / relu / integrator, 128-bit stores.
 //   warp 4     TMEM allocation; one lane waits on the full barriers and issues the six tcgen05.mma of the
 //              stage, tcgen05.commit releases the stage to the loaders and finally the accumulator.
-// Every mbarrier wait is bounded: on expiry the kernel raises an error word and runs to completion
-// instead of hanging the device.
+// Every mbarrier wait is bounded: on expiry the kernel raises an error word and traps instead of hanging the
+// device or publishing a wrong product.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -59,11 +59,14 @@ __device__ __forceinline__ bool gtc_mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: false (and *err raised) if the phase never completes
+// bounded wait: if the phase never completes the error word is raised and the kernel stops (carrying on would overwrite a
+// stage the MMAs still read, or read an incomplete accumulator: silently wrong commands)
 __device__ __forceinline__ bool gtc_mbar_wait(uint32_t bar, uint32_t parity, int* err) {
   for (uint32_t it = 0; it < GTC_WAIT_SPINS; ++it)
     if (gtc_mbar_try(bar, parity)) return true;
   if (err) atomicExch(err, 1);
+  __threadfence_system();
+  __trap();
   return false;
 }
 

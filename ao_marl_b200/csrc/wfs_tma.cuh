@@ -75,7 +75,10 @@ __device__ __forceinline__ bool wft_mbar_wait(uint32_t bar, uint32_t parity, int
         : "memory");
     if (ok) return true;
   }
+  // an expired wait would let the warp read a stage that was never filled: raise the error word and stop the kernel
   atomicExch(err, 2);
+  __threadfence_system();
+  __trap();
   return false;
 }
 
