@@ -665,7 +665,7 @@ static int extrude_once(aom_ctx* ctx, int l, int axis, int sign, cudaStream_t st
                          c.n_env, p.N, p.S + p.N, nullptr, 0, 0, 1, st, nullptr, 0, true);
     if (rc) return rc;
   }
-  extrude_scatter_kernel<<<(c.n_env + 7) / 8, 256, 0, st>>>(p);
+  extrude_scatter_kernel<<<c.n_env, EXTRUDE_SCATTER_THREADS, 0, st>>>(p);
   KCHECK();
   return AOM_OK;
 }

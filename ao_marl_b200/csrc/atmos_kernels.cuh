@@ -71,36 +71,51 @@ __global__ void __launch_bounds__(256) extrude_gather_kernel(ExtrudeParams p) {
   for (int k = p.S + N + threadIdx.x; k < p.ldz; k += blockDim.x) Z[k] = 0.f;
 }
 
-// grid: ceil(E / 8) blocks of 256 threads, one warp per environment (no block-wide barrier; 4096 one-environment
-// blocks with two barriers each were block-latency bound: 73 us per launch for 2.6 M stores).
-__global__ void __launch_bounds__(256) extrude_scatter_kernel(ExtrudeParams p) {
-  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (e >= p.E) return;
-  const int lane = threadIdx.x & 31;
+// grid: E blocks of EXTRUDE_SCATTER_THREADS threads, one block per environment, every thread holds its (up to 8) pixels
+// of the new column in registers before it stores them.  A row-direction extrusion (contiguous) takes 9 us per 4096
+// environments (15 us with one warp per environment and a load -> store loop).  A column-direction extrusion is 648
+// four-byte stores into 648 different DRAM rows per environment -- a read-modify-write of a sector each, 91 MB read +
+// 81 MB written for 10.6 MB of pixels -- and stays at 117 us however many stores are in flight (120 us before): it is
+// bound by DRAM row activations (profiles/r02_extrude_kernels_metrics.csv), the price of storing every layer [y][x].
+#define EXTRUDE_SCATTER_THREADS 128
+__global__ void __launch_bounds__(EXTRUDE_SCATTER_THREADS) extrude_scatter_kernel(ExtrudeParams p) {
+  const int e = blockIdx.x;
   const int N = p.N;
   float* scr = p.screen + (size_t)e * N * N;
   const int ox = p.ox[e], oy = p.oy[e];
   const float zr = p.zref ? p.zref[e] : 0.f;           // null: the GEMM already added the reference pixel
-  __syncwarp();                                              // every lane holds the old ring origin
   int nox = ox, noy = oy;
   if (p.axis == 0) nox = (p.sign > 0) ? wrapN(ox + 1, N) : (ox == 0 ? N - 1 : ox - 1);
   else             noy = (p.sign > 0) ? wrapN(oy + 1, N) : (oy == 0 ? N - 1 : oy - 1);
   const float* col = p.newcol + (size_t)e * p.ldn;
-  for (int j = lane; j < N; j += 32) {
-    const float v = col[j] + zr;
-    size_t addr;
-    if (p.axis == 0) {
-      const int pc = (p.sign > 0) ? ox : nox;                 // new logical column N-1 (or 0)
-      const int lr = (p.sign > 0) ? j : N - 1 - j;
-      addr = (size_t)wrapN(lr + oy, N) * N + pc;
-    } else {
-      const int pr = (p.sign > 0) ? oy : noy;                 // new logical row N-1 (or 0)
-      const int lc = (p.sign > 0) ? j : N - 1 - j;
-      addr = (size_t)pr * N + wrapN(lc + ox, N);
+  constexpr int PER = 8;                                    // pixels per thread and pass (N <= 1024 in one pass)
+  for (int j0 = threadIdx.x; j0 < N; j0 += PER * EXTRUDE_SCATTER_THREADS) {
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = j0 + i * EXTRUDE_SCATTER_THREADS;
+      v[i] = (j < N) ? col[j] + zr : 0.f;
     }
-    scr[addr] = v;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = j0 + i * EXTRUDE_SCATTER_THREADS;
+      if (j < N) {
+        size_t addr;
+        if (p.axis == 0) {
+          const int pc = (p.sign > 0) ? ox : nox;                 // new logical column N-1 (or 0)
+          const int lr = (p.sign > 0) ? j : N - 1 - j;
+          addr = (size_t)wrapN(lr + oy, N) * N + pc;
+        } else {
+          const int pr = (p.sign > 0) ? oy : noy;                 // new logical row N-1 (or 0)
+          const int lc = (p.sign > 0) ? j : N - 1 - j;
+          addr = (size_t)pr * N + wrapN(lc + ox, N);
+        }
+        scr[addr] = v[i];
+      }
+    }
   }
-  if (lane == 0) {
+  __syncthreads();                                            // every thread has read the old ring origin
+  if (threadIdx.x == 0) {
     p.ox[e] = nox;
     p.oy[e] = noy;
     p.count[e] += 1;
