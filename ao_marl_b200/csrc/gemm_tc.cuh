@@ -12,12 +12,13 @@
 // (hi.hi + hi.lo + lo.hi) accumulated in float32 in TMEM: ~2^-21 relative per product, so commands,
 // screens and rewards stay well inside the rel 1e-4 parity bar where a single TF32/BF16 pass does not.
 //
-// Structure (one 128 x 128 output tile per CTA, 160 threads, two CTAs per SM):
-//   warps 0-3  loaders: coalesced 128-bit global loads of the A and B slabs (16 k-values per stage),
+// Structure (one 128 x 128 output tile per CTA, 288 threads, two CTAs per SM):
+//   warps 0-7  loaders: coalesced 128-bit global loads of the A and B slabs (16 k-values per stage),
 //              hi/lo split in registers, st.shared into the canonical K-major no-swizzle UMMA layout
 //              (8-row x 16-byte core matrices), fence.proxy.async, mbarrier arrive.   Then the epilogue:
-//              tcgen05.ld of their 32 TMEM lanes, bias / relu / integrator, 128-bit stores.
-//   warp 4     TMEM allocation; one lane waits on the full barriers and issues the six tcgen05.mma of the
+//              tcgen05.ld of their 32 TMEM lanes (two warps per lane quarter, half of the columns each), bias / relu /
+//              integrator, 128-bit stores.  (Four loader warps -- the first version -- left the tensor pipe at 20-25 %.)
+//   warp 8     TMEM allocation; one lane waits on the full barriers and issues the six tcgen05.mma of the
 //              stage, tcgen05.commit releases the stage to the loaders and finally the accumulator.
 // Every mbarrier wait is bounded: on expiry the kernel raises an error word and traps instead of hanging the
 // device or publishing a wrong product.
@@ -37,7 +38,8 @@
 #define GTC_SMEM_BYTES_T(BN) (GTC_STAGES * GTC_STAGE_BYTES_T(BN) + 128)
 #define GTC_SMEM_BYTES GTC_SMEM_BYTES_T(GTC_BN)
 #define GTC_BN_WIDE 144                                       // 9 x 144 = 1296: the 1283 / 1286-wide operators in one wave
-#define GTC_THREADS 160
+#define GTC_LOADERS 8                                         // loader / epilogue warps (two per TMEM lane quarter)
+#define GTC_THREADS ((GTC_LOADERS + 1) * 32)
 #define GTC_WAIT_SPINS (1u << 20)
 
 __device__ __forceinline__ uint32_t gtc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,7 +129,9 @@ template <int EPI, int BN>
 __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, int* err) {
   constexpr int STAGE_BYTES = GTC_STAGE_BYTES_T(BN);
   constexpr int B_OFF = 2 * GTC_TILE_BYTES;                    // B hi at B_OFF, B lo at B_OFF + GTC_BTILE_BYTES(BN)
-  constexpr int B_ITERS = (BN + 31) / 32;
+  constexpr int ROWS_PER_PASS = GTC_LOADERS * 8;               // 64 rows of a slab per pass of the loaders
+  constexpr int A_ITERS = GTC_BM / ROWS_PER_PASS;
+  constexpr int B_ITERS = (BN + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
   constexpr uint32_t TMEM_COLS = BN <= 128 ? 128u : 256u;
   extern __shared__ __align__(1024) uint8_t gtc_smem[];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = tid & 31;
@@ -147,13 +151,13 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
 
   if (tid == 0) {
     for (int s = 0; s < GTC_STAGES; ++s) {
-      gtc_mbar_init(full0 + 8 * s, 4);        // one arrive per loader warp
+      gtc_mbar_init(full0 + 8 * s, GTC_LOADERS);   // one arrive per loader warp
       gtc_mbar_init(empty0 + 8 * s, 1);       // tcgen05.commit
     }
     gtc_mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == GTC_LOADERS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gtc_smem_u32(tmem_slot)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -163,41 +167,41 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp < 4) {
+  if (warp < GTC_LOADERS) {
     // ===== loaders =====
     // eight consecutive lanes take the same 16-byte chunk (4 k-values) of eight consecutive rows: their st.shared.v4 fill
     // one 128-byte core matrix without bank conflicts (with chunk = tid & 3 the four chunks of a row landed 128 B apart on
     // the same banks: 75 % of the shared-memory wavefronts were replays, profiles/r01_gemmtc_E4096_metrics.csv); the
     // global loads of a warp still cover whole 64-byte row segments
     const int c = (tid >> 3) & 3;
-    const int r0 = (tid >> 5) * 8 + (tid & 7);   // rows r0, r0 + 32, r0 + 64, r0 + 96
+    const int r0 = (tid >> 5) * 8 + (tid & 7);   // rows r0, r0 + 64 (eight loader warps: 64 rows per pass)
     // two slabs of global loads stay in flight (register sets 0 / 1): one slab alone left every stage waiting
     // for HBM/L2 latency longer than its three MMAs take
-    float4 va[GTC_INFLIGHT][4], vb[GTC_INFLIGHT][B_ITERS];
-    auto load_regs = [&](int kb, float4 (&xa)[4], float4 (&xb)[B_ITERS]) {
+    float4 va[GTC_INFLIGHT][A_ITERS], vb[GTC_INFLIGHT][B_ITERS];
+    auto load_regs = [&](int kb, float4 (&xa)[A_ITERS], float4 (&xb)[B_ITERS]) {
       const int k = kb * GTC_BK + c * 4;
       const bool kin = k < p.K;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ra = m0 + r0 + 32 * i;
+      for (int i = 0; i < A_ITERS; ++i) {
+        const int ra = m0 + r0 + ROWS_PER_PASS * i;
         xa[i] = (kin && ra < p.M) ? __ldg(reinterpret_cast<const float4*>(A + (long long)ra * p.lda + k))
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int i = 0; i < B_ITERS; ++i) {
-        const int r = r0 + 32 * i, rb = n0 + r;
+        const int r = r0 + ROWS_PER_PASS * i, rb = n0 + r;
         xb[i] = (kin && r < BN && rb < p.N) ? __ldg(reinterpret_cast<const float4*>(B + (long long)rb * p.ldb + k))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto stage_out = [&](int kb, float4 (&xa)[4], float4 (&xb)[B_ITERS]) {
+    auto stage_out = [&](int kb, float4 (&xa)[A_ITERS], float4 (&xb)[B_ITERS]) {
       const int s = kb % GTC_STAGES;
       const uint32_t round = (uint32_t)(kb / GTC_STAGES);
       gtc_mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u, err);
       uint8_t* st = tiles + (size_t)s * STAGE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r0 + 32 * i;
+      for (int i = 0; i < A_ITERS; ++i) {
+        const int r = r0 + ROWS_PER_PASS * i;
         const uint32_t off = (uint32_t)((r >> 3) * 512 + c * 128 + (r & 7) * 16);
         float4 hi, lo;
         gtc_split4(xa[i], hi, lo);
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
       }
 #pragma unroll
       for (int i = 0; i < B_ITERS; ++i) {
-        const int r = r0 + 32 * i;
+        const int r = r0 + ROWS_PER_PASS * i;
         if (r < BN) {
           const uint32_t off = (uint32_t)((r >> 3) * 512 + c * 128 + (r & 7) * 16);
           float4 hi, lo;
@@ -229,15 +233,19 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
         if (kb + j < nkb) stage_out(kb + j, va[j], vb[j]);
     }
 
-    // ===== epilogue: TMEM lanes 32 warp .. 32 warp + 31 are rows m0 + 32 warp + lane =====
+    // ===== epilogue: TMEM lanes 32 q .. 32 q + 31 (q = warp & 3) are rows m0 + 32 q + lane; the two warps of a lane
+    //       quarter take the lower / upper half of the column blocks =====
     gtc_mbar_wait(accum_bar, 0u, err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + warp * 32 + lane;
+    const int lq = warp & 3;
+    const int row = m0 + lq * 32 + lane;
+    constexpr int NCB = BN / 16, CB_SPLIT = (NCB + 1) / 2;
+    const int cb_lo = (warp < 4) ? 0 : CB_SPLIT, cb_hi = (warp < 4) ? CB_SPLIT : NCB;
     const float* bias = p.bias ? p.bias + (long long)bz * p.sBias : nullptr;
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 16; ++cb) {
+    for (int cb = cb_lo; cb < cb_hi; ++cb) {
       uint32_t v[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 16);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(cb * 16);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
           "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else if (gtc_elect()) {
-    // ===== MMA issuer (one elected lane of warp 4) =====
+    // ===== MMA issuer (one elected lane of the last warp) =====
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(GTC_BM >> 4) << 24);
     for (int kb = 0; kb < nkb; ++kb) {
@@ -300,7 +308,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
     gtc_commit(accum_bar);                                       // accumulator complete
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == GTC_LOADERS) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
