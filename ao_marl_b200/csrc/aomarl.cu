@@ -57,6 +57,9 @@ struct aom_ctx {
   uint8_t* oz_xs;
   int* oz_xev;
   size_t oz_xs_bytes;
+  // actor weights as pre-split TF32 hi / lo planes in the tile order of gemm_tc_kernel (W1, W2, WH), floats per agent
+  float* actor_bt[3];
+  size_t actor_bt_per[3];
   // sensor / rtc
   float *slopes_frame, *slopes, *err_v, *com, *com1, *volts, *com_before;
   float *bincube, *phase;
@@ -277,6 +280,7 @@ extern "C" void aom_destroy(aom_ctx* ctx) {
   for (int l = 0; l < AOM_MAX_LAYERS; ++l) { cudaFree(ctx->oz_ab[l]); cudaFree(ctx->oz_ea[l]); }
   for (int t = 0; t < AOM_T_COUNT; ++t) { cudaFree(ctx->ozop[t]); cudaFree(ctx->ozop_ea[t]); }
   cudaFree(ctx->oz_zs); cudaFree(ctx->oz_ev); cudaFree(ctx->oz_xs); cudaFree(ctx->oz_xev);
+  for (int i = 0; i < 3; ++i) cudaFree(ctx->actor_bt[i]);
 
   for (void* b : ctx->fast_dev) cudaFree(b);
   for (void* b : ctx->umma_dev) cudaFree(b);
@@ -377,6 +381,25 @@ extern "C" int aom_set_table(aom_ctx* ctx, int table, int index, const void* hos
     int rc = oz_upload_operator(ctx, (const float*)host, N, AOM_LD(K), K, &ctx->oz_ab[index], &ctx->oz_ea[index],
                                 &ctx->oz_kb[index], &ctx->oz_nt[index]);
     if (rc) return rc;
+  }
+  if (table == AOM_T_ACTOR_W1 || table == AOM_T_ACTOR_W2 || table == AOM_T_ACTOR_WH) {
+    // the same weights pre-split into TF32 hi / lo planes in the tile order of gemm_tc_kernel: the actor GEMMs then take
+    // their B operand by one bulk copy per stage instead of global loads + split + st.shared in the loader warps
+    const aom_config& c = ctx->cfg;
+    const int i = table == AOM_T_ACTOR_W1 ? 0 : table == AOM_T_ACTOR_W2 ? 1 : 2;
+    const int K = i == 0 ? c.actor_in : c.actor_hidden, ldb = AOM_LD(K);
+    const int rows = i == 2 ? 2 * c.actor_out : c.actor_hidden;
+    const int ldc = AOM_LD(rows);                                   // the output's leading dimension fixes the n tiles
+    const size_t per = gtc_pretile_floats(ldc, AOM_LD(K));
+    float* h = (float*)calloc(per * (size_t)c.n_agents, sizeof(float));
+    if (!h) return fail(ctx, AOM_ERR_INVALID, "out of host memory");
+    gtc_pretile_host((const float*)host, c.n_agents, (long long)rows * ldb, ldb, rows, ldc, AOM_LD(K), h);
+    cudaFree(ctx->actor_bt[i]); ctx->actor_bt[i] = nullptr;
+    cudaError_t e = cudaMalloc((void**)&ctx->actor_bt[i], per * c.n_agents * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->actor_bt[i], h, per * c.n_agents * sizeof(float), cudaMemcpyHostToDevice);
+    free(h);
+    if (e != cudaSuccess) return fail(ctx, AOM_ERR_CUDA, "pre-tiled actor weights: %s", cudaGetErrorString(e));
+    ctx->actor_bt_per[i] = per;
   }
   if (table == AOM_T_CMAT || table == AOM_T_V2M || table == AOM_T_M2V) {
     const aom_config& c = ctx->cfg;
@@ -537,7 +560,7 @@ extern "C" int aom_get_buffer(aom_ctx* ctx, int buffer, int index, void** dptr, 
 static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long sA, const float* B, int ldb,
                        long long sB, float* C, int ldc, long long sC, int M, int N, int K, const float* bias,
                        long long sBias, int relu, int batch, cudaStream_t st, float* com = nullptr, int ldcom = 0,
-                       bool exact = false) {
+                       bool exact = false, const float* Bt = nullptr, long long sBt = 0) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int Kp = AOM_LD(K);
@@ -547,13 +570,14 @@ static int launch_gemm(aom_ctx* ctx, int epi, const float* A, int lda, long long
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.M = M; p.N = N; p.K = Kp;
   p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias; p.relu = relu;
   p.com = com; p.ldcom = ldcom; p.gain = ctx->gain; p.closed = ctx->closed;
+  p.Bt = Bt; p.sBt = sBt;
   // `exact`: float32 FFMA accumulation with round-to-nearest (the recursive screen extrusion needs it: the
   // tensor core truncates its float32 accumulator, a ~1e-5 systematic shrink that an autoregression integrates)
   if (!exact && ctx->opt[AOM_OPT_GEMM_PATH] != AOM_GEMM_SIMT) {
     // column tile: the wide one when it saves CTA waves (two CTAs per SM)
     const long long slots = 2LL * ctx->num_sms, rows = (M + GTC_BM - 1) / GTC_BM;
     auto waves = [&](int bn) { return (double)((rows * ((ldc + bn - 1) / bn) * batch + slots - 1) / slots) * bn; };
-    if (waves(GTC_BN_WIDE) < waves(GTC_BN)) {
+    if (!Bt && waves(GTC_BN_WIDE) < waves(GTC_BN)) {
       dim3 grid((ldc + GTC_BN_WIDE - 1) / GTC_BN_WIDE, (unsigned)rows, batch);
       if (epi == 0) gemm_tc_kernel<0, GTC_BN_WIDE><<<grid, GTC_THREADS, GTC_SMEM_BYTES_T(GTC_BN_WIDE), st>>>(p, ctx->d_err);
       else gemm_tc_kernel<1, GTC_BN_WIDE><<<grid, GTC_THREADS, GTC_SMEM_BYTES_T(GTC_BN_WIDE), st>>>(p, ctx->d_err);
@@ -1663,15 +1687,18 @@ extern "C" int aom_actor_forward(aom_ctx* ctx, int eval_mode, void* stream) {
   KCHECK();
   int rc = launch_gemm(ctx, 0, ctx->aX, ctx->ld_ain, (long long)E * ctx->ld_ain, (const float*)ctx->tab[AOM_T_ACTOR_W1][0],
                        ctx->ld_ain, (long long)c.actor_hidden * ctx->ld_ain, ctx->aH1, ctx->ld_ah, (long long)E * ctx->ld_ah, E,
-                       c.actor_hidden, c.actor_in, (const float*)ctx->tab[AOM_T_ACTOR_B1][0], c.actor_hidden, 1, A, st);
+                       c.actor_hidden, c.actor_in, (const float*)ctx->tab[AOM_T_ACTOR_B1][0], c.actor_hidden, 1, A, st, nullptr, 0, false,
+                       ctx->actor_bt[0], (long long)ctx->actor_bt_per[0]);
   if (rc) return rc;
   rc = launch_gemm(ctx, 0, ctx->aH1, ctx->ld_ah, (long long)E * ctx->ld_ah, (const float*)ctx->tab[AOM_T_ACTOR_W2][0], ctx->ld_ah,
                    (long long)c.actor_hidden * ctx->ld_ah, ctx->aH2, ctx->ld_ah, (long long)E * ctx->ld_ah, E, c.actor_hidden,
-                   c.actor_hidden, (const float*)ctx->tab[AOM_T_ACTOR_B2][0], c.actor_hidden, 1, A, st);
+                   c.actor_hidden, (const float*)ctx->tab[AOM_T_ACTOR_B2][0], c.actor_hidden, 1, A, st, nullptr, 0, false,
+                   ctx->actor_bt[1], (long long)ctx->actor_bt_per[1]);
   if (rc) return rc;
   rc = launch_gemm(ctx, 0, ctx->aH2, ctx->ld_ah, (long long)E * ctx->ld_ah, (const float*)ctx->tab[AOM_T_ACTOR_WH][0], ctx->ld_ah,
                    (long long)2 * c.actor_out * ctx->ld_ah, ctx->aHO, ctx->ld_aho, (long long)E * ctx->ld_aho, E, 2 * c.actor_out,
-                   c.actor_hidden, (const float*)ctx->tab[AOM_T_ACTOR_BH][0], 2 * c.actor_out, 0, A, st);
+                   c.actor_hidden, (const float*)ctx->tab[AOM_T_ACTOR_BH][0], 2 * c.actor_out, 0, A, st, nullptr, 0, false,
+                   ctx->actor_bt[2], (long long)ctx->actor_bt_per[2]);
   if (rc) return rc;
   actor_sample_kernel<<<E, 256, 0, st>>>(ctx->aHO, ctx->ld_aho, c.actor_out, (const int*)ctx->tab[AOM_T_AGENT_ACT][0], E, A,
                                          c.log_sig_min, c.log_sig_max, c.pol_act_scale, c.pol_act_bias, eval_mode, ctx->step,

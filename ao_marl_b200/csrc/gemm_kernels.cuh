@@ -24,6 +24,9 @@ struct GemmParams {
   int relu;
   // epilogue 1 (integrator): err = -acc ; C = err ; com += gain * err
   float* com; int ldcom; float gain; int closed;
+  // gemm_tc_kernel only: the B operand already split into TF32 hi / lo planes in the UMMA tile order of 128-column tiles
+  // ([n tile][k block][hi, lo][128 x 16]; gtc_pretile_host), brought in by one bulk copy per stage.  Null: B is split on the fly.
+  const float* Bt; long long sBt;
 };
 
 template <int EPI>

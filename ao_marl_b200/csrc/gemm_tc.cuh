@@ -142,6 +142,9 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
   const int m0 = blockIdx.y * GTC_BM;
   const int n0 = blockIdx.x * BN;
   const int nkb = (p.K + GTC_BK - 1) / GTC_BK;
+  // pre-tiled B (static weights, 128-column tiles only): [n tile][k block][hi, lo][BN x 16 floats]
+  const bool pre = (BN == GTC_BN) && p.Bt != nullptr;
+  const float* __restrict__ Bt = pre ? p.Bt + (long long)bz * p.sBt + (size_t)blockIdx.x * nkb * (2 * BN * GTC_BK) : nullptr;
 
   uint8_t* tiles = gtc_smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(gtc_smem + GTC_STAGES * STAGE_BYTES);
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
 
   if (tid == 0) {
     for (int s = 0; s < GTC_STAGES; ++s) {
-      gtc_mbar_init(full0 + 8 * s, GTC_LOADERS);   // one arrive per loader warp
+      gtc_mbar_init(full0 + 8 * s, GTC_LOADERS + (pre ? 1 : 0));   // one arrive per loader warp (+ the bulk copy's expect_tx)
       gtc_mbar_init(empty0 + 8 * s, 1);       // tcgen05.commit
     }
     gtc_mbar_init(accum_bar, 1);
@@ -187,11 +190,13 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
         xa[i] = (kin && ra < p.M) ? __ldg(reinterpret_cast<const float4*>(A + (long long)ra * p.lda + k))
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (!pre) {
 #pragma unroll
-      for (int i = 0; i < B_ITERS; ++i) {
-        const int r = r0 + ROWS_PER_PASS * i, rb = n0 + r;
-        xb[i] = (kin && r < BN && rb < p.N) ? __ldg(reinterpret_cast<const float4*>(B + (long long)rb * p.ldb + k))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < B_ITERS; ++i) {
+          const int r = r0 + ROWS_PER_PASS * i, rb = n0 + r;
+          xb[i] = (kin && r < BN && rb < p.N) ? __ldg(reinterpret_cast<const float4*>(B + (long long)rb * p.ldb + k))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     auto stage_out = [&](int kb, float4 (&xa)[A_ITERS], float4 (&xb)[B_ITERS]) {
@@ -208,15 +213,25 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + GTC_TILE_BYTES + off) = lo;
       }
+      if (pre) {
+        // the stage's B planes (hi then lo, contiguous in the pre-tiled table) by one bulk copy, off the L1 / LSU path
+        if (tid == 0) {
+          const uint32_t bar = full0 + 8 * s, bytes = 2u * GTC_BTILE_BYTES(BN);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(gtc_smem_u32(st + B_OFF)), "l"(Bt + (size_t)kb * (2 * BN * GTC_BK)), "r"(bytes), "r"(bar) : "memory");
+        }
+      } else {
 #pragma unroll
-      for (int i = 0; i < B_ITERS; ++i) {
-        const int r = r0 + ROWS_PER_PASS * i;
-        if (r < BN) {
-          const uint32_t off = (uint32_t)((r >> 3) * 512 + c * 128 + (r & 7) * 16);
-          float4 hi, lo;
-          gtc_split4(xb[i], hi, lo);
-          *reinterpret_cast<float4*>(st + B_OFF + off) = hi;
-          *reinterpret_cast<float4*>(st + B_OFF + GTC_BTILE_BYTES(BN) + off) = lo;
+        for (int i = 0; i < B_ITERS; ++i) {
+          const int r = r0 + ROWS_PER_PASS * i;
+          if (r < BN) {
+            const uint32_t off = (uint32_t)((r >> 3) * 512 + c * 128 + (r & 7) * 16);
+            float4 hi, lo;
+            gtc_split4(xb[i], hi, lo);
+            *reinterpret_cast<float4*>(st + B_OFF + off) = hi;
+            *reinterpret_cast<float4*>(st + B_OFF + GTC_BTILE_BYTES(BN) + off) = lo;
+          }
         }
       }
       if (kb + GTC_INFLIGHT < nkb) load_regs(kb + GTC_INFLIGHT, xa, xb);   // refill this register set GTC_INFLIGHT slabs ahead
@@ -313,3 +328,35 @@ __global__ void __launch_bounds__(GTC_THREADS, 2) gemm_tc_kernel(GemmParams p, i
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
+
+// Host: TF32 hi / lo planes of a K-major operator [batch][rows][ldb] (K valid columns) in the tile order gemm_tc_kernel
+// reads with one bulk copy per stage: [batch][n tile of 128][k block of 16][hi, lo][128 x 16 floats, 8-row x 16-byte core
+// matrices].  Rows beyond `rows` and columns beyond K are zero.  Returns the number of floats per batch element.
+static inline size_t gtc_pretile_floats(int n_cols_ld, int K) {
+  const size_t NT = (size_t)(n_cols_ld + GTC_BN - 1) / GTC_BN, nkb = (size_t)(K + GTC_BK - 1) / GTC_BK;
+  return NT * nkb * 2 * GTC_BN * GTC_BK;
+}
+static inline void gtc_pretile_host(const float* W, int batch, long long sB, int ldb, int rows, int n_cols_ld, int K, float* out) {
+  const int NT = (n_cols_ld + GTC_BN - 1) / GTC_BN, nkb = (K + GTC_BK - 1) / GTC_BK;
+  const size_t per = gtc_pretile_floats(n_cols_ld, K);
+  for (int b = 0; b < batch; ++b)
+    for (int nt = 0; nt < NT; ++nt)
+      for (int kb = 0; kb < nkb; ++kb) {
+        float* hi = out + (size_t)b * per + ((size_t)(nt * nkb + kb) * 2) * (GTC_BN * GTC_BK);
+        float* lo = hi + GTC_BN * GTC_BK;
+        for (int r = 0; r < GTC_BN; ++r)
+          for (int kk = 0; kk < GTC_BK; ++kk) {
+            const int row = nt * GTC_BN + r, k = kb * GTC_BK + kk;
+            const float x = (row < rows && k < K) ? W[(size_t)b * sB + (size_t)row * ldb + k] : 0.f;
+            uint32_t u;
+            memcpy(&u, &x, 4);
+            u &= 0xFFFFE000u;
+            float h;
+            memcpy(&h, &u, 4);
+            const size_t off = (size_t)((r >> 3) * 512 + (kk >> 2) * 128 + (r & 7) * 16 + (kk & 3) * 4) / 4;
+            hi[off] = h;
+            lo[off] = x - h;
+          }
+      }
+}
+
