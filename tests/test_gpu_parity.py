@@ -219,6 +219,33 @@ def test_wfs_staged_kernel_over_the_seam(sim10, static10, torch):
         sim10.set_wfs_path(sim10.DEFAULT_WFS_PATH)
 
 
+def test_specialised_warps_on_ragged_batches(static10, torch):
+    """wfs_frame_ws_kernel (the default) against the fused tcgen05 kernel, bit for bit, for batch sizes whose last CTA
+    holds a number of work items that is not a multiple of the eight subapertures of a tensor-core tile, and for a
+    single environment."""
+    from ao_marl_b200.lib import Simulator
+    r = np.random.default_rng(3)
+    for n_env in (1, 3, 5, 13):
+        sim = Simulator(static10, n_env, rl=None)
+        try:
+            sim.reset(np.arange(1, n_env + 1, dtype=np.int64))
+            sim.set_dm_volts(torch.as_tensor((r.standard_normal((n_env, static10.nactu)) * 0.3).astype(np.float32), device="cuda"))
+            for _ in range(3):
+                sim.move_atmos()
+            res = {}
+            for path in ("umma", "umma_ws"):
+                sim.set_wfs_path(path)
+                sim.comp_wfs_image(noise=-1.0)          # the same turbulence frame for both
+                sim.do_centroids()
+                res[path] = sim.rows("SLOPES", static10.nslopes).cpu().numpy().copy()
+            assert sim.wfs_kernel() == "wfs_frame_ws_kernel", sim.lib.aom_last_error(sim._ctx)
+            sim.check_device()
+            assert np.abs(res["umma"]).max() > 1e-3
+            assert np.array_equal(res["umma_ws"], res["umma"]), n_env
+        finally:
+            sim.close()
+
+
 def test_noisy_frame_counts(sim10, oracle_tab10, static10, torch):
     """Photon noise: the oracle's sampler applied to the GPU's noise-free image reproduces the GPU's
     noisy image exactly (same Philox stream, same integer Poisson draws) -- for every sensor-kernel generation,
