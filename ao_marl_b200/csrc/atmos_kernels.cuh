@@ -122,6 +122,33 @@ __global__ void __launch_bounds__(EXTRUDE_SCATTER_THREADS) extrude_scatter_kerne
   }
 }
 
+// In-place transpose of E square screens [N][N].  grid (T (T + 1) / 2, E) with T = ceil(N / 32): every block swaps one pair
+// of 32 x 32 tiles (bi <= bj) through shared memory; block (32, 8).  Used by aom_reset, which runs its 2N start-up
+// extrusions along the contiguous axis of a transposed screen (see there).
+__global__ void __launch_bounds__(256) transpose_screens_kernel(float* __restrict__ screens, int N) {
+  __shared__ float ta[32][33], tb[32][33];
+  const int T = (N + 31) / 32;
+  // tile pair index -> (bi, bj), bi <= bj
+  int t = blockIdx.x, bi = 0;
+  while (t >= T - bi) { t -= T - bi; ++bi; }
+  const int bj = bi + t;
+  float* scr = screens + (size_t)blockIdx.y * N * N;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += 8) {
+    const int ya = bi * 32 + r, xa = bj * 32 + tx;            // tile A = (rows of bi, columns of bj)
+    ta[r][tx] = (ya < N && xa < N) ? scr[(size_t)ya * N + xa] : 0.f;
+    const int yb = bj * 32 + r, xb = bi * 32 + tx;            // tile B = (rows of bj, columns of bi)
+    tb[r][tx] = (yb < N && xb < N) ? scr[(size_t)yb * N + xb] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ya = bi * 32 + r, xa = bj * 32 + tx;
+    if (ya < N && xa < N) scr[(size_t)ya * N + xa] = tb[tx][r];   // A <- B^T
+    const int yb = bj * 32 + r, xb = bi * 32 + tx;
+    if (bi != bj && yb < N && xb < N) scr[(size_t)yb * N + xb] = ta[tx][r];   // B <- A^T
+  }
+}
+
 // grid-stride fill helpers
 __global__ void fill_i32_kernel(int* p, int v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
