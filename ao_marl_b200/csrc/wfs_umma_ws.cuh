@@ -5,13 +5,12 @@
 // pipe (profiles/r02_wfs_umma_v5: 16 warps per SM -- the register file holds no more at 128 registers -- each issuing once
 // every ~8 cycles; removing 13 % of its instructions bought 2 %).  Here a CTA has 12 warps:
 //
-//   warps 0-7   field warps: F phase of one subaperture each, A1
-//               operand, arrival on a count-8 mbarrier; the last one to arrive issues MMA 1 into one of TWO stage-1
-//               accumulators (TMEM columns 0..63 / 64..127), so the field of group i+1 never waits for the read-out of i;
-//   warps 8-11  transform warps: TMEM lane quarter q = warp - 8 holds
-//               rows (s, y) of subapertures 2q, 2q+1 of the stage-1 result -- converted to the MN-major A2 operand -- and
-//               the fx rows of subapertures q and 4 + q of the stage-2 result: |.|^2, binning, noise, centre of gravity.
-//               The last of the four to arrive issues MMA 2.
+//   warps 0-7   field warps: F phase of one subaperture each, A1 operand, arrival on a count-8 mbarrier; the last one to
+//               arrive issues MMA 1 into one of TWO stage-1 accumulators (TMEM columns 0..63 / 64..127), so the field of
+//               group i+1 never waits for the read-out of group i;
+//   warps 8-11  transform warps: TMEM lane quarter q = warp - 8 holds rows (s, y) of subapertures 2q, 2q+1 of the stage-1
+//               result -- converted to the MN-major A2 operand -- and the fx rows of subapertures q and 4 + q of the
+//               stage-2 result: |.|^2, binning, centre of gravity.  The last of the four to arrive issues MMA 2.
 //
 // 24 warps per SM instead of 16 with the same shared memory and tensor memory, and the two halves of the work overlap
 // instead of alternating.  Each role alone needs fewer registers than the fused loop did: the whole kernel fits the 80
@@ -21,9 +20,7 @@
 #include "wfs_umma.cuh"
 
 #define WS_THREADS 384
-#ifndef WS_MIN_BLOCKS
-#define WS_MIN_BLOCKS 2
-#endif
+#define WS_MIN_BLOCKS 2                    // two CTAs per SM: 80 registers per thread
 
 template <int NL, int FULL>
 __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel(const __grid_constant__ WfsUmmaParams P) {
@@ -89,11 +86,7 @@ __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel
   const int n_cta = (int)(end - base);                          // > 0 by construction of the grid
   const int n_iter = (n_cta + WU_WARPS - 1) / WU_WARPS;         // groups of 8 work items
 
-#ifdef WS_SKIP_F
-  if (false) {
-#else
   if (warp < WU_WARPS) {
-#endif
     // =============================== field warps ===============================
     unsigned char* my_tiles = s_tiles + (size_t)warp * NLS * WU_TILE_STRIDE;
     const uint32_t my_tiles_u32 = wu_smem_u32(my_tiles);
@@ -413,11 +406,7 @@ __global__ void __launch_bounds__(WS_THREADS, WS_MIN_BLOCKS) wfs_frame_ws_kernel
       __syncwarp();
       xy_cur = xy_next;
     }
-#ifdef WS_SKIP_CE
-  } else if (false) {
-#else
   } else {
-#endif
     // =============================== transform warps ===============================
     const int q = warp - WU_WARPS;                                 // TMEM lane quarter
     // conversion: rows 32 q .. of the stage-1 result = subapertures 2 q + h; A2 tile q >> 1, rows m = 32 s' + fx with
