@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../ao_marl_b200/csrc/rng.cuh"
 #include "../../ao_marl_b200/csrc/fft16.cuh"
+#include "../../ao_marl_b200/csrc/gemm_tc_host.h"
 
 extern "C" {
 
@@ -75,5 +76,11 @@ void h_spot(int R, const float* inr, const float* ini, float* inten) {
         inten[(R * q + b) * W + c] = outr[4 + q] * outr[4 + q] + outi[4 + q] * outi[4 + q];
       }
     }
+}
+
+// pre-split TF32 planes of the actor weights in the tile order of gemm_tc_kernel (gemm_tc_host.h)
+long long h_pretile_floats(int n_cols_ld, int K) { return (long long)gtc_pretile_floats(n_cols_ld, K); }
+void h_pretile(const float* W, int batch, long long sB, int ldb, int rows, int n_cols_ld, int K, float* out) {
+  gtc_pretile_host(W, batch, sB, ldb, rows, n_cols_ld, K, out);
 }
 }

@@ -196,3 +196,35 @@ def test_psf_peak_fit_known_answers():
     jj, ii = np.mgrid[0:32, 0:32]
     gimg = 0.7 * np.exp(-((jj - 10.3) ** 2 + (ii - 20.6) ** 2) / 8.0)
     assert abs(af.fit_peak(gimg) - 0.7) < 1e-12
+
+
+def test_pretiled_actor_weights_layout(harness):
+    """gtc_pretile_host (what aom_set_table runs on the actor weights): TF32 hi / lo planes in the UMMA K-major no-swizzle
+    tile order gemm_tc_kernel reads with one bulk copy per stage -- hi keeps the leading 11 significant bits, hi + lo is the
+    weight exactly, rows / columns beyond the operator are zero, and every element sits at
+    [n tile][k block][hi, lo][(r >> 3) * 128 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3)]."""
+    L = harness
+    L.h_pretile_floats.restype = ctypes.c_longlong
+    r = np.random.default_rng(5)
+    batch, rows, K = 3, 60, 272                       # the head layer of the 40x40 actors: 2 x 30 outputs, 256 + pad inputs
+    ldb, ldc = 272, 64
+    W = (r.standard_normal((batch, rows, ldb)) * r.choice([1e-3, 1.0, 50.0], (batch, rows, 1))).astype(np.float32)
+    W[:, :, 260:] = 0.0
+    per = L.h_pretile_floats(ldc, K)
+    NT, nkb = (ldc + 127) // 128, (K + 15) // 16
+    assert per == NT * nkb * 2 * 128 * 16
+    out = np.full(batch * per, np.nan, np.float32)
+    L.h_pretile(P(W), batch, ctypes.c_longlong(rows * ldb), ldb, rows, ldc, K, P(out))
+    out = out.reshape(batch, NT, nkb, 2, 128 * 16)
+    assert np.isfinite(out).all()
+    rr, kk = np.meshgrid(np.arange(128), np.arange(16), indexing="ij")
+    off = (rr >> 3) * 128 + (kk >> 2) * 32 + (rr & 7) * 4 + (kk & 3)
+    assert len(np.unique(off)) == 128 * 16
+    for b in range(batch):
+        for kb in range(nkb):
+            tile = np.zeros((128, 16), np.float32)
+            tile[:rows] = W[b, :, 16 * kb:16 * kb + 16]
+            hi = (tile.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+            assert np.array_equal(out[b, 0, kb, 0][off], hi)
+            assert np.array_equal(out[b, 0, kb, 1][off], tile - hi)
+            assert np.array_equal(out[b, 0, kb, 0][off] + out[b, 0, kb, 1][off], tile)
