@@ -233,6 +233,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) wfs_frame_tma_kernel(const __gr
       }
       n_seam = seam;
       n_d = dbits;
+      if (!seam) {
+        // the stage was read (or, on the seam path, written) through the generic proxy: order those accesses before the
+        // async-proxy writes of the new boxes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+      }
       if (!seam && lane == 0) {
         const uint32_t bar = my_bar_u32 + stage * 8;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(NL * WFT_TILE_BYTES) : "memory");
